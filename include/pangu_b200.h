@@ -1,0 +1,159 @@
+/*
+ * pangu_b200.h -- C ABI of libpangu_b200.so: the B200 (sm_100a) kernels behind the Pangu-Weather
+ * forward path of comdaze/pangu-pytorch-demo.
+ *
+ * The reference has NO foreign-function interface: its hot path is `PanguModel.forward`
+ * (models/pangu_model.py:61-104) over the nn.Modules of models/layers.py, executed by ATen.
+ * The drop-in boundary is therefore the Python class API (pangu-pytorch-demo_b200/models/), and
+ * THIS header is what those classes bind with ctypes -- each entry point cites the reference lines
+ * whose arithmetic it replaces.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch's allocator); `stream` is a
+ *     cudaStream_t passed as void*; no entry point synchronises the host or allocates memory;
+ *   - returns 0 on success, a negative pangu_status otherwise; pangu_last_error() gives the text
+ *     (thread-local);
+ *   - token tensors are row-major [N, C] with n = (z*H + h)*W + w (models/layers.py:116-119);
+ *   - dtype: 0 = fp32 (SIMT FFMA path, the <=1e-5 parity path), 1 = bf16 operands with fp32
+ *     accumulation (tcgen05/TMEM/TMA path);
+ *   - the window is fixed at (2, 6, 12) = 144 tokens, head_dim 32, pad 5 rows
+ *     (models/layers.py:168,178,338).
+ */
+#ifndef PANGU_B200_H_
+#define PANGU_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  PANGU_OK = 0,
+  PANGU_ERR_BAD_ARG = -1,
+  PANGU_ERR_CUDA = -2,
+  PANGU_ERR_UNSUPPORTED = -3
+} pangu_status;
+
+typedef enum { PANGU_F32 = 0, PANGU_BF16 = 1 } pangu_dtype;
+
+/* epilogue activation of pangu_linear */
+typedef enum { PANGU_ACT_NONE = 0, PANGU_ACT_GELU_ERF = 1 } pangu_act;
+
+/* Token grid of one stage: stage A = {8,181,360,192,6}, stage B = {8,91,180,384,12}. */
+typedef struct {
+  int32_t Z, H, W;   /* token grid (un-padded)                    */
+  int32_t C;         /* channels                                  */
+  int32_t heads;     /* C / 32                                    */
+} pangu_geom;
+
+const char* pangu_last_error(void);
+int pangu_abi_version(void);
+/* 1 if the library was built with tcgen05/TMA kernels for sm_100a (always, for this build). */
+int pangu_has_tcgen05(void);
+
+/* ------------------------------------------------------------------ index kernels (bit-exact) */
+
+/* win[l,t,k,:] = x[src(l,t,k),:] or 0 -- F.pad + torch.roll(-1,-3,-6) + window partition,
+ * models/layers.py:224-262.  x [Z*H*W, C] -> win [nLon, T, 144, C]. elem_bytes in {2,4}. */
+int pangu_window_partition(const void* x, void* win, const pangu_geom* g, int roll,
+                           int elem_bytes, void* stream);
+/* x[src(l,t,k),:] = win[l,t,k,:] for real tokens -- window reverse + roll back + crop,
+ * models/layers.py:269-293. */
+int pangu_window_reverse(const void* win, void* x, const pangu_geom* g, int roll,
+                         int elem_bytes, void* stream);
+/* idx[l,t,k] = source token of window element or -1 (int64 [nLon,T,144]); the map the two
+ * kernels above apply, exported for the bit-exact tests. */
+int pangu_window_source_index(int64_t* idx, const pangu_geom* g, int roll, void* stream);
+/* mask[t,i,j] = region(i) != region(j) ? -100 : 0, float32 [T,144,144] -- EarthSpecificBlock.gen_mask,
+ * models/layers.py:187-216 (identical for every longitude window). */
+int pangu_shift_mask(float* mask, const pangu_geom* g, void* stream);
+/* EarthAttention3D._construct_index, models/layers.py:371-411: int64 [144*144]. */
+int pangu_position_index(int64_t* idx, void* stream);
+
+/* ------------------------------------------------------------------ dense linears */
+
+/* out[M,N] = act(A[M,K] . W[N,K]^T + bias[N])      nn.Linear / Conv1d(k=1):
+ * models/layers.py:88,113 (embed), :312,315 (Mlp), :419,481 (attention), :522 (down),
+ * :542,566 (up), :591,608 (recover).
+ * dtype = PANGU_F32 : A, W, out fp32 (FFMA).  dtype = PANGU_BF16: A, W bf16, fp32 accumulate in
+ * TMEM (tcgen05.mma), out bf16 or fp32 per out_dtype.  bias fp32 or NULL.  lda/ldo in elements. */
+int pangu_linear(const void* A, int64_t lda, const void* W, const float* bias, void* out,
+                 int64_t ldo, int64_t M, int32_t K, int32_t N, int act, int dtype,
+                 int out_dtype, void* stream);
+
+/* x_out = residual + LayerNorm_C(y) * gamma + beta   (post-norm residual, models/layers.py:296-297;
+ * eps 1e-5).  y is fp32 or bf16 (y_dtype); residual/x_out fp32; x_out_bf16 optional shadow copy
+ * (operand of the next GEMM) or NULL.  residual may be NULL (plain LayerNorm). */
+int pangu_ln_residual(const void* y, int y_dtype, const float* gamma, const float* beta,
+                      const float* residual, float* x_out, void* x_out_bf16, int64_t M,
+                      int32_t C, float eps, void* stream);
+
+/* Fused bf16 linear + bias + LayerNorm + residual (N == C in {192,384}):
+ *   x_out = residual + LN(A . W^T + bias) * gamma + beta, plus bf16 shadow.
+ * attention.linear2 + norm1 + shortcut (models/layers.py:481,296) and Mlp.linear2 + norm2 +
+ * residual (:315,297). */
+int pangu_linear_ln_residual_bf16(const void* A, int64_t lda, const void* W, const float* bias,
+                                  const float* gamma, const float* beta, const float* residual,
+                                  float* x_out, void* x_out_bf16, int64_t M, int32_t K, int32_t C,
+                                  float eps, void* stream);
+
+/* ------------------------------------------------------------------ 3-D window attention */
+
+/* EarthAttention3D.forward between linear1 and linear2 (models/layers.py:422-478) with the block's
+ * pad/roll/partition/mask/reverse/crop folded into the addressing (models/layers.py:224-293):
+ *   qkv  [Z*H*W, 3C] : linear1 output in TOKEN order (channel = s*C + head*32 + d, :422-427);
+ *   qkv_bias [3C]    : linear1.bias -- the value of q/k/v on zero pad rows (:228-229,419);
+ *   earth_bias [T, heads, 144, 144] (fp32 or bf16 per bias_dtype), added to the scores (:450-453);
+ *   roll != 0        : shifted block: source (z+1,h+3,w+6) mod (Z,H+5,W), -100 shift mask (:237,457-464);
+ *   out  [Z*H*W, C]  : softmax(q*scale k^T + bias + mask) v, heads merged (:476-478), written at the
+ *                      un-rolled token position; pad rows dropped.
+ * dtype selects fp32 (SIMT) or bf16 (tensor cores) for qkv/out. */
+int pangu_window_attention(const void* qkv, const float* qkv_bias, const void* earth_bias,
+                           int bias_dtype, void* out, const pangu_geom* g, int roll, int dtype,
+                           void* stream);
+
+/* ------------------------------------------------------------------ layout / bandwidth kernels */
+
+/* PatchEmbedding_pretrain.forward up to the two convs (models/layers.py:56-112): normalise
+ * (surface :65; upper air with level-flipped stats :95-99), concat constants (:75,:101), zero-pad
+ * (:37,:49), patchify.  Writes the GEMM operands
+ *   patches_surface [181*360, 112]  feature = c*16 + ph*4 + pw
+ *   patches_upper   [7*181*360, 192] feature = c*32 + pz*16 + ph*4 + pw
+ * in out_dtype.  input [5,13,721,1440], input_surface [4,721,1440], maps [3,724,1440],
+ * const_h [13,721,1440], surface_mean/std [4], upper_mean/std [13,5] (as stored: index 12-level). */
+int pangu_patch_embed_gather(const float* input, const float* input_surface,
+                             const float* surface_mean, const float* surface_std,
+                             const float* upper_mean, const float* upper_std, const float* maps,
+                             const float* const_h, void* patches_surface, void* patches_upper,
+                             int out_dtype, void* stream);
+
+/* PatchRecovery_pretrain.forward after the two convs (models/layers.py:593-619): un-patchify + crop.
+ *   y_upper [7*181*360, 160] (ch = v*32+pz*16+ph*4+pw), y_surface [181*360, 64] (ch = v*16+ph*4+pw), fp32
+ *   -> output [5,13,721,1440], output_surface [4,721,1440] fp32. */
+int pangu_patch_recover_scatter(const float* y_upper, const float* y_surface, float* output,
+                                float* output_surface, void* stream);
+
+/* DownSample.forward before the linear (models/layers.py:501-519): pad H to even, 2x2 merge
+ * (feature = dh*2C + dw*C + c), LayerNorm(4C).  x fp32 [Z*H*W, C] -> out [Z*ceil(H/2)*(W/2), 4C]. */
+int pangu_downsample_merge_ln(const float* x, const float* gamma, const float* beta, void* out,
+                              int out_dtype, int32_t Z, int32_t H, int32_t W, int32_t C, float eps,
+                              void* stream);
+
+/* UpSample.forward between linear1 and linear2 (models/layers.py:546-563): pixel-shuffle
+ * (in-feature = dh*2C' + dw*C' + c), crop to H rows, LayerNorm(C').
+ * y [Z*H2*W2, 4C'] (y_dtype) -> out [Z*H*(2*W2), C'] (out_dtype). */
+int pangu_upsample_shuffle_ln(const void* y, int y_dtype, const float* gamma, const float* beta,
+                              void* out, int out_dtype, int32_t Z, int32_t H2, int32_t W2, int32_t H,
+                              int32_t Cout, float eps, void* stream);
+
+/* fp32 -> bf16 cast of n elements (operand staging for the bf16 path). */
+int pangu_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
+/* out[n, 0:C1] = a[n,:], out[n, C1:C1+C2] = b[n,:] as bf16 (skip concat, models/pangu_model.py:98). */
+int pangu_concat_cast_bf16(const float* a, const float* b, void* out, int64_t n, int32_t C1,
+                           int32_t C2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANGU_B200_H_ */

@@ -1,0 +1,99 @@
+// extern "C" entry points of libpangu_b200.so that dispatch between the fp32 SIMT path and the
+// bf16 tcgen05 path, plus error plumbing.  See include/pangu_b200.h for the contract.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace pangu {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+    return PANGU_ERR_CUDA;
+  }
+  return PANGU_OK;
+}
+
+// simt_fp32.cu
+int launch_sgemm(const float* A, long long lda, const float* W, const float* bias, float* out,
+                 long long ldo, long long M, int K, int N, int act, cudaStream_t st);
+int launch_ln_residual(const void* y, int y_dtype, const float* gamma, const float* beta,
+                       const float* residual, float* x_out, void* xb, long long M, int C, float eps,
+                       cudaStream_t st);
+int launch_window_attention_f32(const float* qkv, const float* qkv_bias, const float* earth_bias,
+                                float* out, const WinGeom& g, int roll, cudaStream_t st);
+// tc_gemm.cu
+int launch_tc_linear(const void* A, long long lda, const void* W, const float* bias, void* out,
+                     long long ldo, long long M, int K, int N, int act, int out_dtype, cudaStream_t st);
+int launch_tc_linear_ln(const void* A, long long lda, const void* W, const float* bias,
+                        const float* gamma, const float* beta, const float* residual, float* x_out,
+                        void* x_out_bf16, long long M, int K, int C, float eps, cudaStream_t st);
+// tc_attention.cu
+int launch_window_attention_bf16(const void* qkv, const float* qkv_bias, const void* earth_bias,
+                                 int bias_dtype, void* out, const WinGeom& g, int roll, cudaStream_t st);
+
+}  // namespace pangu
+
+using namespace pangu;
+
+extern "C" const char* pangu_last_error(void) { return g_err; }
+extern "C" int pangu_abi_version(void) { return 1; }
+extern "C" int pangu_has_tcgen05(void) { return 1; }
+
+extern "C" int pangu_linear(const void* A, int64_t lda, const void* W, const float* bias, void* out,
+                            int64_t ldo, int64_t M, int32_t K, int32_t N, int act, int dtype,
+                            int out_dtype, void* stream) {
+  if (!A || !W || !out || M < 0 || K <= 0 || N <= 0) { set_error("linear: bad argument"); return PANGU_ERR_BAD_ARG; }
+  if (act != PANGU_ACT_NONE && act != PANGU_ACT_GELU_ERF) { set_error("linear: unknown activation %d", act); return PANGU_ERR_BAD_ARG; }
+  if (dtype == PANGU_F32) {
+    if (out_dtype != PANGU_F32) { set_error("linear: fp32 path writes fp32"); return PANGU_ERR_UNSUPPORTED; }
+    return launch_sgemm((const float*)A, lda, (const float*)W, bias, (float*)out, ldo, M, K, N, act, as_stream(stream));
+  }
+  if (dtype == PANGU_BF16)
+    return launch_tc_linear(A, lda, W, bias, out, ldo, M, K, N, act, out_dtype, as_stream(stream));
+  set_error("linear: unknown dtype %d", dtype);
+  return PANGU_ERR_BAD_ARG;
+}
+
+extern "C" int pangu_ln_residual(const void* y, int y_dtype, const float* gamma, const float* beta,
+                                 const float* residual, float* x_out, void* x_out_bf16, int64_t M,
+                                 int32_t C, float eps, void* stream) {
+  if (!y || !gamma || !beta || (!x_out && !x_out_bf16) || M < 0) { set_error("ln_residual: bad argument"); return PANGU_ERR_BAD_ARG; }
+  if (y_dtype != PANGU_F32 && y_dtype != PANGU_BF16) { set_error("ln_residual: unknown dtype"); return PANGU_ERR_BAD_ARG; }
+  return launch_ln_residual(y, y_dtype, gamma, beta, residual, x_out, x_out_bf16, M, C, eps, as_stream(stream));
+}
+
+extern "C" int pangu_linear_ln_residual_bf16(const void* A, int64_t lda, const void* W, const float* bias,
+                                             const float* gamma, const float* beta, const float* residual,
+                                             float* x_out, void* x_out_bf16, int64_t M, int32_t K,
+                                             int32_t C, float eps, void* stream) {
+  if (!A || !W || !gamma || !beta || !x_out || M < 0 || K <= 0) { set_error("linear_ln_residual: bad argument"); return PANGU_ERR_BAD_ARG; }
+  return launch_tc_linear_ln(A, lda, W, bias, gamma, beta, residual, x_out, x_out_bf16, M, K, C, eps, as_stream(stream));
+}
+
+extern "C" int pangu_window_attention(const void* qkv, const float* qkv_bias, const void* earth_bias,
+                                      int bias_dtype, void* out, const pangu_geom* gg, int roll, int dtype,
+                                      void* stream) {
+  WinGeom g;
+  if (!make_geom(gg, g) || !qkv || !qkv_bias || !earth_bias || !out) { set_error("window_attention: bad argument"); return PANGU_ERR_BAD_ARG; }
+  if (g.C != g.heads * kHeadDim) { set_error("window_attention: C=%d must equal heads*32", g.C); return PANGU_ERR_BAD_ARG; }
+  if (dtype == PANGU_F32) {
+    if (bias_dtype != PANGU_F32) { set_error("window_attention: fp32 path needs an fp32 bias table"); return PANGU_ERR_UNSUPPORTED; }
+    return launch_window_attention_f32((const float*)qkv, qkv_bias, (const float*)earth_bias, (float*)out, g, roll, as_stream(stream));
+  }
+  if (dtype == PANGU_BF16)
+    return launch_window_attention_bf16(qkv, qkv_bias, earth_bias, bias_dtype, out, g, roll, as_stream(stream));
+  set_error("window_attention: unknown dtype %d", dtype);
+  return PANGU_ERR_BAD_ARG;
+}
