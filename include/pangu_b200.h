@@ -105,7 +105,9 @@ int pangu_linear_ln_residual_bf16(const void* A, int64_t lda, const void* W, con
  *   qkv  [Z*H*W, 3C] : linear1 output in TOKEN order (channel = s*C + head*32 + d, :422-427);
  *   qkv_bias [3C]    : linear1.bias -- the value of q/k/v on zero pad rows (:228-229,419);
  *   earth_bias [T, heads, 144, 144] (fp32 or bf16 per bias_dtype), added to the scores (:450-453);
- *   roll != 0        : shifted block: source (z+1,h+3,w+6) mod (Z,H+5,W), -100 shift mask (:237,457-464);
+ *   roll == 1        : shifted block: source (z+1,h+3,w+6) mod (Z,H+5,W), -100 shift mask (:237,457-464);
+ *   roll == 2        : qkv/out are already in window order [nLon*T*144, .] (identity map, no mask) --
+ *                      the stand-alone EarthAttention3D.forward(x_window, mask) call;
  *   out  [Z*H*W, C]  : softmax(q*scale k^T + bias + mask) v, heads merged (:476-478), written at the
  *                      un-rolled token position; pad rows dropped.
  * dtype selects fp32 (SIMT) or bf16 (tensor cores) for qkv/out. */

@@ -1,0 +1,71 @@
+"""Build libpangu_b200.so in-tree with nvcc for sm_100a (B200).
+
+    python pangu-pytorch-demo_b200/pangu_b200/build.py [--force]
+
+nvcc cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box with the
+gpurun snapshot.  No torch / pybind dependency: the library is plain C ABI (include/pangu_b200.h).
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libpangu_b200.so")
+STAMP = os.path.join(HERE, "build", "stamp.txt")
+SOURCES = ["abi.cu", "index_kernels.cu", "simt_fp32.cu", "layout_kernels.cu", "tc_gemm.cu", "tc_attention.cu",
+           "tc_mlp.cu"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
+
+
+def _sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def _digest():
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)) + [os.path.join(ROOT, "include", "pangu_b200.h")]:
+        p = f if os.path.isabs(f) else os.path.join(CSRC, f)
+        with open(p, "rb") as fh:
+            h.update(p.encode())
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    dig = _digest()
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs, procs = [], []
+    for src in _sources():
+        obj = os.path.join(HERE, "build", os.path.basename(src).replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-c", src, "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = []
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"==== {os.path.basename(src)}\n{out}")
+        failed |= p.returncode != 0
+    with open(os.path.join(HERE, "build", "nvcc.log"), "w") as fh:
+        fh.write("\n".join(log))
+    if failed or verbose:
+        sys.stderr.write("\n".join(log))
+    if failed:
+        raise RuntimeError("nvcc failed, see build/nvcc.log")
+    link = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    subprocess.check_call(link)
+    with open(STAMP, "w") as fh:
+        fh.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -37,11 +37,12 @@ inline bool make_geom(const pangu_geom* g, WinGeom& o) {
 // pad (layers.py:228) + roll by (-1,-3,-6) on the padded grid (:237) + partition (:253-262).
 __host__ __device__ __forceinline__ long long window_source(const WinGeom& g, int l, int t, int k,
                                                             int roll) {
+  if (roll == 2) return ((long long)l * g.T + t) * kWinTokens + k;   // pre-partitioned windows: identity
   const int zw = t / g.nH, hw = t - zw * g.nH;
   const int dz = k / 72, r = k - dz * 72;
   const int dh = r / 12, dw = r - dh * 12;
   int z = 2 * zw + dz, h = 6 * hw + dh, w = 12 * l + dw;
-  if (roll) {
+  if (roll == 1) {
     z += 1; if (z >= g.Z) z -= g.Z;
     h += 3; if (h >= g.Hp) h -= g.Hp;
     w += 6; if (w >= g.W) w -= g.W;

@@ -221,7 +221,7 @@ window_attention_f32_kernel(const float* __restrict__ qkv, const float* __restri
 #pragma unroll
         for (int d = 0; d < 32; ++d) a = fmaf(sq[i * 32 + d], sk[j * 33 + d], a);
         a += __ldg(brow + i * kWinTokens + j);
-        if (roll && sgid[j] != gi) a += kMaskValue;
+        if (roll == 1 && sgid[j] != gi) a += kMaskValue;
       }
       s[jj] = a;
       mx = fmaxf(mx, a);

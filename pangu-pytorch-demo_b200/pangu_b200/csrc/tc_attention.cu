@@ -1,0 +1,298 @@
+// bf16 3-D window attention with the Earth-specific bias (models/layers.py:422-478) and the block's
+// pad / roll / partition / shift-mask / reverse / crop (models/layers.py:224-293) folded into the
+// addressing.  One CTA owns ONE (window type t, head) bias tile -- staged once in shared memory --
+// and walks a chunk of longitude windows l, so the 144x144 bias tile is reused instead of re-read.
+//
+// Per (window, head): S = q k^T on tensor cores (bf16 mma, fp32 accumulate), online softmax in
+// registers over three 48-key blocks (exp2 with scale*log2e folded into one FMA), O = P v on tensor
+// cores, O staged through shared memory and written as 64-byte rows at the UN-rolled token position.
+//
+// Round-1 note: the two small GEMMs (7 % of the model's FLOPs) use warp-level mma.sync fragments so that
+// softmax stays register-resident; the tcgen05/TMEM formulation is the planned upgrade.
+#include "common.cuh"
+
+namespace pangu {
+namespace attn {
+
+constexpr int kWarps = 9;                         // 9 x 16 query rows = 144
+constexpr int kThreads = kWarps * 32;
+constexpr int kKvBlock = 48;                      // keys per online-softmax block (3 blocks)
+constexpr int kBiasPitch = 152;                   // bf16 elements per bias row in smem (304 B: conflict-free)
+constexpr int kTileBytes = kWinTokens * 64;       // one [144][32] bf16 operand tile, 64-byte rows, XOR-swizzled
+constexpr int kBufBytes = 3 * kTileBytes;         // q, k, v
+constexpr int kSmemBytes = kWinTokens * kBiasPitch * 2 + 2 * kBufBytes + kWinTokens * 4 /*rowbase*/ +
+                           kWinTokens * 4 /*dw*/ + kWinTokens /*gid*/ + 16;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// byte offset of 16-byte chunk c (0..3) of row r in a 64-byte-row tile; XOR swizzle keeps both the
+// cp.async fills and the ldmatrix reads (8 consecutive rows, same chunk) bank-conflict free.
+__device__ __forceinline__ int tile_off(int r, int c) { return r * 64 + ((c ^ ((r >> 1) & 3)) << 4); }
+
+template <typename TB>
+__global__ void __launch_bounds__(kThreads, 2)
+window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ qkv_bias,
+                             const TB* __restrict__ earth_bias, __nv_bfloat16* __restrict__ out, WinGeom g,
+                             int roll, int lon_chunk) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(smem);                       // [144][152]
+  uint8_t* s_buf = smem + kWinTokens * kBiasPitch * 2;                                  // 2 x {q,k,v}
+  int* s_rowbase = reinterpret_cast<int*>(s_buf + 2 * kBufBytes);                       // [144] (z*H+h)*W or -1
+  int* s_dw = s_rowbase + kWinTokens;                                                   // [144]
+  uint8_t* s_gid = reinterpret_cast<uint8_t*>(s_dw + kWinTokens);                       // [144]
+
+  const int head = blockIdx.x, lchunk = blockIdx.y, t = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = g.C;
+  const int l_begin = lchunk * lon_chunk;
+  const int l_end = min(g.nLon, l_begin + lon_chunk);
+
+  // ---- per-CTA tables: source row of every window element (independent of l) and mask group ids
+  for (int k = tid; k < kWinTokens; k += kThreads) {
+    const int zw = t / g.nH, hw = t - zw * g.nH;
+    const int dz = k / 72, r = k - dz * 72, dh = r / 12, dw = r - dh * 12;
+    int z = 2 * zw + dz, h = 6 * hw + dh;
+    if (roll == 1) { z += 1; if (z >= g.Z) z -= g.Z; h += 3; if (h >= g.Hp) h -= g.Hp; }
+    if (roll == 2) {                                        // pre-partitioned windows: identity map
+      s_rowbase[k] = t * kWinTokens + k;
+      s_dw[k] = 0;
+    } else {
+      s_rowbase[k] = h < g.H ? (z * g.H + h) * g.W : -1;
+      s_dw[k] = dw;
+    }
+    s_gid[k] = (uint8_t)shift_group(g, t, k);
+  }
+  // ---- bias tile of this (t, head) -> smem (bf16)
+  {
+    const TB* src = earth_bias + ((long long)t * g.heads + head) * kWinTokens * kWinTokens;
+    if (sizeof(TB) == 2) {
+      for (int i = tid; i < kWinTokens * 18; i += kThreads) {          // 18 chunks of 8 bf16 per row
+        const int r = i / 18, c = i - r * 18;
+        cp_async16(smem_u32(s_bias + r * kBiasPitch + c * 8), reinterpret_cast<const __nv_bfloat16*>(src) + r * kWinTokens + c * 8);
+      }
+    } else {
+      for (int i = tid; i < kWinTokens * 36; i += kThreads) {          // fp32 table: convert on the fly
+        const int r = i / 36, c = i - r * 36;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + r * kWinTokens + c * 4));
+        uint2 o = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+        *reinterpret_cast<uint2*>(s_bias + r * kBiasPitch + c * 4) = o;
+      }
+    }
+  }
+  __syncthreads();
+
+  // token of window element k in longitude window l (rb = s_rowbase[k] >= 0)
+  auto token_of = [&](int l, int k, int rb) -> long long {
+    if (roll == 2) return (long long)l * g.T * kWinTokens + rb;
+    int w = 12 * l + (roll == 1 ? 6 : 0) + s_dw[k];
+    if (w >= g.W) w -= g.W;
+    return (long long)rb + w;
+  };
+  // issue the gather of window l into buffer b: 144 tokens x {q,k,v} x 4 chunks of 16 B
+  auto issue_load = [&](int l, int b) {
+    uint8_t* buf = s_buf + b * kBufBytes;
+    for (int i = tid; i < kWinTokens * 12; i += kThreads) {
+      const int k = i / 12, part = i - k * 12, s = part >> 2, c = part & 3;
+      uint8_t* dst = buf + s * kTileBytes + tile_off(k, c);
+      const int rb = s_rowbase[k];
+      if (rb >= 0) {
+        const __nv_bfloat16* src = qkv + token_of(l, k, rb) * 3 * C + s * C + head * kHeadDim + c * 8;
+        cp_async16(smem_u32(dst), src);
+      } else {                                            // zero pad row: linear1(0) = bias (layers.py:228,419)
+        const float* bsrc = qkv_bias + s * C + head * kHeadDim + c * 8;
+        uint4 o;
+        o.x = pack_bf16(bsrc[0], bsrc[1]); o.y = pack_bf16(bsrc[2], bsrc[3]);
+        o.z = pack_bf16(bsrc[4], bsrc[5]); o.w = pack_bf16(bsrc[6], bsrc[7]);
+        *reinterpret_cast<uint4*>(dst) = o;
+      }
+    }
+  };
+
+  issue_load(l_begin, 0);
+  cp_async_commit();
+
+  const float sl2 = rsqrtf((float)kHeadDim) * kLog2e;      // scale * log2(e)
+  const float mask_l2 = kMaskValue * kLog2e;
+  const int gq = lane >> 2, tq = lane & 3;                 // fragment coordinates
+  const int row0 = warp * 16;
+  const int mi = lane >> 3, mr = lane & 7;                 // ldmatrix: matrix index / row within matrix
+  const bool masked_type = roll == 1 && ((t / g.nH == g.nZ - 1) || (t % g.nH == g.nH - 1));
+
+  for (int l = l_begin; l < l_end; ++l) {
+    const int b = (l - l_begin) & 1;
+    if (l + 1 < l_end) issue_load(l + 1, b ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    uint8_t* sq = s_buf + b * kBufBytes;
+    uint8_t* sk = sq + kTileBytes;
+    uint8_t* sv = sk + kTileBytes;
+
+    // Q fragments of this warp's 16 rows, two k-steps (d 0..15, 16..31)
+    uint32_t qa[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int r = row0 + (mi & 1) * 8 + mr, c = ks * 2 + (mi >> 1);
+      ldmatrix_x4(smem_u32(sq + tile_off(r, c)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+    }
+    const int gid_lo = s_gid[row0 + gq], gid_hi = s_gid[row0 + gq + 8];
+
+    float o_acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o_acc[i][j] = 0.f;
+    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+
+#pragma unroll 1
+    for (int kv0 = 0; kv0 < kWinTokens; kv0 += kKvBlock) {
+      float s_acc[6][4];
+#pragma unroll
+      for (int nt = 0; nt < 6; ++nt) {
+        s_acc[nt][0] = s_acc[nt][1] = s_acc[nt][2] = s_acc[nt][3] = 0.f;
+        uint32_t k0, k1, k2, k3;                            // b0,b1 of k-step 0 ; b0,b1 of k-step 1
+        ldmatrix_x4(smem_u32(sk + tile_off(kv0 + nt * 8 + mr, mi)), k0, k1, k2, k3);
+        mma_bf16(s_acc[nt], qa[0], k0, k1);
+        mma_bf16(s_acc[nt], qa[1], k2, k3);
+      }
+      // scores in log2 units: s*scale*log2e + bias*log2e (+ mask)
+      float mx_lo = m_lo, mx_hi = m_hi;
+#pragma unroll
+      for (int nt = 0; nt < 6; ++nt) {
+        const int j = kv0 + nt * 8 + 2 * tq;
+        const __nv_bfloat162 b_lo = *reinterpret_cast<const __nv_bfloat162*>(s_bias + (row0 + gq) * kBiasPitch + j);
+        const __nv_bfloat162 b_hi = *reinterpret_cast<const __nv_bfloat162*>(s_bias + (row0 + gq + 8) * kBiasPitch + j);
+        s_acc[nt][0] = fmaf(s_acc[nt][0], sl2, __low2float(b_lo) * kLog2e);
+        s_acc[nt][1] = fmaf(s_acc[nt][1], sl2, __high2float(b_lo) * kLog2e);
+        s_acc[nt][2] = fmaf(s_acc[nt][2], sl2, __low2float(b_hi) * kLog2e);
+        s_acc[nt][3] = fmaf(s_acc[nt][3], sl2, __high2float(b_hi) * kLog2e);
+        if (masked_type) {
+          const int g0 = s_gid[j], g1 = s_gid[j + 1];
+          if (g0 != gid_lo) s_acc[nt][0] += mask_l2;
+          if (g1 != gid_lo) s_acc[nt][1] += mask_l2;
+          if (g0 != gid_hi) s_acc[nt][2] += mask_l2;
+          if (g1 != gid_hi) s_acc[nt][3] += mask_l2;
+        }
+        mx_lo = fmaxf(mx_lo, fmaxf(s_acc[nt][0], s_acc[nt][1]));
+        mx_hi = fmaxf(mx_hi, fmaxf(s_acc[nt][2], s_acc[nt][3]));
+      }
+      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+      const float a_lo = ex2(m_lo - mx_lo), a_hi = ex2(m_hi - mx_hi);     // 0 on the first block (m = -inf)
+      m_lo = mx_lo; m_hi = mx_hi;
+      l_lo *= a_lo; l_hi *= a_hi;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        o_acc[nt][0] *= a_lo; o_acc[nt][1] *= a_lo; o_acc[nt][2] *= a_hi; o_acc[nt][3] *= a_hi;
+      }
+      uint32_t pa[3][4];                                    // P as A fragments, 3 k-steps of 16 keys
+#pragma unroll
+      for (int nt = 0; nt < 6; ++nt) {
+        const float p0 = ex2(s_acc[nt][0] - m_lo), p1 = ex2(s_acc[nt][1] - m_lo);
+        const float p2 = ex2(s_acc[nt][2] - m_hi), p3 = ex2(s_acc[nt][3] - m_hi);
+        l_lo += p0 + p1; l_hi += p2 + p3;
+        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
+      }
+      // O += P V : 3 k-steps x 4 d-tiles; V fragments via transposed ldmatrix
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk) {
+#pragma unroll
+        for (int dp = 0; dp < 2; ++dp) {
+          uint32_t v0, v1, v2, v3;                          // (b0,b1) of d-tile 2dp ; (b0,b1) of d-tile 2dp+1
+          const int r = kv0 + kk * 16 + (mi & 1) * 8 + mr, c = dp * 2 + (mi >> 1);
+          ldmatrix_x4_trans(smem_u32(sv + tile_off(r, c)), v0, v1, v2, v3);
+          mma_bf16(o_acc[dp * 2], pa[kk], v0, v1);
+          mma_bf16(o_acc[dp * 2 + 1], pa[kk], v2, v3);
+        }
+      }
+    }
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+    const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;
+
+    // stage O (bf16) into this warp's own, now dead, Q rows; then 64-byte coalesced row stores
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      // element (row, d = nt*8 + 2tq): chunk nt, byte 4*tq inside the chunk
+      *reinterpret_cast<uint32_t*>(sq + tile_off(row0 + gq, nt) + 4 * tq) = pack_bf16(o_acc[nt][0] * inv_lo, o_acc[nt][1] * inv_lo);
+      *reinterpret_cast<uint32_t*>(sq + tile_off(row0 + gq + 8, nt) + 4 * tq) = pack_bf16(o_acc[nt][2] * inv_hi, o_acc[nt][3] * inv_hi);
+    }
+    __syncwarp();
+    {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int idx = lane + i * 32, r = row0 + (idx >> 2), c = idx & 3;
+        const int rb = s_rowbase[r];
+        if (rb >= 0) {                                      // pad rows are cropped (layers.py:287-288)
+          const uint4 val = *reinterpret_cast<const uint4*>(sq + tile_off(r, c));
+          *reinterpret_cast<uint4*>(out + token_of(l, r, rb) * C + head * kHeadDim + c * 8) = val;
+        }
+      }
+    }
+    __syncthreads();                                        // buffer b may be refilled by the next prefetch
+  }
+  cp_async_wait<0>();
+}
+
+}  // namespace attn
+
+int launch_window_attention_bf16(const void* qkv, const float* qkv_bias, const void* earth_bias,
+                                 int bias_dtype, void* out, const WinGeom& g, int roll, cudaStream_t st) {
+  using namespace attn;
+  const int lon_chunk = g.nLon % 5 == 0 ? 5 : (g.nLon % 3 == 0 ? 3 : (g.nLon % 2 == 0 ? 2 : 1));
+  dim3 grid((unsigned)g.heads, (unsigned)((g.nLon + lon_chunk - 1) / lon_chunk), (unsigned)g.T);
+  cudaError_t e;
+  if (bias_dtype == PANGU_BF16) {
+    auto kern = window_attention_bf16_kernel<__nv_bfloat16>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { set_error("attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
+    kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, qkv_bias, (const __nv_bfloat16*)earth_bias,
+                                             (__nv_bfloat16*)out, g, roll, lon_chunk);
+  } else if (bias_dtype == PANGU_F32) {
+    auto kern = window_attention_bf16_kernel<float>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { set_error("attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
+    kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, qkv_bias, (const float*)earth_bias,
+                                             (__nv_bfloat16*)out, g, roll, lon_chunk);
+  } else {
+    set_error("attention_bf16: unknown bias dtype %d", bias_dtype);
+    return PANGU_ERR_BAD_ARG;
+  }
+  return check_launch("window_attention_bf16");
+}
+
+}  // namespace pangu

@@ -1,0 +1,189 @@
+"""Op sequences of the reference modules (models/layers.py) on the B200 kernels.
+
+Two numeric modes:
+  * "fp32": CUDA-core FFMA kernels end to end -- the parity path (rel-L2 <= 1e-5 vs the reference);
+  * "bf16": bf16 GEMM operands on tcgen05 tensor cores with fp32 accumulation; the residual stream,
+    LayerNorm statistics and softmax stay fp32 (a bf16 shadow copy of the stream feeds the next GEMM).
+
+All functions take plain [N, C] token tensors of ONE sample (the reference is only correct for
+batch 1; batches are looped by the modules).
+"""
+import os
+
+import torch
+
+from . import ops
+from .abi import ACT_GELU, ACT_NONE, ROLL_NONE, ROLL_SHIFT, WINDOWED, PanguError  # noqa: F401
+
+MODES = ("fp32", "bf16")
+
+
+def default_mode():
+    m = os.environ.get("PANGU_B200_COMPUTE", "bf16").lower()
+    if m not in MODES:
+        raise PanguError(f"PANGU_B200_COMPUTE={m!r}: expected one of {MODES}")
+    return m
+
+
+class WeightCache:
+    """bf16 copies of parameters, refreshed when the parameter is updated in place or replaced."""
+
+    def __init__(self):
+        self._c = {}
+
+    def bf16(self, key, p):
+        ent = self._c.get(key)
+        tag = (p.data_ptr(), p._version, p.device)
+        if ent is None or ent[0] != tag:
+            t = p.detach()
+            if t.dim() == 3:                       # Conv1d(k=1) weight [out, in, 1]
+                t = t[:, :, 0]
+            ent = (tag, t.contiguous().to(torch.bfloat16))
+            self._c[key] = ent
+        return ent[1]
+
+    def clear(self):
+        self._c.clear()
+
+
+def _w2d(p):
+    """Linear [out,in] or Conv1d(k=1) [out,in,1] weight as a contiguous fp32 matrix."""
+    t = p.detach()
+    if t.dim() == 3:
+        t = t[:, :, 0]
+    return t.contiguous()
+
+
+def _f(p):
+    return None if p is None else p.detach().contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+def block_forward(blk, x, Z, H, W, roll, mode, xb=None):
+    """EarthSpecificBlock.forward (models/layers.py:218-299), eval semantics.
+    x fp32 [N, C]; returns (x_out fp32, x_out_bf16 or None)."""
+    att, mlp = blk.attention, blk.linear
+    heads = att.head_number
+    rmode = ROLL_SHIFT if roll else ROLL_NONE
+    if mode == "fp32":
+        qkv = ops.linear(x, _w2d(att.linear1.weight), _f(att.linear1.bias))
+        o = ops.window_attention(qkv, _f(att.linear1.bias), _f(att.earth_specific_bias), Z, H, W, heads, rmode)
+        del qkv
+        y = ops.linear(o, _w2d(att.linear2.weight), _f(att.linear2.bias))
+        x1, _ = ops.ln_residual(y, _f(blk.norm1.weight), _f(blk.norm1.bias), residual=x, eps=blk.norm1.eps)
+        h = ops.linear(x1, _w2d(mlp.linear1.weight), _f(mlp.linear1.bias), act=ACT_GELU)
+        y = ops.linear(h, _w2d(mlp.linear2.weight), _f(mlp.linear2.bias))
+        del h
+        x2, _ = ops.ln_residual(y, _f(blk.norm2.weight), _f(blk.norm2.bias), residual=x1, eps=blk.norm2.eps)
+        return x2, None
+    wc = blk._wcache
+    if xb is None:
+        xb = ops.cast_bf16(x)
+    qkv = ops.linear(xb, wc.bf16("a1", att.linear1.weight), _f(att.linear1.bias))
+    o = ops.window_attention(qkv, _f(att.linear1.bias), wc.bf16("eb", att.earth_specific_bias), Z, H, W, heads, rmode)
+    del qkv
+    x1, x1b = ops.linear_ln_residual_bf16(o, wc.bf16("a2", att.linear2.weight), _f(att.linear2.bias),
+                                          _f(blk.norm1.weight), _f(blk.norm1.bias), x, eps=blk.norm1.eps)
+    del o
+    h = ops.linear(x1b, wc.bf16("m1", mlp.linear1.weight), _f(mlp.linear1.bias), act=ACT_GELU)
+    x2, x2b = ops.linear_ln_residual_bf16(h, wc.bf16("m2", mlp.linear2.weight), _f(mlp.linear2.bias),
+                                          _f(blk.norm2.weight), _f(blk.norm2.bias), x1, eps=blk.norm2.eps)
+    return x2, x2b
+
+
+def attention_windows_forward(att, xw, mask, mode):
+    """EarthAttention3D.forward (models/layers.py:413-484) on pre-partitioned windows
+    xw [nLon, T, 144, C]; mask [nLon, T, 144, 144] (identical across nLon, as gen_mask builds it) or None."""
+    nLon, T, L, C = xw.shape
+    heads = att.head_number
+    bias = att.earth_specific_bias.detach()[0]                       # [T, heads, 144, 144]
+    if mask is not None:
+        m0 = mask[0] if mask.dim() == 4 else mask
+        if mask.dim() == 4 and mask.shape[0] > 1 and not bool((mask == mask[0:1]).all()):
+            raise PanguError("EarthAttention3D: masks that differ between longitude windows are not supported")
+        bias = bias + m0.to(bias.dtype).unsqueeze(1)
+    bias = bias.contiguous()
+    # geometry that reproduces (nLon, T) for the windowed identity map: Z=2*nZ.. any (Z,H,W) with the
+    # same window counts works because mode WINDOWED ignores coordinates.
+    Zf, Hf, Wf = 2, 6 * T - 5, 12 * nLon
+    flat = xw.reshape(nLon * T * L, C)
+    if mode == "fp32":
+        qkv = ops.linear(flat.contiguous(), _w2d(att.linear1.weight), _f(att.linear1.bias))
+        o = ops.window_attention(qkv, _f(att.linear1.bias), bias, Zf, Hf, Wf, heads, WINDOWED)
+        y = ops.linear(o, _w2d(att.linear2.weight), _f(att.linear2.bias))
+    else:
+        wc = att._wcache
+        qkv = ops.linear(ops.cast_bf16(flat.contiguous()), wc.bf16("a1", att.linear1.weight), _f(att.linear1.bias))
+        o = ops.window_attention(qkv, _f(att.linear1.bias), bias.to(torch.bfloat16), Zf, Hf, Wf, heads, WINDOWED)
+        y = ops.linear(o, wc.bf16("a2", att.linear2.weight), _f(att.linear2.bias), out_dtype=torch.float32)
+    return y.reshape(nLon, T, L, C)
+
+
+def mlp_forward(mlp, x2d, mode):
+    """Mlp.forward (models/layers.py:311-317) on [M, C]."""
+    if mode == "fp32":
+        h = ops.linear(x2d, _w2d(mlp.linear1.weight), _f(mlp.linear1.bias), act=ACT_GELU)
+        return ops.linear(h, _w2d(mlp.linear2.weight), _f(mlp.linear2.bias))
+    wc = mlp._wcache
+    h = ops.linear(ops.cast_bf16(x2d), wc.bf16("m1", mlp.linear1.weight), _f(mlp.linear1.bias), act=ACT_GELU)
+    return ops.linear(h, wc.bf16("m2", mlp.linear2.weight), _f(mlp.linear2.bias), out_dtype=torch.float32)
+
+
+def patch_embed_forward(pe, inp, inp_s, statistics, maps, const_h, mode):
+    """PatchEmbedding_pretrain.forward (models/layers.py:53-120) for one sample -> ([N, dim] fp32, bf16|None)."""
+    dim = pe.conv.out_channels
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    ps, pu = ops.patch_embed_gather(inp, inp_s, statistics, maps, const_h, dt)
+    x = torch.empty((8 * 181 * 360, dim), dtype=torch.float32, device=inp.device)
+    ns = 181 * 360
+    if mode == "fp32":
+        ops.linear(ps, _w2d(pe.conv_surface.weight), _f(pe.conv_surface.bias), out=x[:ns])
+        ops.linear(pu, _w2d(pe.conv.weight), _f(pe.conv.bias), out=x[ns:])
+        return x, None
+    wc = pe._wcache
+    ops.linear(ps, wc.bf16("cs", pe.conv_surface.weight), _f(pe.conv_surface.bias), out=x[:ns])
+    ops.linear(pu, wc.bf16("c", pe.conv.weight), _f(pe.conv.bias), out=x[ns:])
+    return x, None
+
+
+def downsample_forward(ds, x, Z, H, W, mode):
+    """DownSample.forward (models/layers.py:497-524) -> ([N/4.., 2C] fp32, bf16|None)."""
+    if mode == "fp32":
+        m = ops.downsample_merge_ln(x, _f(ds.norm.weight), _f(ds.norm.bias), Z, H, W, torch.float32, ds.norm.eps)
+        return ops.linear(m, _w2d(ds.linear.weight), None), None
+    m = ops.downsample_merge_ln(x, _f(ds.norm.weight), _f(ds.norm.bias), Z, H, W, torch.bfloat16, ds.norm.eps)
+    y = ops.linear(m, ds._wcache.bf16("l", ds.linear.weight), None, out_dtype=torch.float32)
+    return y, None
+
+
+def upsample_forward(us, x, mode, xb=None, Z=8, H2=91, W2=180, H=181):
+    """UpSample.forward (models/layers.py:540-567; sizes hard-coded there)."""
+    if mode == "fp32":
+        y = ops.linear(x, _w2d(us.linear1.weight), None)
+        n = ops.upsample_shuffle_ln(y, _f(us.norm.weight), _f(us.norm.bias), Z, H2, W2, H, torch.float32, us.norm.eps)
+        return ops.linear(n, _w2d(us.linear2.weight), None), None
+    wc = us._wcache
+    if xb is None:
+        xb = ops.cast_bf16(x)
+    y = ops.linear(xb, wc.bf16("l1", us.linear1.weight), None)
+    n = ops.upsample_shuffle_ln(y, _f(us.norm.weight), _f(us.norm.bias), Z, H2, W2, H, torch.bfloat16, us.norm.eps)
+    return ops.linear(n, wc.bf16("l2", us.linear2.weight), None, out_dtype=torch.float32), None
+
+
+def patch_recover_forward(pr, x, Z, H, W, mode, skip=None):
+    """PatchRecovery_pretrain.forward (models/layers.py:582-621).  x [N, dim] fp32, or when `skip` is given
+    the pair (skip, x) whose channel concat (models/pangu_model.py:98) is the input."""
+    if (Z, H, W) != (8, 181, 360):
+        raise PanguError("PatchRecovery_pretrain is hard-wired to the (8,181,360) grid, like the reference")
+    ns = H * W
+    if mode == "fp32":
+        if skip is not None:
+            x = torch.cat((skip, x), dim=-1)
+        yu = ops.linear(x[ns:], _w2d(pr.conv.weight), _f(pr.conv.bias))
+        ys = ops.linear(x[:ns], _w2d(pr.conv_surface.weight), _f(pr.conv_surface.bias))
+        return ops.patch_recover_scatter(yu, ys)
+    xb = ops.concat_cast_bf16(skip, x) if skip is not None else ops.cast_bf16(x)
+    wc = pr._wcache
+    yu = ops.linear(xb[ns:], wc.bf16("c", pr.conv.weight), _f(pr.conv.bias), out_dtype=torch.float32)
+    ys = ops.linear(xb[:ns], wc.bf16("cs", pr.conv_surface.weight), _f(pr.conv_surface.bias), out_dtype=torch.float32)
+    return ops.patch_recover_scatter(yu, ys)

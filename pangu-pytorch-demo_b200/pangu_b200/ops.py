@@ -1,0 +1,207 @@
+"""torch.Tensor wrappers over the C ABI.  PyTorch is used for device memory and streams only."""
+import torch
+
+from . import abi
+from .abi import ACT_GELU, ACT_NONE, BF16, F32, Geom
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise abi.PanguError(f"{name} must be a CUDA tensor: the B200 path has no CPU fallback")
+    if not t.is_contiguous():
+        raise abi.PanguError(f"{name} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise abi.PanguError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def geom(Z, H, W, C, heads=None):
+    return Geom(Z, H, W, C, heads if heads is not None else C // 32)
+
+
+def window_counts(Z, H, W):
+    Hp = H + 5
+    if Z % 2 or Hp % 6 or W % 12:
+        raise abi.PanguError(f"grid ({Z},{H},{W}) is not tileable by (2,6,12) windows after padding H by 5")
+    return W // 12, (Z // 2) * (Hp // 6)
+
+
+# ------------------------------------------------------------------ index kernels
+def window_partition(x, Z, H, W, roll):
+    """x [Z*H*W, C] -> [nLon, T, 144, C]  (models/layers.py:224-262)."""
+    _chk(x, name="x")
+    C = x.shape[-1]
+    nLon, T = window_counts(Z, H, W)
+    out = torch.empty((nLon, T, 144, C), dtype=x.dtype, device=x.device)
+    g = geom(Z, H, W, C)
+    abi.check(abi.lib().pangu_window_partition(_ptr(x), _ptr(out), g, int(roll), x.element_size(), _stream()),
+              "pangu_window_partition")
+    return out
+
+
+def window_reverse(win, Z, H, W, roll):
+    """[nLon, T, 144, C] -> x [Z*H*W, C]  (models/layers.py:269-293)."""
+    _chk(win, name="win")
+    C = win.shape[-1]
+    out = torch.empty((Z * H * W, C), dtype=win.dtype, device=win.device)
+    g = geom(Z, H, W, C)
+    abi.check(abi.lib().pangu_window_reverse(_ptr(win), _ptr(out), g, int(roll), win.element_size(), _stream()),
+              "pangu_window_reverse")
+    return out
+
+
+def window_source_index(Z, H, W, roll, device):
+    nLon, T = window_counts(Z, H, W)
+    out = torch.empty((nLon, T, 144), dtype=torch.int64, device=device)
+    g = geom(Z, H, W, 32)
+    abi.check(abi.lib().pangu_window_source_index(_ptr(out), g, int(roll), _stream()), "pangu_window_source_index")
+    return out
+
+
+def shift_mask(Z, H, W, device):
+    nLon, T = window_counts(Z, H, W)
+    out = torch.empty((T, 144, 144), dtype=torch.float32, device=device)
+    g = geom(Z, H, W, 32)
+    abi.check(abi.lib().pangu_shift_mask(_ptr(out), g, _stream()), "pangu_shift_mask")
+    return out
+
+
+def position_index(device):
+    out = torch.empty((144 * 144,), dtype=torch.int64, device=device)
+    abi.check(abi.lib().pangu_position_index(_ptr(out), _stream()), "pangu_position_index")
+    return out
+
+
+# ------------------------------------------------------------------ dense
+def linear(a, w, bias=None, act=ACT_NONE, out_dtype=None, out=None):
+    """out = act(a @ w.T + bias); a [M,K], w [N,K] (fp32 both, or bf16 both)."""
+    _chk(a, name="a")
+    _chk(w, a.dtype, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    out_dtype = out_dtype or a.dtype
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    abi.check(abi.lib().pangu_linear(_ptr(a), K, _ptr(w), _ptr(bias), _ptr(out), N, M, K, N, act, _DT[a.dtype],
+                                     _DT[out.dtype], _stream()), "pangu_linear")
+    return out
+
+
+def ln_residual(y, gamma, beta, residual=None, want_f32=True, want_bf16=False, eps=1e-5):
+    """residual + LayerNorm(y)*gamma + beta -> (fp32 or None, bf16 or None)."""
+    _chk(y, name="y")
+    M, C = y.shape
+    x_out = torch.empty((M, C), dtype=torch.float32, device=y.device) if want_f32 else None
+    xb = torch.empty((M, C), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    if residual is not None:
+        _chk(residual, torch.float32, "residual")
+    abi.check(abi.lib().pangu_ln_residual(_ptr(y), _DT[y.dtype], _ptr(gamma), _ptr(beta), _ptr(residual), _ptr(x_out),
+                                          _ptr(xb), M, C, eps, _stream()), "pangu_ln_residual")
+    return x_out, xb
+
+
+def linear_ln_residual_bf16(a, w, bias, gamma, beta, residual, want_bf16=True, eps=1e-5):
+    """residual + LN(a @ w.T + bias)*gamma + beta with the LayerNorm fused in the GEMM epilogue."""
+    _chk(a, torch.bfloat16, "a")
+    _chk(w, torch.bfloat16, "w")
+    M, K = a.shape
+    C = w.shape[0]
+    x_out = torch.empty((M, C), dtype=torch.float32, device=a.device)
+    xb = torch.empty((M, C), dtype=torch.bfloat16, device=a.device) if want_bf16 else None
+    abi.check(abi.lib().pangu_linear_ln_residual_bf16(_ptr(a), K, _ptr(w), _ptr(bias), _ptr(gamma), _ptr(beta),
+                                                      _ptr(residual), _ptr(x_out), _ptr(xb), M, K, C, eps, _stream()),
+              "pangu_linear_ln_residual_bf16")
+    return x_out, xb
+
+
+def window_attention(qkv, qkv_bias, earth_bias, Z, H, W, heads, mode):
+    """qkv [N, 3C] (token order, or window order when mode == WINDOWED) -> [N, C]."""
+    _chk(qkv, name="qkv")
+    _chk(qkv_bias, torch.float32, "qkv_bias")
+    _chk(earth_bias, name="earth_bias")
+    N, C3 = qkv.shape
+    C = C3 // 3
+    out = torch.empty((N, C), dtype=qkv.dtype, device=qkv.device)
+    g = geom(Z, H, W, C, heads)
+    abi.check(abi.lib().pangu_window_attention(_ptr(qkv), _ptr(qkv_bias), _ptr(earth_bias), _DT[earth_bias.dtype],
+                                               _ptr(out), g, int(mode), _DT[qkv.dtype], _stream()),
+              "pangu_window_attention")
+    return out
+
+
+# ------------------------------------------------------------------ layout
+def patch_embed_gather(inp, inp_s, statistics, maps, const_h, out_dtype):
+    sm, ss, um, us = statistics
+    dev = inp.device
+    for t, n in ((inp, "input"), (inp_s, "input_surface"), (maps, "maps"), (const_h, "const_h")):
+        _chk(t, torch.float32, n)
+    sm, ss = sm.reshape(-1).contiguous().float(), ss.reshape(-1).contiguous().float()
+    um, us = um.reshape(13, 5).contiguous().float(), us.reshape(13, 5).contiguous().float()
+    ps = torch.empty((181 * 360, 112), dtype=out_dtype, device=dev)
+    pu = torch.empty((7 * 181 * 360, 192), dtype=out_dtype, device=dev)
+    abi.check(abi.lib().pangu_patch_embed_gather(_ptr(inp), _ptr(inp_s), _ptr(sm), _ptr(ss), _ptr(um), _ptr(us),
+                                                 _ptr(maps), _ptr(const_h), _ptr(ps), _ptr(pu), _DT[out_dtype],
+                                                 _stream()), "pangu_patch_embed_gather")
+    return ps, pu
+
+
+def patch_recover_scatter(y_upper, y_surface):
+    _chk(y_upper, torch.float32, "y_upper")
+    _chk(y_surface, torch.float32, "y_surface")
+    dev = y_upper.device
+    out = torch.empty((1, 5, 13, 721, 1440), dtype=torch.float32, device=dev)
+    out_s = torch.empty((1, 4, 721, 1440), dtype=torch.float32, device=dev)
+    abi.check(abi.lib().pangu_patch_recover_scatter(_ptr(y_upper), _ptr(y_surface), _ptr(out), _ptr(out_s), _stream()),
+              "pangu_patch_recover_scatter")
+    return out, out_s
+
+
+def downsample_merge_ln(x, gamma, beta, Z, H, W, out_dtype, eps=1e-5):
+    _chk(x, torch.float32, "x")
+    C = x.shape[-1]
+    rows = Z * ((H + 1) // 2) * (W // 2)
+    out = torch.empty((rows, 4 * C), dtype=out_dtype, device=x.device)
+    abi.check(abi.lib().pangu_downsample_merge_ln(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), _DT[out_dtype], Z, H, W,
+                                                  C, eps, _stream()), "pangu_downsample_merge_ln")
+    return out
+
+
+def upsample_shuffle_ln(y, gamma, beta, Z, H2, W2, H, out_dtype, eps=1e-5):
+    _chk(y, name="y")
+    Co = y.shape[-1] // 4
+    out = torch.empty((Z * H * 2 * W2, Co), dtype=out_dtype, device=y.device)
+    abi.check(abi.lib().pangu_upsample_shuffle_ln(_ptr(y), _DT[y.dtype], _ptr(gamma), _ptr(beta), _ptr(out),
+                                                  _DT[out_dtype], Z, H2, W2, H, Co, eps, _stream()),
+              "pangu_upsample_shuffle_ln")
+    return out
+
+
+def cast_bf16(x):
+    _chk(x, torch.float32, "x")
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    abi.check(abi.lib().pangu_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "pangu_cast_f32_bf16")
+    return out
+
+
+def concat_cast_bf16(a, b):
+    _chk(a, torch.float32, "a")
+    _chk(b, torch.float32, "b")
+    n, C1 = a.shape
+    C2 = b.shape[1]
+    out = torch.empty((n, C1 + C2), dtype=torch.bfloat16, device=a.device)
+    abi.check(abi.lib().pangu_concat_cast_bf16(_ptr(a), _ptr(b), _ptr(out), n, C1, C2, _stream()),
+              "pangu_concat_cast_bf16")
+    return out

@@ -1,0 +1,113 @@
+"""bf16 tensor-core path (tcgen05 GEMMs, tensor-core window attention) against the oracle / goldens.
+Tolerance: relative L2 <= 2e-2 for model-level outputs (north_star); unit tests are much tighter
+because they compare against the same computation on bf16-rounded operands."""
+import pytest
+import torch
+
+import pangu_oracle as orc
+from util_gpu import check_digest, load_params
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def L():
+    import models.layers as layers
+    return layers
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 64), (128, 192, 192), (1000, 192, 576), (333, 112, 192),
+                                   (4133, 384, 1152), (640, 768, 384), (257, 1536, 256), (129, 384, 160),
+                                   (300, 384, 64), (521, 192, 768)])
+def test_tc_linear(M, K, N):
+    from pangu_b200 import ops
+    g = torch.Generator().manual_seed(M + K + N)
+    a = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.05).bfloat16()
+    b = torch.randn(N, generator=g)
+    want = a.double() @ w.double().t() + b.double()
+    got = ops.linear(a.cuda(), w.cuda(), b.cuda(), out_dtype=torch.float32).cpu()
+    assert orc.rel_l2(got, want) <= 3e-5, "fp32-out GEMM on bf16 operands must be exact to fp32 accumulation"
+    got = ops.linear(a.cuda(), w.cuda(), b.cuda()).cpu()
+    assert got.dtype == torch.bfloat16 and orc.rel_l2(got, want) <= 3e-3
+
+
+def test_tc_linear_gelu():
+    from pangu_b200 import ops
+    from pangu_b200.abi import ACT_GELU
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(700, 192, generator=g).bfloat16()
+    w = (torch.randn(768, 192, generator=g) * 0.2).bfloat16()
+    b = torch.randn(768, generator=g)
+    want = torch.nn.functional.gelu(a.double() @ w.double().t() + b.double())
+    got = ops.linear(a.cuda(), w.cuda(), b.cuda(), act=ACT_GELU, out_dtype=torch.float32).cpu()
+    assert float((got.double() - want).abs().max()) <= 2e-3      # tanh-form GELU fit + MUFU.TANH
+    assert orc.rel_l2(got, want) <= 1e-3
+
+
+@pytest.mark.parametrize("C,K", [(192, 192), (192, 768), (384, 384), (384, 1536)])
+def test_tc_linear_ln_residual(C, K):
+    from pangu_b200 import ops
+    g = torch.Generator().manual_seed(C + K)
+    M = 777
+    a = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(C, K, generator=g) * 0.05).bfloat16()
+    b, gamma, beta = torch.randn(C, generator=g), torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    res = torch.randn(M, C, generator=g)
+    y = a.double() @ w.double().t() + b.double()
+    want = res.double() + torch.nn.functional.layer_norm(y, (C,), gamma.double(), beta.double(), 1e-5)
+    x, xb = ops.linear_ln_residual_bf16(a.cuda(), w.cuda(), b.cuda(), gamma.cuda(), beta.cuda(), res.cuda())
+    assert orc.rel_l2(x.cpu(), want) <= 3e-5
+    assert orc.rel_l2(xb.cpu(), want) <= 3e-3
+
+
+@pytest.mark.parametrize("Z,H,W,C,heads", [(8, 181, 24, 192, 6), (8, 91, 24, 384, 12)])
+@pytest.mark.parametrize("roll", [0, 1])
+def test_attention_bf16_vs_fp32_kernel(Z, H, W, C, heads, roll):
+    """Tensor-core attention against the fp32 SIMT kernel on the same bf16-rounded q/k/v."""
+    from pangu_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    T = (Z // 2) * ((H + 5) // 6)
+    qkv = torch.randn(Z * H * W, 3 * C, generator=g).bfloat16()
+    qb = torch.randn(3 * C, generator=g) * 0.1
+    eb = (torch.randn(T, heads, 144, 144, generator=g) * 0.5).bfloat16()
+    want = ops.window_attention(qkv.float().cuda(), qb.bfloat16().float().cuda(), eb.float().cuda(), Z, H, W, heads, roll)
+    got = ops.window_attention(qkv.cuda(), qb.cuda(), eb.cuda(), Z, H, W, heads, roll)
+    assert orc.rel_l2(got.float().cpu(), want.cpu()) <= 6e-3      # P and the output are rounded to bf16
+
+
+@pytest.mark.parametrize("tag,dim,heads,Z,H,W,pfx", [
+    ("blockA", 192, 6, 8, 181, 24, "layers.EarthSpecificLayer0.blocks.EarthSpecificBlock1."),
+    ("blockB", 384, 12, 8, 91, 24, "layers.EarthSpecificLayer1.blocks.EarthSpecificBlock3."),
+])
+def test_block_bf16(L, goldens, tag, dim, heads, Z, H, W, pfx):
+    params = orc.synth_params(seed=0, only_prefix=pfx)
+    blk = load_params(L.EarthSpecificBlock(dim, 0.0, heads, "cpu"), params, pfx)
+    L.set_compute_dtype(blk, "bf16")
+    g = torch.Generator().manual_seed(7)
+    if tag == "blockB":
+        torch.randn(1, 8 * 181 * 24, 192, generator=g)
+    x = torch.randn(1, Z * H * W, dim, generator=g)
+    for roll in (False, True):
+        with torch.no_grad():
+            y = blk(x.cuda(), Z, H, W, roll)
+        err = check_digest(goldens, f"{tag}.roll{int(roll)}", y, TOL)
+        print(f"{tag} roll={roll} bf16 rel-L2 {err:.2e}")
+
+
+def test_full_model_bf16_vs_reference_golden(goldens):
+    if "output.val" not in goldens:
+        pytest.skip("goldens were generated with --skip-full")
+    from models.pangu_model import PanguModel
+    params = orc.synth_params(seed=0)
+    model = PanguModel(device="cpu")
+    model.load_state_dict(params, strict=True)
+    model = model.cuda().eval().set_compute_dtype("bf16")
+    inp, inp_s, stats, maps, const_h = orc.synth_inputs(seed=1)
+    stats = tuple(s.cuda() for s in stats)
+    with torch.no_grad():
+        out, out_s = model(inp.cuda(), inp_s.cuda(), stats, maps.cuda(), const_h.cuda())
+    e1 = check_digest(goldens, "output", out, TOL)
+    e2 = check_digest(goldens, "output_surface", out_s, TOL)
+    print(f"bf16 full model rel-L2: output {e1:.2e} surface {e2:.2e}")
