@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the Pangu-Weather 24 h forecast step (PanguModel.forward, 721x1440, batch 1, bf16).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode replicas]
+
+A "step" is one full forward of the model over one synthetic ERA5-shaped sample (BASELINE.json
+configs[1]).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is defined.
+
+  value     steps/s with inputs resident in HBM, CUDA-event timed, max over ranks, whole job
+  e2e       the same through the public API (models.pangu_model.PanguModel.forward) starting from pinned
+            HOST buffers, H2D of the 287 MB inputs and D2H of the 287 MB outputs inside the timed region
+  roofline  the dominant kernel class (tcgen05 GEMM), FLOPs / CUDA-event time vs the measured bf16 peak
+  cpu_baseline  the oracle port (oracle/pangu_oracle.py) timed on the host cores on a bounded sample
+
+--impl reference times the reference algorithm's CPU implementation (the oracle port: the reference is a
+Python project that cannot travel to the GPU box) on all host cores.
+"""
+import argparse
+import json
+import os
+import statistics as pystats
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "pangu-pytorch-demo_b200")
+sys.path.insert(0, PKG)
+
+METRIC = "24h forecast steps/s at 721x1440 bf16"
+UNIT = "steps/s"
+FLOPS_TOTAL = 8.421e12            # algorithmic FLOPs of one forward
+FLOPS_ATTN_MLP = 8.132e12         # attention + MLP blocks
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi in the background, killed by exact PID)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": pystats.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on a bounded sample
+# --------------------------------------------------------------------------------------------
+def cpu_reference_step(orc, torch, params, shrink, cache):
+    """One bounded sample of the forward on the CPU: ONE stage-A block and ONE stage-B block (rolled: the
+    expensive variant with the mask) at 1/shrink of the longitude extent, extrapolated to 4 A + 12 B blocks
+    and the full width; the non-block ops (3.4 % of the FLOPs) are extrapolated by FLOP share.
+    Returns the extrapolated seconds of one full forward."""
+    Wa, Wb = 360 // shrink, 180 // shrink
+    Wa, Wb = max(12, Wa - Wa % 12), max(12, Wb - Wb % 12)
+    if "xa" not in cache:
+        g = torch.Generator().manual_seed(3)
+        cache["xa"] = torch.randn(1, 8 * 181 * Wa, 192, generator=g)
+        cache["xb"] = torch.randn(1, 8 * 91 * Wb, 384, generator=g)
+    pa = "layers.EarthSpecificLayer0.blocks.EarthSpecificBlock1."
+    pb = "layers.EarthSpecificLayer1.blocks.EarthSpecificBlock1."
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        orc.earth_block(cache["xa"], 8, 181, Wa, True, params, pa, 6)
+        t1 = time.perf_counter()
+        orc.earth_block(cache["xb"], 8, 91, Wb, True, params, pb, 12)
+        t2 = time.perf_counter()
+    ta, tb = (t1 - t0) * 360 / Wa, (t2 - t1) * 180 / Wb
+    blocks = 4 * ta + 12 * tb
+    return blocks * FLOPS_TOTAL / FLOPS_ATTN_MLP, {"block_A_s": ta, "block_B_s": tb, "W_A": Wa, "W_B": Wb}
+
+
+def run_cpu_reference(args, as_impl):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import pangu_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pa = "layers.EarthSpecificLayer0.blocks.EarthSpecificBlock1."
+    pb = "layers.EarthSpecificLayer1.blocks.EarthSpecificBlock1."
+    params = orc.synth_params(0, only_prefix=pa)
+    params.update(orc.synth_params(0, only_prefix=pb))
+    steps, warm = (args.steps, args.warmup) if as_impl else (2, 1)
+    # calibrate the sample size so that the whole run stays within ~150 s (as_impl) / ~25 s (baseline leg)
+    cache = {}
+    t0 = time.perf_counter()
+    est, _ = cpu_reference_step(orc, torch, params, 15, cache)
+    calib = time.perf_counter() - t0                       # seconds for 1/15 of the width
+    budget = (150.0 if as_impl else 25.0) / max(1, steps + warm)
+    shrink = 1
+    for s in (1, 2, 3, 5, 15):
+        shrink = s
+        if calib * 15 / s <= budget:
+            break
+    cache = {}
+    for _ in range(warm):
+        cpu_reference_step(orc, torch, params, shrink, cache)
+    times, detail = [], {}
+    for _ in range(steps):
+        sec, detail = cpu_reference_step(orc, torch, params, shrink, cache)
+        times.append(sec)
+    sec = sum(times) / len(times)
+    sample = (f"1 rolled stage-A block + 1 rolled stage-B block of the oracle at 1/{shrink} of the longitude extent "
+              f"(W={detail['W_A']}/{detail['W_B']}), extrapolated to 4 A + 12 B blocks x full width x "
+              f"{FLOPS_TOTAL / FLOPS_ATTN_MLP:.3f} (non-block FLOP share); torch {torch.__version__} CPU fp32, {cores} threads")
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            "seconds_per_forward": sec, "detail": detail, "steps": steps, "warmup": warm, "times": times}
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="replicas", choices=["replicas"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-times", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    config = {"workload": "PanguModel 24h forward full-res bf16, batch 1 per GPU (BASELINE.json configs[1])",
+              "grid": "13x721x1440 upper-air x5 + 721x1440 surface x4", "tokens": "521280@C192 + 131040@C384",
+              "blocks": 16, "params": 276659936, "parallelism": f"replicas x{world} (one forecast per GPU, no data-path collective)",
+              "cache": "inputs+activations per step (>= 6 GB) exceed the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = run_cpu_reference(args, as_impl=True)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * r["seconds_per_forward"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))       # synthetic weights/inputs only (seeded generators)
+    import pangu_oracle as orc
+    from models.pangu_model import PanguModel
+    from pangu_b200 import ops
+
+    model = PanguModel(device="cpu")
+    model.load_state_dict(orc.synth_params(seed=0), strict=True)
+    model = model.to(dev).eval().set_compute_dtype(args.dtype)
+    inp, inp_s, stats, maps, const_h = orc.synth_inputs(seed=1 + rank)
+    h_inp, h_inp_s = inp.pin_memory(), inp_s.pin_memory()
+    d_inp, d_inp_s = inp.to(dev), inp_s.to(dev)
+    stats = tuple(s.to(dev) for s in stats)
+    maps, const_h = maps.to(dev), const_h.to(dev)
+    h_out = torch.empty((1, 5, 13, 721, 1440), dtype=torch.float32).pin_memory()
+    h_out_s = torch.empty((1, 4, 721, 1440), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.no_grad():
+            return model(d_inp, d_inp_s, stats, maps, const_h)
+
+    def step_e2e():
+        with torch.no_grad():
+            a = h_inp.to(dev, non_blocking=True)
+            b = h_inp_s.to(dev, non_blocking=True)
+            o, os_ = model(a, b, stats, maps, const_h)
+            h_out.copy_(o, non_blocking=True)
+            h_out_s.copy_(os_, non_blocking=True)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.LAUNCHES = 0
+    total_ms = timed(step_resident, args.steps)
+    launches = ops.LAUNCHES
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * args.steps / (total_ms / 1000.0)
+
+    for _ in range(2):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+    e2e_value = world * args.steps / (e2e_ms / 1000.0)
+    h2d = (h_inp.numel() + h_inp_s.numel()) * 4
+    d2h = (h_out.numel() + h_out_s.numel()) * 4
+
+    kernels, roofline = None, None
+    peaks = load_peaks()
+    if not args.no_kernel_times:
+        ops.start_kernel_timing()
+        inst_ms = timed(step_resident, args.steps)
+        table = ops.stop_kernel_timing()               # {op-class: (calls, total_ms, flops, bytes)}
+        kernels = {k: {"calls_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
+                       "tflops": (v[2] / (v[1] / 1000.0) / 1e12) if v[1] > 0 and v[2] > 0 else None,
+                       "gbs": (v[3] / (v[1] / 1000.0) / 1e9) if v[1] > 0 and v[3] > 0 else None}
+                   for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])}
+        gemm = {k: v for k, v in table.items() if k.startswith("gemm")}
+        if gemm:
+            dom = max(gemm, key=lambda k: gemm[k][1])
+            calls, tms, fl, _ = gemm[dom]
+            ach = fl / (tms / 1000.0) / 1e12
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tf_sust"], "traffic": None, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
+                        "avg_launch_ms": tms / calls, "flops_per_launch": fl / calls,
+                        "all_gemm_tflops": sum(v[2] for v in gemm.values()) / (sum(v[1] for v in gemm.values()) / 1000.0) / 1e12,
+                        "model_attn_mlp_frac": FLOPS_ATTN_MLP * (value / world) / 1e12 / peaks["tf_sust"],
+                        "instrumented_ms_per_step": inst_ms / args.steps}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = run_cpu_reference(args, as_impl=False)
+        cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic (seeded random-init weights, ERA5-shaped inputs)", "config": config,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms / args.steps, "api": "models.pangu_model.PanguModel.forward on pinned host inputs"},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "kernels": kernels, "tflops_model": FLOPS_TOTAL * (value / world) / 1e12}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -6,6 +6,42 @@ from .abi import ACT_GELU, ACT_NONE, BF16, F32, Geom
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
+LAUNCHES = 0          # kernels launched through this module (bench.py reads it as `gpu_launches`)
+_TIMING = None        # list of (op-class, start event, end event, flops, bytes) while kernel timing is on
+
+
+def start_kernel_timing():
+    global _TIMING
+    _TIMING = []
+
+
+def stop_kernel_timing():
+    """-> {op-class: (calls, total_ms, flops, bytes)} measured with CUDA events on the launching stream."""
+    global _TIMING
+    rec, _TIMING = _TIMING or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, fl, by in rec:
+        c = out.setdefault(name, [0, 0.0, 0.0, 0.0])
+        c[0] += 1
+        c[1] += e0.elapsed_time(e1)
+        c[2] += fl
+        c[3] += by
+    return {k: tuple(v) for k, v in out.items()}
+
+
+def _call(name, fn, args, kernels=1, flops=0.0, nbytes=0.0):
+    global LAUNCHES
+    LAUNCHES += kernels
+    if _TIMING is None:
+        abi.check(getattr(abi.lib(), fn)(*args), fn)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    abi.check(getattr(abi.lib(), fn)(*args), fn)
+    e1.record()
+    _TIMING.append((name, e0, e1, flops, nbytes))
+
 
 def _ptr(t):
     return None if t is None else t.data_ptr()
@@ -44,8 +80,7 @@ def window_partition(x, Z, H, W, roll):
     nLon, T = window_counts(Z, H, W)
     out = torch.empty((nLon, T, 144, C), dtype=x.dtype, device=x.device)
     g = geom(Z, H, W, C)
-    abi.check(abi.lib().pangu_window_partition(_ptr(x), _ptr(out), g, int(roll), x.element_size(), _stream()),
-              "pangu_window_partition")
+    _call("window_partition", "pangu_window_partition", (_ptr(x), _ptr(out), g, int(roll), x.element_size(), _stream(),))
     return out
 
 
@@ -55,8 +90,7 @@ def window_reverse(win, Z, H, W, roll):
     C = win.shape[-1]
     out = torch.empty((Z * H * W, C), dtype=win.dtype, device=win.device)
     g = geom(Z, H, W, C)
-    abi.check(abi.lib().pangu_window_reverse(_ptr(win), _ptr(out), g, int(roll), win.element_size(), _stream()),
-              "pangu_window_reverse")
+    _call("window_reverse", "pangu_window_reverse", (_ptr(win), _ptr(out), g, int(roll), win.element_size(), _stream(),))
     return out
 
 
@@ -64,7 +98,7 @@ def window_source_index(Z, H, W, roll, device):
     nLon, T = window_counts(Z, H, W)
     out = torch.empty((nLon, T, 144), dtype=torch.int64, device=device)
     g = geom(Z, H, W, 32)
-    abi.check(abi.lib().pangu_window_source_index(_ptr(out), g, int(roll), _stream()), "pangu_window_source_index")
+    _call("window_source_index", "pangu_window_source_index", (_ptr(out), g, int(roll), _stream(),))
     return out
 
 
@@ -72,13 +106,13 @@ def shift_mask(Z, H, W, device):
     nLon, T = window_counts(Z, H, W)
     out = torch.empty((T, 144, 144), dtype=torch.float32, device=device)
     g = geom(Z, H, W, 32)
-    abi.check(abi.lib().pangu_shift_mask(_ptr(out), g, _stream()), "pangu_shift_mask")
+    _call("shift_mask", "pangu_shift_mask", (_ptr(out), g, _stream(),))
     return out
 
 
 def position_index(device):
     out = torch.empty((144 * 144,), dtype=torch.int64, device=device)
-    abi.check(abi.lib().pangu_position_index(_ptr(out), _stream()), "pangu_position_index")
+    _call("position_index", "pangu_position_index", (_ptr(out), _stream(),))
     return out
 
 
@@ -95,8 +129,10 @@ def linear(a, w, bias=None, act=ACT_NONE, out_dtype=None, out=None):
     out_dtype = out_dtype or a.dtype
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype, device=a.device)
-    abi.check(abi.lib().pangu_linear(_ptr(a), K, _ptr(w), _ptr(bias), _ptr(out), N, M, K, N, act, _DT[a.dtype],
-                                     _DT[out.dtype], _stream()), "pangu_linear")
+    tag = "gemm_%s[K=%d,N=%d%s]" % ("bf16" if a.dtype == torch.bfloat16 else "f32", K, N, ",gelu" if act == ACT_GELU else "")
+    _call(tag, "pangu_linear", (_ptr(a), K, _ptr(w), _ptr(bias), _ptr(out), N, M, K, N, act, _DT[a.dtype],
+                                     _DT[out.dtype], _stream(),), flops=2.0 * M * K * N,
+          nbytes=float(a.numel() * a.element_size() + out.numel() * out.element_size() + w.numel() * w.element_size()))
     return out
 
 
@@ -108,8 +144,9 @@ def ln_residual(y, gamma, beta, residual=None, want_f32=True, want_bf16=False, e
     xb = torch.empty((M, C), dtype=torch.bfloat16, device=y.device) if want_bf16 else None
     if residual is not None:
         _chk(residual, torch.float32, "residual")
-    abi.check(abi.lib().pangu_ln_residual(_ptr(y), _DT[y.dtype], _ptr(gamma), _ptr(beta), _ptr(residual), _ptr(x_out),
-                                          _ptr(xb), M, C, eps, _stream()), "pangu_ln_residual")
+    _call("ln_residual[C=%d]" % C, "pangu_ln_residual", (_ptr(y), _DT[y.dtype], _ptr(gamma), _ptr(beta), _ptr(residual), _ptr(x_out),
+                                          _ptr(xb), M, C, eps, _stream(),),
+          nbytes=float(M * C * (y.element_size() + 4 * (residual is not None) + 4 * want_f32 + 2 * want_bf16)))
     return x_out, xb
 
 
@@ -121,9 +158,9 @@ def linear_ln_residual_bf16(a, w, bias, gamma, beta, residual, want_bf16=True, e
     C = w.shape[0]
     x_out = torch.empty((M, C), dtype=torch.float32, device=a.device)
     xb = torch.empty((M, C), dtype=torch.bfloat16, device=a.device) if want_bf16 else None
-    abi.check(abi.lib().pangu_linear_ln_residual_bf16(_ptr(a), K, _ptr(w), _ptr(bias), _ptr(gamma), _ptr(beta),
-                                                      _ptr(residual), _ptr(x_out), _ptr(xb), M, K, C, eps, _stream()),
-              "pangu_linear_ln_residual_bf16")
+    _call("gemm_bf16_ln[K=%d,N=%d]" % (K, C), "pangu_linear_ln_residual_bf16", (_ptr(a), K, _ptr(w), _ptr(bias), _ptr(gamma), _ptr(beta),
+                                                      _ptr(residual), _ptr(x_out), _ptr(xb), M, K, C, eps, _stream(),),
+          flops=2.0 * M * K * C, nbytes=float(M * K * 2 + C * K * 2 + M * C * (8 + 2 * want_bf16)))
     return x_out, xb
 
 
@@ -136,9 +173,12 @@ def window_attention(qkv, qkv_bias, earth_bias, Z, H, W, heads, mode):
     C = C3 // 3
     out = torch.empty((N, C), dtype=qkv.dtype, device=qkv.device)
     g = geom(Z, H, W, C, heads)
-    abi.check(abi.lib().pangu_window_attention(_ptr(qkv), _ptr(qkv_bias), _ptr(earth_bias), _DT[earth_bias.dtype],
-                                               _ptr(out), g, int(mode), _DT[qkv.dtype], _stream()),
-              "pangu_window_attention")
+    nwin = (W // 12) * (Z // 2) * ((H + 5) // 6)
+    tag = "attention_%s[C=%d]" % ("bf16" if qkv.dtype == torch.bfloat16 else "f32", C)
+    _call(tag, "pangu_window_attention", (_ptr(qkv), _ptr(qkv_bias), _ptr(earth_bias), _DT[earth_bias.dtype],
+                                               _ptr(out), g, int(mode), _DT[qkv.dtype], _stream(),),
+          flops=nwin * heads * 4.0 * 144 * 144 * 32,
+          nbytes=float(qkv.numel() * qkv.element_size() + out.numel() * out.element_size() + earth_bias.numel() * earth_bias.element_size()))
     return out
 
 
@@ -152,9 +192,10 @@ def patch_embed_gather(inp, inp_s, statistics, maps, const_h, out_dtype):
     um, us = um.reshape(13, 5).contiguous().float(), us.reshape(13, 5).contiguous().float()
     ps = torch.empty((181 * 360, 112), dtype=out_dtype, device=dev)
     pu = torch.empty((7 * 181 * 360, 192), dtype=out_dtype, device=dev)
-    abi.check(abi.lib().pangu_patch_embed_gather(_ptr(inp), _ptr(inp_s), _ptr(sm), _ptr(ss), _ptr(um), _ptr(us),
+    _call("patch_embed_gather", "pangu_patch_embed_gather", (_ptr(inp), _ptr(inp_s), _ptr(sm), _ptr(ss), _ptr(um), _ptr(us),
                                                  _ptr(maps), _ptr(const_h), _ptr(ps), _ptr(pu), _DT[out_dtype],
-                                                 _stream()), "pangu_patch_embed_gather")
+                                                 _stream(),), kernels=2,
+          nbytes=float((inp.numel() + inp_s.numel() + maps.numel() + const_h.numel()) * 4 + (ps.numel() + pu.numel()) * ps.element_size()))
     return ps, pu
 
 
@@ -164,8 +205,8 @@ def patch_recover_scatter(y_upper, y_surface):
     dev = y_upper.device
     out = torch.empty((1, 5, 13, 721, 1440), dtype=torch.float32, device=dev)
     out_s = torch.empty((1, 4, 721, 1440), dtype=torch.float32, device=dev)
-    abi.check(abi.lib().pangu_patch_recover_scatter(_ptr(y_upper), _ptr(y_surface), _ptr(out), _ptr(out_s), _stream()),
-              "pangu_patch_recover_scatter")
+    _call("patch_recover_scatter", "pangu_patch_recover_scatter", (_ptr(y_upper), _ptr(y_surface), _ptr(out), _ptr(out_s), _stream(),),
+          kernels=2, nbytes=float((y_upper.numel() + y_surface.numel() + out.numel() + out_s.numel()) * 4))
     return out, out_s
 
 
@@ -174,8 +215,9 @@ def downsample_merge_ln(x, gamma, beta, Z, H, W, out_dtype, eps=1e-5):
     C = x.shape[-1]
     rows = Z * ((H + 1) // 2) * (W // 2)
     out = torch.empty((rows, 4 * C), dtype=out_dtype, device=x.device)
-    abi.check(abi.lib().pangu_downsample_merge_ln(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), _DT[out_dtype], Z, H, W,
-                                                  C, eps, _stream()), "pangu_downsample_merge_ln")
+    _call("downsample_merge_ln", "pangu_downsample_merge_ln", (_ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), _DT[out_dtype], Z, H, W,
+                                                  C, eps, _stream(),),
+          nbytes=float(x.numel() * 4 + out.numel() * out.element_size()))
     return out
 
 
@@ -183,16 +225,16 @@ def upsample_shuffle_ln(y, gamma, beta, Z, H2, W2, H, out_dtype, eps=1e-5):
     _chk(y, name="y")
     Co = y.shape[-1] // 4
     out = torch.empty((Z * H * 2 * W2, Co), dtype=out_dtype, device=y.device)
-    abi.check(abi.lib().pangu_upsample_shuffle_ln(_ptr(y), _DT[y.dtype], _ptr(gamma), _ptr(beta), _ptr(out),
-                                                  _DT[out_dtype], Z, H2, W2, H, Co, eps, _stream()),
-              "pangu_upsample_shuffle_ln")
+    _call("upsample_shuffle_ln", "pangu_upsample_shuffle_ln", (_ptr(y), _DT[y.dtype], _ptr(gamma), _ptr(beta), _ptr(out),
+                                                  _DT[out_dtype], Z, H2, W2, H, Co, eps, _stream(),),
+          nbytes=float(y.numel() * y.element_size() + out.numel() * out.element_size()))
     return out
 
 
 def cast_bf16(x):
     _chk(x, torch.float32, "x")
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-    abi.check(abi.lib().pangu_cast_f32_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "pangu_cast_f32_bf16")
+    _call("cast_f32_bf16", "pangu_cast_f32_bf16", (_ptr(x), _ptr(out), x.numel(), _stream(),), nbytes=float(x.numel() * 6))
     return out
 
 
@@ -202,6 +244,6 @@ def concat_cast_bf16(a, b):
     n, C1 = a.shape
     C2 = b.shape[1]
     out = torch.empty((n, C1 + C2), dtype=torch.bfloat16, device=a.device)
-    abi.check(abi.lib().pangu_concat_cast_bf16(_ptr(a), _ptr(b), _ptr(out), n, C1, C2, _stream()),
-              "pangu_concat_cast_bf16")
+    _call("concat_cast_bf16", "pangu_concat_cast_bf16", (_ptr(a), _ptr(b), _ptr(out), n, C1, C2, _stream(),),
+          nbytes=float(n * (C1 + C2) * 6))
     return out
