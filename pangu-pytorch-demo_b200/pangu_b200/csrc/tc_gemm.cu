@@ -4,7 +4,8 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor 128B-swizzled A/W tiles -> smem ring)
 //   warp 1      MMA issuer     (one thread; tcgen05.mma kind::f16, fp32 accumulators in TMEM)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue       (tcgen05.ld -> registers -> bias / GELU / LayerNorm+residual -> global)
+//   warps 4..11 epilogue       (tcgen05.ld -> registers -> bias / GELU / LayerNorm+residual -> swizzled smem
+//                               staging -> row-contiguous global stores; two warps per TMEM lane quarter)
 // TMEM holds two accumulator tiles when 2*BN <= 512 columns, so the epilogue of tile i overlaps the
 // mainloop of tile i+1.  Tiles are enumerated m-major, so the N tiles that share an A tile run on
 // neighbouring CTAs at the same time and A is fetched from HBM once (the rest hits L2).
@@ -35,28 +36,45 @@ struct GemmArgs {
   float eps;
 };
 
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter, interleaved 32-column chunks
+constexpr int kThreads = 128 + kEpiWarps * 32;
+constexpr int kStageEpiBytes = 4096;         // per epilogue warp: 32 rows x 128 B staging tile
+
 template <int BN>
 struct GemmCfg {
   static constexpr int UMMA_N = BN <= 256 ? BN : BN / 2;      // 384 -> 2 x 192
   static constexpr int N_SPLIT = BN / UMMA_N;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_BYTES = kEpiWarps * kStageEpiBytes + 2 * 2 * 128 * 8 /*LN partial sums*/;
+  static constexpr int AVAIL = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - EPI_BYTES;
+  static constexpr int STAGES = AVAIL / STAGE_BYTES > 6 ? 6 : AVAIL / STAGE_BYTES;
   static constexpr int NACC = 2 * BN <= 512 ? 2 : 1;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
   static_assert(BN % 32 == 0, "epilogue works in 32-column chunks");
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
 };
 
+// Staging tile addressing (per warp, 4 KiB).  fp32: 32 rows x 128 B, 16-byte chunk cc of row r lives at
+// chunk position cc ^ (r & 7); bf16: 32 rows x 64 B, chunk position cc ^ ((r >> 1) & 3).  Both the
+// thread-per-row accesses (TMEM layout) and the row-contiguous accesses (coalesced global I/O) are
+// bank-conflict free.
+__device__ __forceinline__ int stg_f32(int r, int cc) { return r * 128 + ((cc ^ (r & 7)) << 4); }
+__device__ __forceinline__ int stg_b16(int r, int cc) { return r * 64 + ((cc ^ ((r >> 1) & 3)) << 4); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+
 template <int BN, bool LN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmArgs a) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES, NACC = Cfg::NACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
+  float2* ln_part = reinterpret_cast<float2*>(epi_smem + kEpiWarps * kStageEpiBytes);   // [2 parity][2 half][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [NACC]
@@ -72,7 +90,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < NACC; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -134,21 +152,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (128 threads, thread = row)
+    // ------------------------------------------------------------ epilogue: 8 warps.
+    // Warp (q, hf): TMEM lanes [32q, 32q+32) = tile rows, 32-column chunks hf, hf+2, ...  Results go
+    // through a per-warp swizzled staging tile so that every global access is row-contiguous.
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int hf = (warp - 4) >> 2;
+    uint8_t* stg = epi_smem + (warp - 4) * kStageEpiBytes;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, tile_par = 0;
     uint32_t v[32];
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const long long m = (long long)(tile / a.n_tiles) * BM + q * 32 + lane;
+      const long long m_base = (long long)(tile / a.n_tiles) * BM + q * 32;
       const int n0 = (tile % a.n_tiles) * BN;
-      const bool valid = m < a.M;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       if (!LN) {
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = hf; c < BN / 32; c += 2) {
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
           const int n = n0 + c * 32;
@@ -166,85 +187,114 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
           }
-          if (valid) {
-            if (a.out_dtype == PANGU_BF16) {
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.out) + m * a.ldo + n);
+          if (a.out_dtype == PANGU_BF16) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                dst[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                    pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-            } else {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + m * a.ldo + n);
+            for (int cc = 0; cc < 4; ++cc)
+              *reinterpret_cast<uint4*>(stg + stg_b16(lane, cc)) =
+                  make_uint4(pack_bf16(f[8 * cc], f[8 * cc + 1]), pack_bf16(f[8 * cc + 2], f[8 * cc + 3]),
+                             pack_bf16(f[8 * cc + 4], f[8 * cc + 5]), pack_bf16(f[8 * cc + 6], f[8 * cc + 7]));
+            __syncwarp();
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            for (int i = 0; i < 4; ++i) {
+              const int rr = (lane >> 2) + 8 * i, cc = lane & 3;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_b16(rr, cc));
+              const long long m = m_base + rr;
+              if (m < a.M) *reinterpret_cast<uint4*>(out + m * a.ldo + n + cc * 8) = val;
+            }
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc)
+              *reinterpret_cast<float4*>(stg + stg_f32(lane, cc)) =
+                  make_float4(f[4 * cc], f[4 * cc + 1], f[4 * cc + 2], f[4 * cc + 3]);
+            __syncwarp();
+            float* out = reinterpret_cast<float*>(a.out);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = (lane >> 3) + 4 * i, cc = lane & 7;
+              const float4 val = *reinterpret_cast<const float4*>(stg + stg_f32(rr, cc));
+              const long long m = m_base + rr;
+              if (m < a.M) *reinterpret_cast<float4*>(out + m * a.ldo + n + cc * 4) = val;
             }
           }
+          __syncwarp();
         }
       } else {
-        // LayerNorm over the full row (BN == C): pass 1 mean, pass 2 centred variance, pass 3 write.
-        float s = 0.f;
+        // LayerNorm over the full row (BN == C).  Pass 1: row sums of x and x^2 (fp32) over this warp's
+        // chunks, combined with the sibling warp through smem.  Pass 2: normalise, affine, add the fp32
+        // residual (fetched row-contiguously, staged), write fp32 + bf16 row-contiguously.
+        float s = 0.f, ss = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = hf; c < BN / 32; c += 2) {
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c * 32 + j));
-            s += (__uint_as_float(v[j]) + b.x) + (__uint_as_float(v[j + 1]) + b.y) +
-                 (__uint_as_float(v[j + 2]) + b.z) + (__uint_as_float(v[j + 3]) + b.w);
+            const float x0 = __uint_as_float(v[j]) + b.x, x1 = __uint_as_float(v[j + 1]) + b.y;
+            const float x2 = __uint_as_float(v[j + 2]) + b.z, x3 = __uint_as_float(v[j + 3]) + b.w;
+            s += (x0 + x1) + (x2 + x3);
+            ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
           }
         }
-        const float mean = s * (1.0f / BN);
-        float qs = 0.f;
+        float2* part = ln_part + tile_par * 256;
+        part[hf * 128 + q * 32 + lane] = make_float2(s, ss);
+        epi_bar_sync();
+        const float2 p0 = part[q * 32 + lane], p1 = part[128 + q * 32 + lane];
+        const float mean = (p0.x + p1.x) * (1.0f / BN);
+        const float var = fmaxf((p0.y + p1.y) * (1.0f / BN) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + a.eps);
+        tile_par ^= 1;
+
+        const int rcc = lane & 7;               // row-contiguous view: chunk rcc of rows (lane>>3) + 4i
+        float4 rg[8];
+        auto load_residual = [&](int c) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const long long m = m_base + (lane >> 3) + 4 * i;
+            rg[i] = (a.residual != nullptr && m < a.M)
+                        ? __ldg(reinterpret_cast<const float4*>(a.residual + m * BN + c * 32 + rcc * 4))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        load_residual(hf);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = hf; c < BN / 32; c += 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(stg + stg_f32((lane >> 3) + 4 * i, rcc)) = rg[i];
+          __syncwarp();
+          if (c + 2 < BN / 32) load_residual(c + 2);
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c * 32 + j));
-            const float d0 = __uint_as_float(v[j]) + b.x - mean, d1 = __uint_as_float(v[j + 1]) + b.y - mean;
-            const float d2 = __uint_as_float(v[j + 2]) + b.z - mean, d3 = __uint_as_float(v[j + 3]) + b.w - mean;
-            qs = fmaf(d0, d0, qs); qs = fmaf(d1, d1, qs); qs = fmaf(d2, d2, qs); qs = fmaf(d3, d3, qs);
-          }
-        }
-        const float rstd = rsqrtf(qs * (1.0f / BN) + a.eps);
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int cc = 0; cc < 8; ++cc) {
+            const int j = cc * 4;
+            float4* p = reinterpret_cast<float4*>(stg + stg_f32(lane, cc));
+            float4 r = *p;
             const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c * 32 + j));
             const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + c * 32 + j));
             const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta + c * 32 + j));
-            f[j] = fmaf((__uint_as_float(v[j]) + b.x - mean) * rstd, g.x, be.x);
-            f[j + 1] = fmaf((__uint_as_float(v[j + 1]) + b.y - mean) * rstd, g.y, be.y);
-            f[j + 2] = fmaf((__uint_as_float(v[j + 2]) + b.z - mean) * rstd, g.z, be.z);
-            f[j + 3] = fmaf((__uint_as_float(v[j + 3]) + b.w - mean) * rstd, g.w, be.w);
+            r.x += fmaf((__uint_as_float(v[j]) + b.x - mean) * rstd, g.x, be.x);
+            r.y += fmaf((__uint_as_float(v[j + 1]) + b.y - mean) * rstd, g.y, be.y);
+            r.z += fmaf((__uint_as_float(v[j + 2]) + b.z - mean) * rstd, g.z, be.z);
+            r.w += fmaf((__uint_as_float(v[j + 3]) + b.w - mean) * rstd, g.w, be.w);
+            *p = r;
           }
-          if (valid) {
-            const long long off = m * BN + c * 32;
-            if (a.residual != nullptr) {
-              const float4* r = reinterpret_cast<const float4*>(a.residual + off);
+          __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 rv = r[j];
-                f[4 * j] += rv.x; f[4 * j + 1] += rv.y; f[4 * j + 2] += rv.z; f[4 * j + 3] += rv.w;
-              }
-            }
-            float4* dst = reinterpret_cast<float4*>(a.x_out + off);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            if (a.x_out_bf16 != nullptr) {
-              uint4* db = reinterpret_cast<uint4*>(a.x_out_bf16 + off);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                db[j] = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                   pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (lane >> 3) + 4 * i;
+            const long long m = m_base + rr;
+            const float4 val = *reinterpret_cast<const float4*>(stg + stg_f32(rr, rcc));
+            if (m < a.M) {
+              const long long off = m * BN + c * 32 + rcc * 4;
+              *reinterpret_cast<float4*>(a.x_out + off) = val;
+              if (a.x_out_bf16 != nullptr)
+                *reinterpret_cast<uint2*>(a.x_out_bf16 + off) = make_uint2(pack_bf16(val.x, val.y), pack_bf16(val.z, val.w));
             }
           }
+          __syncwarp();
         }
       }
       // all of this warp's TMEM reads are done -> hand the accumulator back to the MMA warp
@@ -335,7 +385,7 @@ static int launch_gemm_t(const void* A, long long lda, const void* W, GemmArgs& 
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmB, a);
+  kern<<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmB, a);
   return check_launch("gemm_bf16");
 }
 
