@@ -98,6 +98,19 @@ int pangu_linear_ln_residual_bf16(const void* A, int64_t lda, const void* W, con
                                   float* x_out, void* x_out_bf16, int64_t M, int32_t K, int32_t C,
                                   float eps, void* stream);
 
+/* Fused Mlp + norm2 + residual, bf16 operands (models/layers.py:311-317 and :297):
+ *   x_out = residual + LN( GELU(x . W1^T + b1) . W2^T + b2 ) * gamma + beta,  plus bf16 shadow.
+ * x [M,C] bf16, W1 [4C,C] bf16, W2 [C,4C] bf16, biases/affine fp32, residual/x_out fp32 [M,C]; C in {192,384}.
+ * One kernel: the 4C-wide hidden activation stays in TMEM (tcgen05 cta_group::2, CTA pairs). */
+int pangu_mlp_ln_residual_bf16(const void* x, const void* w1, const float* b1, const void* w2,
+                               const float* b2, const float* gamma, const float* beta,
+                               const float* residual, float* x_out, void* x_out_bf16, int64_t M,
+                               int32_t C, float eps, void* stream);
+
+/* Bring-up aid: copies the fused-Mlp kernel's pipeline timeline (clock64 stamps recorded by CTA 0 when
+ * $PANGU_MLP_DBG has bit 16 set) to HOST memory `out` (n <= 512 int64).  Synchronises the device. */
+int pangu_debug_mlp_trace(int64_t* out, int32_t n);
+
 /* ------------------------------------------------------------------ 3-D window attention */
 
 /* EarthAttention3D.forward between linear1 and linear2 (models/layers.py:422-478) with the block's

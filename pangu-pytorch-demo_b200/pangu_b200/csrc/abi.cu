@@ -39,6 +39,11 @@ int launch_tc_linear(const void* A, long long lda, const void* W, const float* b
 int launch_tc_linear_ln(const void* A, long long lda, const void* W, const float* bias,
                         const float* gamma, const float* beta, const float* residual, float* x_out,
                         void* x_out_bf16, long long M, int K, int C, float eps, cudaStream_t st);
+// tc_mlp.cu
+int launch_tc_mlp(const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
+                  const float* gamma, const float* beta, const float* residual, float* x_out,
+                  void* x_out_bf16, long long M, int C, float eps, cudaStream_t st);
+int debug_read_mlp_trace(long long* out, int n);
 // tc_attention.cu
 int launch_window_attention_bf16(const void* qkv, const float* qkv_bias, const void* earth_bias,
                                  int bias_dtype, void* out, const WinGeom& g, int roll, cudaStream_t st);
@@ -80,6 +85,18 @@ extern "C" int pangu_linear_ln_residual_bf16(const void* A, int64_t lda, const v
                                              int32_t C, float eps, void* stream) {
   if (!A || !W || !gamma || !beta || !x_out || M < 0 || K <= 0) { set_error("linear_ln_residual: bad argument"); return PANGU_ERR_BAD_ARG; }
   return launch_tc_linear_ln(A, lda, W, bias, gamma, beta, residual, x_out, x_out_bf16, M, K, C, eps, as_stream(stream));
+}
+
+extern "C" int pangu_debug_mlp_trace(int64_t* out, int32_t n) {
+  return debug_read_mlp_trace(reinterpret_cast<long long*>(out), n);
+}
+
+extern "C" int pangu_mlp_ln_residual_bf16(const void* x, const void* w1, const float* b1, const void* w2,
+                                          const float* b2, const float* gamma, const float* beta,
+                                          const float* residual, float* x_out, void* x_out_bf16, int64_t M,
+                                          int32_t C, float eps, void* stream) {
+  if (!x || !w1 || !b1 || !w2 || !b2 || !gamma || !beta || !x_out || M < 0) { set_error("mlp_ln_residual: bad argument"); return PANGU_ERR_BAD_ARG; }
+  return launch_tc_mlp(x, w1, b1, w2, b2, gamma, beta, residual, x_out, x_out_bf16, M, C, eps, as_stream(stream));
 }
 
 extern "C" int pangu_window_attention(const void* qkv, const float* qkv_bias, const void* earth_bias,

@@ -2,6 +2,7 @@
 // tcgen05.ld / tcgen05.commit wrappers and the UMMA descriptor encodings used by the bf16 kernels.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdio>
 
 #include "common.cuh"
@@ -48,6 +49,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+
+// One lane of a fully converged warp.  Role warps run their loops warp-uniformly and wrap only the
+// single-thread instructions (TMA, tcgen05.mma, tcgen05.commit) in `if (elect_one())`, so that descriptors
+// and addresses stay in uniform registers instead of being re-broadcast (R2UR + ELECT loops) per issue.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---------------------------------------------------------------- proxies / fences
@@ -189,6 +199,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 bool encode_tmap_2d_bf16(CUtensorMap* map, const void* gptr, uint64_t inner, uint64_t rows,
                          uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows);
 
+int num_sms();
+
 // ---------------------------------------------------------------- misc math
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
@@ -204,6 +216,29 @@ __device__ __forceinline__ float gelu_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xc * p));
   const float hx = 0.5f * x;
   return fmaf(t, hx, hx);
+}
+
+// Two GELUs at once in packed fp16 (same fitted tanh form as gelu_fast): 8 half2 ops + one MUFU per PAIR.
+// Used where the result is consumed as an fp16 tensor-core operand; |error| ~1e-3 of the value (the fp16
+// significand), below the bf16 rounding the un-fused path applies to the hidden activation.
+__device__ __forceinline__ uint32_t gelu_fast_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const __half2 lim = __float2half2_rn(8.0f);
+  const __half2 xc = __hmin2(__hmax2(h, __hneg2(lim)), lim);
+  const __half2 x2 = __hmul2(xc, xc);
+  __half2 p = __hfma2(x2, __float2half2_rn(-3.51519787e-4f), __float2half2_rn(3.70056658e-2f));
+  p = __hfma2(x2, p, __float2half2_rn(7.97507861e-1f));
+  const __half2 u = __hmul2(xc, p);
+  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 hx = __hmul2(h, __float2half2_rn(0.5f));
+  const __half2 o = __hfma2(t, hx, hx);
+  return *reinterpret_cast<const uint32_t*>(&o);
+}
+// Instruction descriptor for kind::f16 with fp16 A/B operands and fp32 accumulation.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace tc

@@ -16,6 +16,8 @@ from . import ops
 from .abi import ACT_GELU, ACT_NONE, ROLL_NONE, ROLL_SHIFT, WINDOWED, PanguError  # noqa: F401
 
 MODES = ("fp32", "bf16")
+# bf16 mode: Mlp + norm2 + residual as ONE tcgen05 kernel (0 = two GEMM kernels; kept for A/B measurements)
+FUSED_MLP = os.environ.get("PANGU_B200_FUSED_MLP", "1") != "0"
 
 
 def default_mode():
@@ -31,14 +33,17 @@ class WeightCache:
     def __init__(self):
         self._c = {}
 
-    def bf16(self, key, p):
+    def f16(self, key, p):
+        return self.bf16(key, p, torch.float16)
+
+    def bf16(self, key, p, dtype=torch.bfloat16):
         ent = self._c.get(key)
         tag = (p.data_ptr(), p._version, p.device)
         if ent is None or ent[0] != tag:
             t = p.detach()
             if t.dim() == 3:                       # Conv1d(k=1) weight [out, in, 1]
                 t = t[:, :, 0]
-            ent = (tag, t.contiguous().to(torch.bfloat16))
+            ent = (tag, t.contiguous().to(dtype))
             self._c[key] = ent
         return ent[1]
 
@@ -85,6 +90,11 @@ def block_forward(blk, x, Z, H, W, roll, mode, xb=None):
     x1, x1b = ops.linear_ln_residual_bf16(o, wc.bf16("a2", att.linear2.weight), _f(att.linear2.bias),
                                           _f(blk.norm1.weight), _f(blk.norm1.bias), x, eps=blk.norm1.eps)
     del o
+    if FUSED_MLP:
+        x2, x2b = ops.mlp_ln_residual_bf16(x1b, wc.bf16("m1", mlp.linear1.weight), _f(mlp.linear1.bias),
+                                           wc.f16("m2h", mlp.linear2.weight), _f(mlp.linear2.bias),
+                                           _f(blk.norm2.weight), _f(blk.norm2.bias), x1, eps=blk.norm2.eps)
+        return x2, x2b
     h = ops.linear(x1b, wc.bf16("m1", mlp.linear1.weight), _f(mlp.linear1.bias), act=ACT_GELU)
     x2, x2b = ops.linear_ln_residual_bf16(h, wc.bf16("m2", mlp.linear2.weight), _f(mlp.linear2.bias),
                                           _f(blk.norm2.weight), _f(blk.norm2.bias), x1, eps=blk.norm2.eps)

@@ -164,6 +164,23 @@ def linear_ln_residual_bf16(a, w, bias, gamma, beta, residual, want_bf16=True, e
     return x_out, xb
 
 
+def mlp_ln_residual_bf16(xb, w1, b1, w2, b2, gamma, beta, residual, want_bf16=True, eps=1e-5):
+    """residual + LN(gelu(xb @ w1.T + b1) @ w2.T + b2)*gamma + beta in ONE kernel (hidden stays in TMEM)."""
+    _chk(xb, torch.bfloat16, "x")
+    _chk(w1, torch.bfloat16, "w1")
+    _chk(w2, torch.float16, "w2 (the GELU output / second GEMM run in fp16)")
+    _chk(residual, torch.float32, "residual")
+    M, C = xb.shape
+    assert w1.shape == (4 * C, C) and w2.shape == (C, 4 * C)
+    x_out = torch.empty((M, C), dtype=torch.float32, device=xb.device)
+    xo_b = torch.empty((M, C), dtype=torch.bfloat16, device=xb.device) if want_bf16 else None
+    _call("mlp_fused_bf16[C=%d]" % C, "pangu_mlp_ln_residual_bf16",
+          (_ptr(xb), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2), _ptr(gamma), _ptr(beta), _ptr(residual), _ptr(x_out),
+           _ptr(xo_b), M, C, eps, _stream(),),
+          flops=16.0 * M * C * C, nbytes=float(M * C * (2 + 4 + 4 + 2 * want_bf16) + 16 * C * C))
+    return x_out, xo_b
+
+
 def window_attention(qkv, qkv_bias, earth_bias, Z, H, W, heads, mode):
     """qkv [N, 3C] (token order, or window order when mode == WINDOWED) -> [N, C]."""
     _chk(qkv, name="qkv")

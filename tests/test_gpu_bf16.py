@@ -62,6 +62,27 @@ def test_tc_linear_ln_residual(C, K):
     assert orc.rel_l2(xb.cpu(), want) <= 3e-3
 
 
+@pytest.mark.parametrize("C,M", [(192, 256), (192, 1000), (384, 128), (384, 777), (384, 20000)])
+def test_tc_fused_mlp_ln_residual(C, M):
+    """Fused Mlp + norm2 + residual kernel (tcgen05 cta_group::2, hidden kept in TMEM as fp16) against
+    fp64 on the same bf16/fp16 operands."""
+    from pangu_b200 import ops
+    g = torch.Generator().manual_seed(C + M)
+    a = torch.randn(M, C, generator=g).bfloat16()
+    w1 = (torch.randn(4 * C, C, generator=g) * 0.08).bfloat16()
+    w2 = (torch.randn(C, 4 * C, generator=g) * 0.05).half()
+    b1, b2 = torch.randn(4 * C, generator=g) * 0.5, torch.randn(C, generator=g)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    res = torch.randn(M, C, generator=g)
+    h = torch.nn.functional.gelu(a.double() @ w1.double().t() + b1.double())
+    y = h @ w2.double().t() + b2.double()
+    want = res.double() + torch.nn.functional.layer_norm(y, (C,), gamma.double(), beta.double(), 1e-5)
+    x, xb = ops.mlp_ln_residual_bf16(a.cuda(), w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), gamma.cuda(),
+                                     beta.cuda(), res.cuda())
+    assert orc.rel_l2(x.cpu(), want) <= 2e-3            # fp16 GELU / hidden rounding only
+    assert orc.rel_l2(xb.cpu(), want) <= 4e-3
+
+
 @pytest.mark.parametrize("Z,H,W,C,heads", [(8, 181, 24, 192, 6), (8, 91, 24, 384, 12)])
 @pytest.mark.parametrize("roll", [0, 1])
 def test_attention_bf16_vs_fp32_kernel(Z, H, W, C, heads, roll):

@@ -1,0 +1,32 @@
+"""Print the fused-Mlp kernel's pipeline timeline (see tc_mlp.cu g_mlp_trace)."""
+import ctypes
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "pangu-pytorch-demo_b200"))
+os.environ["PANGU_MLP_DBG"] = str(16 | int(os.environ.get("PANGU_MLP_DBG", "0")))
+from pangu_b200 import abi, ops  # noqa: E402
+
+C = int(sys.argv[1]) if len(sys.argv) > 1 else 384
+M = 148 * 128 * 2
+g = torch.Generator(device="cuda").manual_seed(0)
+xb = torch.randn(M, C, device="cuda", generator=g).bfloat16()
+x = torch.randn(M, C, device="cuda", generator=g)
+w1 = (torch.randn(4 * C, C, device="cuda", generator=g) * 0.05).bfloat16()
+w2 = (torch.randn(C, 4 * C, device="cuda", generator=g) * 0.05).half()
+b1, b2 = torch.zeros(4 * C, device="cuda"), torch.zeros(C, device="cuda")
+ga, be = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+for _ in range(3):
+    ops.mlp_ln_residual_bf16(xb, w1, b1, w2, b2, ga, be, x)
+torch.cuda.synchronize()
+buf = (ctypes.c_int64 * 512)()
+abi.check(abi.lib().pangu_debug_mlp_trace(ctypes.cast(buf, ctypes.c_void_p), 512), "trace")
+nch = 4 * C // 64
+t0 = min(v for v in buf[:nch * 8] if v > 0)
+print("chunk | mma: p_full  g2_issued g1_issued | epi: h_full  loaded  gelu_done  p_stored   (cycles since first event)")
+for j in range(nch):
+    r = [buf[j * 8 + k] - t0 if buf[j * 8 + k] else -1 for k in range(8)]
+    print(f"{j:3d}   | {r[0]:8d} {r[1]:8d} {r[2]:8d} | {r[4]:8d} {r[5]:8d} {r[6]:8d} {r[7]:8d}")

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "pangu-pytorch-demo_b200"))
 
 CASES = ["ident_64", "ident_k128", "rand_128x192x192", "rand_tail", "rand_big", "gelu", "ln192", "ln384",
-         "attn_a", "attn_b_roll"]
+         "attn_a", "attn_b_roll", "mlp192_256", "mlp192", "mlp384_256", "mlp384", "mlp384_big"]
 
 
 def report(name, got, want):
@@ -71,6 +71,24 @@ def run_case(name):
         y = a.double() @ w.double().t() + b.double()
         want = res.double() + torch.nn.functional.layer_norm(y, (C,), gamma.double(), beta.double(), 1e-5)
         x, xb = ops.linear_ln_residual_bf16(a.cuda(), w.cuda(), b.cuda(), gamma.cuda(), beta.cuda(), res.cuda())
+        report(name + ".f32", x, want)
+        report(name + ".bf16", xb, want)
+    elif name.startswith("mlp"):
+        C = int(name[3:6])
+        M = {"256": 256, "": 777, "big": 40000}[name[7:]]
+        a = torch.randn(M, C, generator=g).bfloat16()
+        w1 = (torch.randn(4 * C, C, generator=g) * 0.08).bfloat16()
+        w2 = (torch.randn(C, 4 * C, generator=g) * 0.05).half()
+        b1, b2 = torch.randn(4 * C, generator=g) * 0.5, torch.randn(C, generator=g)
+        gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+        res = torch.randn(M, C, generator=g)
+        h = torch.nn.functional.gelu(a.double() @ w1.double().t() + b1.double())
+        hb = h.float().half().double()                          # the kernel feeds GEMM2 with an fp16 hidden
+        y = hb @ w2.double().t() + b2.double()
+        want = res.double() + torch.nn.functional.layer_norm(y, (C,), gamma.double(), beta.double(), 1e-5)
+        x, xb = ops.mlp_ln_residual_bf16(a.cuda(), w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), gamma.cuda(),
+                                         beta.cuda(), res.cuda())
+        torch.cuda.synchronize()
         report(name + ".f32", x, want)
         report(name + ".bf16", xb, want)
     elif name.startswith("attn"):
