@@ -100,57 +100,56 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / a.n_tiles) * BM, n0 = (tile % a.n_tiles) * BN;
-        for (int kb = 0; kb < a.k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + A_STAGE_BYTES;
+    // ------------------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / a.n_tiles) * BM, n0 = (tile % a.n_tiles) * BN;
+      for (int kb = 0; kb < a.k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + A_STAGE_BYTES;
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
 #pragma unroll
           for (int h = 0; h < Cfg::N_SPLIT; ++h)
             tma_load_2d(sb + h * Cfg::UMMA_N * BK * 2, &tmB, &full_bar[stage], kb * BK, n0 + h * Cfg::UMMA_N);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, Cfg::UMMA_N, 0, 0);
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+    constexpr uint32_t idesc = make_idesc_bf16(BM, Cfg::UMMA_N, 0, 0);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tcgen05_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < a.k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tcgen05_after_sync();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < a.k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_after_sync();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
-          const uint64_t da = make_desc_k_sw128(sa);
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + A_STAGE_BYTES;
+        const uint64_t da = make_desc_k_sw128(sa);
 #pragma unroll
-          for (int h = 0; h < Cfg::N_SPLIT; ++h) {
-            const uint64_t db = make_desc_k_sw128(sb + h * Cfg::UMMA_N * BK * 2);
+        for (int h = 0; h < Cfg::N_SPLIT; ++h) {
+          const uint64_t db = make_desc_k_sw128(sb + h * Cfg::UMMA_N * BK * 2);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)   // +32 bytes per UMMA_K=16 step inside the swizzle span
-              umma_bf16(d_tmem + h * Cfg::UMMA_N, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          }
-          umma_commit(&empty_bar[stage]);       // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < BK / 16; ++k)   // +32 bytes per UMMA_K=16 step inside the swizzle span
+            if (elect_one()) umma_bf16(d_tmem + h * Cfg::UMMA_N, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
         }
-        umma_commit(&tfull_bar[acc]);           // accumulator complete -> epilogue
-        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
+        if (elect_one()) umma_commit(&empty_bar[stage]);       // frees the smem slot once these MMAs have read it
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tfull_bar[acc]);           // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: 8 warps.
     // Warp (q, hf): TMEM lanes [32q, 32q+32) = tile rows, 32-column chunks hf, hf+2, ...  Results go
