@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -162,7 +162,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="replicas", choices=["replicas"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "bands"],
+                    help="multi-GPU partition: replicas = one forecast per GPU (weak scaling); bands = ONE forecast "
+                         "sharded over latitude bands with NCCL halo exchange (strong scaling, BASELINE configs[3]); "
+                         "auto = bands when N > 1")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-times", action="store_true")
@@ -173,9 +176,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    config = {"workload": "PanguModel 24h forward full-res bf16, batch 1 per GPU (BASELINE.json configs[1])",
+    mode = args.mode if args.mode != "auto" else ("bands" if world > 1 else "replicas")
+    if mode == "bands" and world not in (1, 2, 4, 8):
+        mode = "replicas"
+    par = (f"replicas x{world} (one forecast per GPU, no data-path collective)" if mode == "replicas" else
+           f"latitude bands x{world} (ONE forecast sharded over {world} GPUs; NCCL neighbour halo exchange of 3 rows "
+           "around each of the 8 shifted-window blocks)")
+    config = {"workload": "PanguModel 24h forward full-res bf16, batch 1 (BASELINE.json configs[1]"
+                          + ("" if mode == "replicas" else " sharded as configs[3]") + ")",
               "grid": "13x721x1440 upper-air x5 + 721x1440 surface x4", "tokens": "521280@C192 + 131040@C384",
-              "blocks": 16, "params": 276659936, "parallelism": f"replicas x{world} (one forecast per GPU, no data-path collective)",
+              "blocks": 16, "params": 276659936, "parallelism": par, "mode": mode,
               "cache": "inputs+activations per step (>= 6 GB) exceed the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
@@ -208,13 +218,25 @@ def main():
     model = PanguModel(device="cpu")
     model.load_state_dict(orc.synth_params(seed=0), strict=True)
     model = model.to(dev).eval().set_compute_dtype(args.dtype)
-    inp, inp_s, stats, maps, const_h = orc.synth_inputs(seed=1 + rank)
+    if mode == "bands":
+        # every rank holds its latitude band of ONE sample (same seed on all ranks)
+        from pangu_b200.dist import BandedPangu, BandPlan
+        inp, inp_s, stats, maps, const_h = orc.synth_inputs(seed=1)
+        plan = BandPlan(world, rank)
+        inp, inp_s, maps, const_h = plan.slice_inputs(inp[0], inp_s[0], maps, const_h)
+        forward = BandedPangu(model) if world > 1 else model
+        if world == 1:
+            inp, inp_s = inp[None], inp_s[None]
+    else:
+        inp, inp_s, stats, maps, const_h = orc.synth_inputs(seed=1 + rank)
+        forward = model
     h_inp, h_inp_s = inp.pin_memory(), inp_s.pin_memory()
     d_inp, d_inp_s = inp.to(dev), inp_s.to(dev)
     stats = tuple(s.to(dev) for s in stats)
     maps, const_h = maps.to(dev), const_h.to(dev)
-    h_out = torch.empty((1, 5, 13, 721, 1440), dtype=torch.float32).pin_memory()
-    h_out_s = torch.empty((1, 4, 721, 1440), dtype=torch.float32).pin_memory()
+    lat = inp.shape[-2]
+    h_out = torch.empty((1, 5, 13, lat, 1440), dtype=torch.float32).pin_memory()
+    h_out_s = torch.empty((1, 4, lat, 1440), dtype=torch.float32).pin_memory()
 
     def barrier():
         if world > 1:
@@ -223,13 +245,13 @@ def main():
 
     def step_resident():
         with torch.no_grad():
-            return model(d_inp, d_inp_s, stats, maps, const_h)
+            return forward(d_inp, d_inp_s, stats, maps, const_h)
 
     def step_e2e():
         with torch.no_grad():
             a = h_inp.to(dev, non_blocking=True)
             b = h_inp_s.to(dev, non_blocking=True)
-            o, os_ = model(a, b, stats, maps, const_h)
+            o, os_ = forward(a, b, stats, maps, const_h)
             h_out.copy_(o, non_blocking=True)
             h_out_s.copy_(os_, non_blocking=True)
 
@@ -246,23 +268,24 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                                    # samples cover warm-up + the timed region (both under load)
+    for _ in range(args.warmup):
+        step_resident()
     ops.LAUNCHES = 0
     total_ms = timed(step_resident, args.steps)
     launches = ops.LAUNCHES
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
-    value = world * args.steps / (total_ms / 1000.0)
+    jobs = world if mode == "replicas" else 1              # forecasts completed per step across the job
+    value = jobs * args.steps / (total_ms / 1000.0)
 
     for _ in range(2):
         step_e2e()
     e2e_ms = timed(step_e2e, args.steps)
-    e2e_value = world * args.steps / (e2e_ms / 1000.0)
-    h2d = (h_inp.numel() + h_inp_s.numel()) * 4
+    e2e_value = jobs * args.steps / (e2e_ms / 1000.0)
+    h2d = (h_inp.numel() + h_inp_s.numel()) * 4            # per rank
     d2h = (h_out.numel() + h_out_s.numel()) * 4
 
     kernels, roofline = None, None
@@ -275,7 +298,7 @@ def main():
                        "tflops": (v[2] / (v[1] / 1000.0) / 1e12) if v[1] > 0 and v[2] > 0 else None,
                        "gbs": (v[3] / (v[1] / 1000.0) / 1e9) if v[1] > 0 and v[3] > 0 else None}
                    for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])}
-        gemm = {k: v for k, v in table.items() if k.startswith("gemm")}
+        gemm = {k: v for k, v in table.items() if k.startswith("gemm") or k.startswith("mlp_fused")}
         if gemm:
             dom = max(gemm, key=lambda k: gemm[k][1])
             calls, tms, fl, _ = gemm[dom]
@@ -284,7 +307,7 @@ def main():
                         "frac": ach / peaks["tf_sust"], "traffic": None, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
                         "avg_launch_ms": tms / calls, "flops_per_launch": fl / calls,
                         "all_gemm_tflops": sum(v[2] for v in gemm.values()) / (sum(v[1] for v in gemm.values()) / 1000.0) / 1e12,
-                        "model_attn_mlp_frac": FLOPS_ATTN_MLP * (value / world) / 1e12 / peaks["tf_sust"],
+                        "model_attn_mlp_frac": FLOPS_ATTN_MLP * value / world / 1e12 / peaks["tf_sust"],
                         "instrumented_ms_per_step": inst_ms / args.steps}
 
     cpu_baseline = None
@@ -294,12 +317,13 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak" if mode == "replicas" else "strong", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic (seeded random-init weights, ERA5-shaped inputs)", "config": config,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps, "api": "models.pangu_model.PanguModel.forward on pinned host inputs"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "kernels": kernels, "tflops_model": FLOPS_TOTAL * (value / world) / 1e12}
+                "kernels": kernels, "tflops_model_per_gpu": FLOPS_TOTAL * value / world / 1e12}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

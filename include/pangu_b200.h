@@ -47,6 +47,18 @@ typedef struct {
   int32_t heads;     /* C / 32                                    */
 } pangu_geom;
 
+/* Latitude band of one stage's token grid held by one rank (pangu_b200/dist.py; new -- the reference has no
+ * spatial sharding).  The rank's tensors hold global rows [h0, h0+hrows); the launch covers the h-windows
+ * [hw0, hw0+nhw) of the (rolled or un-rolled) padded grid, the last of them being the global wrap-around
+ * window nH-1 when wrap != 0 (rolled blocks, rank 0); `halo` rows of the next rank follow the own rows in
+ * separate halo buffers. */
+typedef struct {
+  int32_t h0, hrows;
+  int32_t hw0, nhw;
+  int32_t wrap;
+  int32_t halo;
+} pangu_band;
+
 const char* pangu_last_error(void);
 int pangu_abi_version(void);
 /* 1 if the library was built with tcgen05/TMA kernels for sm_100a (always, for this build). */
@@ -128,6 +140,14 @@ int pangu_window_attention(const void* qkv, const float* qkv_bias, const void* e
                            int bias_dtype, void* out, const pangu_geom* g, int roll, int dtype,
                            void* stream);
 
+/* Band-sharded variant (bf16 only): qkv/out hold the band's own rows [Z*hrows*W, .], halo_qkv/halo_out the
+ * `halo` rows of the southern neighbour [Z*halo*W, .] (read for the windows that straddle the band edge in a
+ * rolled block; the attention output computed for them is written to halo_out and returned to the
+ * neighbour).  g is the GLOBAL geometry; bias/mask types are global.  roll in {0,1}. */
+int pangu_window_attention_band(const void* qkv, const void* halo_qkv, const float* qkv_bias,
+                                const void* earth_bias, int bias_dtype, void* out, void* halo_out,
+                                const pangu_geom* g, const pangu_band* band, int roll, void* stream);
+
 /* ------------------------------------------------------------------ layout / bandwidth kernels */
 
 /* PatchEmbedding_pretrain.forward up to the two convs (models/layers.py:56-112): normalise
@@ -143,11 +163,26 @@ int pangu_patch_embed_gather(const float* input, const float* input_surface,
                              const float* const_h, void* patches_surface, void* patches_upper,
                              int out_dtype, void* stream);
 
+/* Same for a latitude band: the arrays hold lat_rows valid pixel rows (input [5,13,lat_rows,1440], ...),
+ * maps holds map_rows rows, and tok_rows = ceil(lat_rows/4) token rows are produced (rows beyond lat_rows
+ * are the zero padding of models/layers.py:37,49).  Full grid: 721, 181, 724. */
+int pangu_patch_embed_gather_rows(const float* input, const float* input_surface,
+                                  const float* surface_mean, const float* surface_std,
+                                  const float* upper_mean, const float* upper_std, const float* maps,
+                                  const float* const_h, void* patches_surface, void* patches_upper,
+                                  int out_dtype, int32_t lat_rows, int32_t tok_rows, int32_t map_rows,
+                                  void* stream);
+
 /* PatchRecovery_pretrain.forward after the two convs (models/layers.py:593-619): un-patchify + crop.
  *   y_upper [7*181*360, 160] (ch = v*32+pz*16+ph*4+pw), y_surface [181*360, 64] (ch = v*16+ph*4+pw), fp32
  *   -> output [5,13,721,1440], output_surface [4,721,1440] fp32. */
 int pangu_patch_recover_scatter(const float* y_upper, const float* y_surface, float* output,
                                 float* output_surface, void* stream);
+
+/* Same for a latitude band of tok_rows token rows / lat_rows output pixel rows. */
+int pangu_patch_recover_scatter_rows(const float* y_upper, const float* y_surface, float* output,
+                                     float* output_surface, int32_t lat_rows, int32_t tok_rows,
+                                     void* stream);
 
 /* DownSample.forward before the linear (models/layers.py:501-519): pad H to even, 2x2 merge
  * (feature = dh*2C + dw*C + c), LayerNorm(4C).  x fp32 [Z*H*W, C] -> out [Z*ceil(H/2)*(W/2), 4C]. */

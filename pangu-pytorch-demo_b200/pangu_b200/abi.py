@@ -24,6 +24,12 @@ class Geom(Structure):
     _fields_ = [("Z", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("heads", c_int32)]
 
 
+class Band(Structure):
+    """pangu_band: latitude band of one stage's window grid (include/pangu_b200.h)."""
+    _fields_ = [("h0", c_int32), ("hrows", c_int32), ("hw0", c_int32), ("nhw", c_int32), ("wrap", c_int32),
+                ("halo", c_int32)]
+
+
 _PROTOS = {
     "pangu_last_error": (c_char_p, []),
     "pangu_abi_version": (c_int, []),
@@ -43,8 +49,12 @@ _PROTOS = {
     "pangu_debug_mlp_trace": (c_int, [c_void_p, c_int32]),
     "pangu_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(Geom), c_int, c_int,
                                        c_void_p]),
+    "pangu_window_attention_band": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                            POINTER(Geom), POINTER(Band), c_int, c_void_p]),
     "pangu_patch_embed_gather": (c_int, [c_void_p] * 10 + [c_int, c_void_p]),
+    "pangu_patch_embed_gather_rows": (c_int, [c_void_p] * 10 + [c_int, c_int32, c_int32, c_int32, c_void_p]),
     "pangu_patch_recover_scatter": (c_int, [c_void_p] * 5),
+    "pangu_patch_recover_scatter_rows": (c_int, [c_void_p] * 4 + [c_int32, c_int32, c_void_p]),
     "pangu_downsample_merge_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int32, c_int32, c_int32,
                                           c_int32, c_float, c_void_p]),
     "pangu_upsample_shuffle_ln": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int32, c_int32,

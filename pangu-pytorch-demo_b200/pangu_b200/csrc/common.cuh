@@ -23,6 +23,14 @@ struct WinGeom {
   int Hp, nZ, nH, nLon, T;
 };
 
+// Latitude band of the window grid handled by one launch (see tc_attention.cu).
+struct BandGeom {
+  int h0, hrows;     // qkv/out hold global rows [h0, h0 + hrows)
+  int hw0, nhw;      // h-windows [hw0, hw0 + nhw) ; with wrap the last one is the global window nH-1
+  int wrap;
+  int halo;          // rows available in the halo buffers right after the own rows
+};
+
 inline bool make_geom(const pangu_geom* g, WinGeom& o) {
   if (!g) return false;
   o.Z = g->Z; o.H = g->H; o.W = g->W; o.C = g->C; o.heads = g->heads;

@@ -8,6 +8,9 @@ namespace pangu {
 constexpr int kLat = 721, kLon = 1440, kLev = 13;
 constexpr int kLatPad = 724;                     // models/layers.py:37,49 (+3 rows)
 constexpr int kTokH = 181, kTokW = 360;          // 724/4, 1440/4
+// The kernels take the latitude extent at run time (lat = valid pixel rows of the arrays they are given,
+// tokH = token rows, mapRows = rows of the constant-map array) so that a latitude band of the grid can be
+// embedded / recovered on its own; the full grid is lat = 721, tokH = 181, mapRows = 724.
 constexpr int kTileTok = 32;                     // tokens (along w') per CTA
 
 template <typename T>
@@ -34,7 +37,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 patch_embed_upper_kernel(const float* __restrict__ input, const float* __restrict__ const_h,
                          const float* __restrict__ upper_mean, const float* __restrict__ upper_std,
-                         T* __restrict__ patches) {
+                         T* __restrict__ patches, int lat, int tokH) {
   constexpr int F = 192, PITCH = F + 1;
   __shared__ float tile[kTileTok * PITCH];
   const int w0 = blockIdx.x * kTileTok, hp = blockIdx.y, zp = blockIdx.z;
@@ -45,10 +48,10 @@ patch_embed_upper_kernel(const float* __restrict__ input, const float* __restric
     const int c = r >> 3, pz = (r >> 2) & 1, ph = r & 3;
     const int lev = 2 * zp + pz, y = 4 * hp + ph;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tok < ntok && lev < kLev && y < kLat) {
-      const long long off = ((long long)lev * kLat + y) * kLon + 4 * (w0 + tok);
+    if (tok < ntok && lev < kLev && y < lat) {
+      const long long off = ((long long)lev * lat + y) * kLon + 4 * (w0 + tok);
       if (c < 5) {
-        v = __ldg(reinterpret_cast<const float4*>(input + (long long)c * kLev * kLat * kLon + off));
+        v = __ldg(reinterpret_cast<const float4*>(input + (long long)c * kLev * lat * kLon + off));
         // statistics are stored in flipped level order (layers.py:95-99): index 12 - lev
         const float m = __ldg(upper_mean + (kLev - 1 - lev) * 5 + c);
         const float s = __ldg(upper_std + (kLev - 1 - lev) * 5 + c);
@@ -61,7 +64,7 @@ patch_embed_upper_kernel(const float* __restrict__ input, const float* __restric
     d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
   __syncthreads();
-  const long long tok0 = ((long long)zp * kTokH + hp) * kTokW + w0;
+  const long long tok0 = ((long long)zp * tokH + hp) * kTokW + w0;
   store_tile_row_major<T>(patches + tok0 * F, tile, PITCH, ntok, F, threadIdx.x, blockDim.x);
 }
 
@@ -71,7 +74,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 patch_embed_surface_kernel(const float* __restrict__ input_surface, const float* __restrict__ maps,
                            const float* __restrict__ surface_mean, const float* __restrict__ surface_std,
-                           T* __restrict__ patches) {
+                           T* __restrict__ patches, int lat, int mapRows) {
   constexpr int F = 112, PITCH = F + 1;
   __shared__ float tile[kTileTok * PITCH];
   const int w0 = blockIdx.x * kTileTok, hp = blockIdx.y;
@@ -84,13 +87,14 @@ patch_embed_surface_kernel(const float* __restrict__ input_surface, const float*
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tok < ntok) {
       if (c < 4) {
-        if (y < kLat) {
-          v = __ldg(reinterpret_cast<const float4*>(input_surface + ((long long)c * kLat + y) * kLon + 4 * (w0 + tok)));
+        if (y < lat) {
+          v = __ldg(reinterpret_cast<const float4*>(input_surface + ((long long)c * lat + y) * kLon + 4 * (w0 + tok)));
           const float m = __ldg(surface_mean + c), s = __ldg(surface_std + c);
           v.x = (v.x - m) / s; v.y = (v.y - m) / s; v.z = (v.z - m) / s; v.w = (v.w - m) / s;
         }
       } else {
-        v = __ldg(reinterpret_cast<const float4*>(maps + ((long long)(c - 4) * kLatPad + y) * kLon + 4 * (w0 + tok)));
+        if (y < mapRows)
+          v = __ldg(reinterpret_cast<const float4*>(maps + ((long long)(c - 4) * mapRows + y) * kLon + 4 * (w0 + tok)));
       }
     }
     float* d = tile + tok * PITCH + c * 16 + ph * 4;
@@ -104,12 +108,12 @@ patch_embed_surface_kernel(const float* __restrict__ input_surface, const float*
 // Un-patchify (layers.py:593-603 upper, :609-619 surface).  One CTA = 32 tokens along w'.
 template <int kF, int kRows, bool kUpper>
 __global__ void __launch_bounds__(256)
-patch_recover_kernel(const float* __restrict__ y, float* __restrict__ out) {
+patch_recover_kernel(const float* __restrict__ y, float* __restrict__ out, int lat, int tokH) {
   constexpr int PITCH = kF + 1;
   __shared__ float tile[kTileTok * PITCH];
   const int w0 = blockIdx.x * kTileTok, hp = blockIdx.y, zp = blockIdx.z;
   const int ntok = min(kTileTok, kTokW - w0);
-  const long long tok0 = ((long long)zp * kTokH + hp) * kTokW + w0;
+  const long long tok0 = ((long long)zp * tokH + hp) * kTokW + w0;
   const float* src = y + tok0 * kF;
   for (int i = threadIdx.x; i < ntok * kF; i += blockDim.x) tile[(i / kF) * PITCH + (i % kF)] = __ldg(src + i);
   __syncthreads();
@@ -120,14 +124,14 @@ patch_recover_kernel(const float* __restrict__ y, float* __restrict__ out) {
     int v, lev, yy;
     if (kUpper) {                                   // r = v*8 + pz*4 + ph ; channel = v*32+pz*16+ph*4+pw
       v = r >> 3; lev = 2 * zp + ((r >> 2) & 1); yy = 4 * hp + (r & 3);
-      if (lev >= kLev || yy >= kLat) continue;
+      if (lev >= kLev || yy >= lat) continue;
     } else {                                        // r = v*4 + ph ; channel = v*16+ph*4+pw
       v = r >> 2; lev = 0; yy = 4 * hp + (r & 3);
-      if (yy >= kLat) continue;
+      if (yy >= lat) continue;
     }
     const float* s = tile + tok * PITCH + r * 4;
     const long long plane = kUpper ? ((long long)v * kLev + lev) : (long long)v;
-    *reinterpret_cast<float4*>(out + (plane * kLat + yy) * kLon + 4 * (w0 + tok)) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(out + (plane * lat + yy) * kLon + 4 * (w0 + tok)) = make_float4(s[0], s[1], s[2], s[3]);
   }
 }
 
@@ -233,33 +237,54 @@ concat_cast_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b
 
 using namespace pangu;
 
+extern "C" int pangu_patch_embed_gather_rows(const float* input, const float* input_surface,
+                                             const float* surface_mean, const float* surface_std,
+                                             const float* upper_mean, const float* upper_std,
+                                             const float* maps, const float* const_h, void* patches_surface,
+                                             void* patches_upper, int out_dtype, int32_t lat_rows,
+                                             int32_t tok_rows, int32_t map_rows, void* stream) {
+  if (!input || !input_surface || !surface_mean || !surface_std || !upper_mean || !upper_std || !maps ||
+      !const_h || !patches_surface || !patches_upper) { set_error("patch_embed_gather: null pointer"); return PANGU_ERR_BAD_ARG; }
+  if (lat_rows <= 0 || tok_rows <= 0 || 4 * tok_rows < lat_rows || 4 * (tok_rows - 1) >= lat_rows || map_rows < lat_rows) {
+    set_error("patch_embed_gather: inconsistent rows (lat %d, tokens %d, maps %d)", lat_rows, tok_rows, map_rows);
+    return PANGU_ERR_BAD_ARG;
+  }
+  cudaStream_t st = as_stream(stream);
+  dim3 gu((kTokW + kTileTok - 1) / kTileTok, tok_rows, 7), gs((kTokW + kTileTok - 1) / kTileTok, tok_rows);
+  if (out_dtype == PANGU_F32) {
+    patch_embed_upper_kernel<float><<<gu, 256, 0, st>>>(input, const_h, upper_mean, upper_std, (float*)patches_upper, lat_rows, tok_rows);
+    patch_embed_surface_kernel<float><<<gs, 256, 0, st>>>(input_surface, maps, surface_mean, surface_std, (float*)patches_surface, lat_rows, map_rows);
+  } else {
+    patch_embed_upper_kernel<__nv_bfloat16><<<gu, 256, 0, st>>>(input, const_h, upper_mean, upper_std, (__nv_bfloat16*)patches_upper, lat_rows, tok_rows);
+    patch_embed_surface_kernel<__nv_bfloat16><<<gs, 256, 0, st>>>(input_surface, maps, surface_mean, surface_std, (__nv_bfloat16*)patches_surface, lat_rows, map_rows);
+  }
+  return check_launch("patch_embed_gather");
+}
+
 extern "C" int pangu_patch_embed_gather(const float* input, const float* input_surface,
                                         const float* surface_mean, const float* surface_std,
                                         const float* upper_mean, const float* upper_std,
                                         const float* maps, const float* const_h, void* patches_surface,
                                         void* patches_upper, int out_dtype, void* stream) {
-  if (!input || !input_surface || !surface_mean || !surface_std || !upper_mean || !upper_std || !maps ||
-      !const_h || !patches_surface || !patches_upper) { set_error("patch_embed_gather: null pointer"); return PANGU_ERR_BAD_ARG; }
+  return pangu_patch_embed_gather_rows(input, input_surface, surface_mean, surface_std, upper_mean, upper_std, maps,
+                                       const_h, patches_surface, patches_upper, out_dtype, kLat, kTokH, kLatPad, stream);
+}
+
+extern "C" int pangu_patch_recover_scatter_rows(const float* y_upper, const float* y_surface, float* output,
+                                                float* output_surface, int32_t lat_rows, int32_t tok_rows,
+                                                void* stream) {
+  if (!y_upper || !y_surface || !output || !output_surface) { set_error("patch_recover_scatter: null pointer"); return PANGU_ERR_BAD_ARG; }
+  if (lat_rows <= 0 || tok_rows <= 0 || 4 * tok_rows < lat_rows) { set_error("patch_recover_scatter: inconsistent rows"); return PANGU_ERR_BAD_ARG; }
   cudaStream_t st = as_stream(stream);
-  dim3 gu((kTokW + kTileTok - 1) / kTileTok, kTokH, 7), gs((kTokW + kTileTok - 1) / kTileTok, kTokH);
-  if (out_dtype == PANGU_F32) {
-    patch_embed_upper_kernel<float><<<gu, 256, 0, st>>>(input, const_h, upper_mean, upper_std, (float*)patches_upper);
-    patch_embed_surface_kernel<float><<<gs, 256, 0, st>>>(input_surface, maps, surface_mean, surface_std, (float*)patches_surface);
-  } else {
-    patch_embed_upper_kernel<__nv_bfloat16><<<gu, 256, 0, st>>>(input, const_h, upper_mean, upper_std, (__nv_bfloat16*)patches_upper);
-    patch_embed_surface_kernel<__nv_bfloat16><<<gs, 256, 0, st>>>(input_surface, maps, surface_mean, surface_std, (__nv_bfloat16*)patches_surface);
-  }
-  return check_launch("patch_embed_gather");
+  dim3 gu((kTokW + kTileTok - 1) / kTileTok, tok_rows, 7), gs((kTokW + kTileTok - 1) / kTileTok, tok_rows, 1);
+  patch_recover_kernel<160, 40, true><<<gu, 256, 0, st>>>(y_upper, output, lat_rows, tok_rows);
+  patch_recover_kernel<64, 16, false><<<gs, 256, 0, st>>>(y_surface, output_surface, lat_rows, tok_rows);
+  return check_launch("patch_recover_scatter");
 }
 
 extern "C" int pangu_patch_recover_scatter(const float* y_upper, const float* y_surface, float* output,
                                            float* output_surface, void* stream) {
-  if (!y_upper || !y_surface || !output || !output_surface) { set_error("patch_recover_scatter: null pointer"); return PANGU_ERR_BAD_ARG; }
-  cudaStream_t st = as_stream(stream);
-  dim3 gu((kTokW + kTileTok - 1) / kTileTok, kTokH, 7), gs((kTokW + kTileTok - 1) / kTileTok, kTokH, 1);
-  patch_recover_kernel<160, 40, true><<<gu, 256, 0, st>>>(y_upper, output);
-  patch_recover_kernel<64, 16, false><<<gs, 256, 0, st>>>(y_surface, output_surface);
-  return check_launch("patch_recover_scatter");
+  return pangu_patch_recover_scatter_rows(y_upper, y_surface, output, output_surface, kLat, kTokH, stream);
 }
 
 extern "C" int pangu_downsample_merge_ln(const float* x, const float* gamma, const float* beta, void* out,

@@ -58,9 +58,10 @@ __device__ __forceinline__ int tile_off(int r, int c) { return r * 64 + ((c ^ ((
 
 template <typename TB>
 __global__ void __launch_bounds__(kThreads, 2)
-window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ qkv_bias,
-                             const TB* __restrict__ earth_bias, __nv_bfloat16* __restrict__ out, WinGeom g,
-                             int roll, int lon_chunk) {
+window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ halo_qkv,
+                             const float* __restrict__ qkv_bias, const TB* __restrict__ earth_bias,
+                             __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ halo_out, WinGeom g,
+                             BandGeom bd, int roll, int lon_chunk) {
   extern __shared__ __align__(128) uint8_t smem[];
   __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(smem);                       // [144][152]
   uint8_t* s_buf = smem + kWinTokens * kBiasPitch * 2;                                  // 2 x {q,k,v}
@@ -68,7 +69,12 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const float*
   int* s_dw = s_rowbase + kWinTokens;                                                   // [144]
   uint8_t* s_gid = reinterpret_cast<uint8_t*>(s_dw + kWinTokens);                       // [144]
 
-  const int head = blockIdx.x, lchunk = blockIdx.y, t = blockIdx.z;
+  // Latitude band (pangu_b200/dist.py): this launch covers bd.nhw h-windows starting at global window bd.hw0
+  // (the last one being the global wrap window nH-1 when bd.wrap); qkv/out hold rows [bd.h0, bd.h0+bd.hrows) of
+  // the global grid, halo_qkv/halo_out the bd.halo rows that follow.  Full grid: {0, H, 0, nH, 0, 0}.
+  const int head = blockIdx.x, lchunk = blockIdx.y;
+  const int zw_ = blockIdx.z / bd.nhw, hwl_ = blockIdx.z - zw_ * bd.nhw;
+  const int t = zw_ * g.nH + ((bd.wrap && hwl_ == bd.nhw - 1) ? g.nH - 1 : bd.hw0 + hwl_);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = g.C;
   const int l_begin = lchunk * lon_chunk;
@@ -84,7 +90,13 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const float*
       s_rowbase[k] = t * kWinTokens + k;
       s_dw[k] = 0;
     } else {
-      s_rowbase[k] = h < g.H ? (z * g.H + h) * g.W : -1;
+      const int hl = h - bd.h0;
+      int rb = -1;                                            // zero pad row (or outside this band: never selected)
+      if (h < g.H) {
+        if (hl >= 0 && hl < bd.hrows) rb = (z * bd.hrows + hl) * g.W;
+        else if (hl >= bd.hrows && hl < bd.hrows + bd.halo) rb = -2 - (z * bd.halo + (hl - bd.hrows)) * g.W;
+      }
+      s_rowbase[k] = rb;
       s_dw[k] = dw;
     }
     s_gid[k] = (uint8_t)shift_group(g, t, k);
@@ -108,12 +120,13 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const float*
   }
   __syncthreads();
 
-  // token of window element k in longitude window l (rb = s_rowbase[k] >= 0)
+  // token of window element k in longitude window l: index into qkv/out (rb >= 0) or into the halo
+  // buffers (rb <= -2, offset -2 - rb)
   auto token_of = [&](int l, int k, int rb) -> long long {
     if (roll == 2) return (long long)l * g.T * kWinTokens + rb;
     int w = 12 * l + (roll == 1 ? 6 : 0) + s_dw[k];
     if (w >= g.W) w -= g.W;
-    return (long long)rb + w;
+    return (long long)(rb >= 0 ? rb : -2 - rb) + w;
   };
   // issue the gather of window l into buffer b: 144 tokens x {q,k,v} x 4 chunks of 16 B
   auto issue_load = [&](int l, int b) {
@@ -122,8 +135,8 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const float*
       const int k = i / 12, part = i - k * 12, s = part >> 2, c = part & 3;
       uint8_t* dst = buf + s * kTileBytes + tile_off(k, c);
       const int rb = s_rowbase[k];
-      if (rb >= 0) {
-        const __nv_bfloat16* src = qkv + token_of(l, k, rb) * 3 * C + s * C + head * kHeadDim + c * 8;
+      if (rb != -1) {
+        const __nv_bfloat16* src = (rb >= 0 ? qkv : halo_qkv) + token_of(l, k, rb) * 3 * C + s * C + head * kHeadDim + c * 8;
         cp_async16(smem_u32(dst), src);
       } else {                                            // zero pad row: linear1(0) = bias (layers.py:228,419)
         const float* bsrc = qkv_bias + s * C + head * kHeadDim + c * 8;
@@ -257,9 +270,9 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const float*
       for (int i = 0; i < 2; ++i) {
         const int idx = lane + i * 32, r = row0 + (idx >> 2), c = idx & 3;
         const int rb = s_rowbase[r];
-        if (rb >= 0) {                                      // pad rows are cropped (layers.py:287-288)
+        if (rb != -1) {                                     // pad rows are cropped (layers.py:287-288)
           const uint4 val = *reinterpret_cast<const uint4*>(sq + tile_off(r, c));
-          *reinterpret_cast<uint4*>(out + token_of(l, r, rb) * C + head * kHeadDim + c * 8) = val;
+          *reinterpret_cast<uint4*>((rb >= 0 ? out : halo_out) + token_of(l, r, rb) * C + head * kHeadDim + c * 8) = val;
         }
       }
     }
@@ -270,24 +283,28 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const float*
 
 }  // namespace attn
 
-int launch_window_attention_bf16(const void* qkv, const float* qkv_bias, const void* earth_bias,
-                                 int bias_dtype, void* out, const WinGeom& g, int roll, cudaStream_t st) {
+int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const float* qkv_bias, const void* earth_bias,
+                                 int bias_dtype, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
+                                 int roll, cudaStream_t st) {
   using namespace attn;
   const int lon_chunk = g.nLon % 5 == 0 ? 5 : (g.nLon % 3 == 0 ? 3 : (g.nLon % 2 == 0 ? 2 : 1));
-  dim3 grid((unsigned)g.heads, (unsigned)((g.nLon + lon_chunk - 1) / lon_chunk), (unsigned)g.T);
+  if (bd.nhw <= 0) return PANGU_OK;
+  dim3 grid((unsigned)g.heads, (unsigned)((g.nLon + lon_chunk - 1) / lon_chunk), (unsigned)(g.nZ * bd.nhw));
   cudaError_t e;
   if (bias_dtype == PANGU_BF16) {
     auto kern = window_attention_bf16_kernel<__nv_bfloat16>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) { set_error("attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, qkv_bias, (const __nv_bfloat16*)earth_bias,
-                                             (__nv_bfloat16*)out, g, roll, lon_chunk);
+    kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)halo_qkv, qkv_bias,
+                                             (const __nv_bfloat16*)earth_bias, (__nv_bfloat16*)out,
+                                             (__nv_bfloat16*)halo_out, g, bd, roll, lon_chunk);
   } else if (bias_dtype == PANGU_F32) {
     auto kern = window_attention_bf16_kernel<float>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) { set_error("attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, qkv_bias, (const float*)earth_bias,
-                                             (__nv_bfloat16*)out, g, roll, lon_chunk);
+    kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)halo_qkv, qkv_bias,
+                                             (const float*)earth_bias, (__nv_bfloat16*)out, (__nv_bfloat16*)halo_out,
+                                             g, bd, roll, lon_chunk);
   } else {
     set_error("attention_bf16: unknown bias dtype %d", bias_dtype);
     return PANGU_ERR_BAD_ARG;

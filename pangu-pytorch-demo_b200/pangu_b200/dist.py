@@ -1,0 +1,269 @@
+"""Latitude-band spatial sharding of the Pangu forward (BASELINE configs[3]) -- new in this repo,
+the reference has no spatial parallelism.
+
+One process per GPU; rank r of P in {1, 2, 4, 8} owns a contiguous band of latitude rows in every stage:
+
+    stage A (C = 192)  24 * (8 / P) token rows      (4 * (8 / P) six-row windows)
+    stage B (C = 384)  12 * (8 / P) token rows      (2 * (8 / P) windows)
+    pixels             96 * (8 / P) rows
+
+the last rank taking the remainder (up to row 180 / 90 / 720 plus the reference's zero padding).  Everything
+except the shifted-window attention is row-local: patch embed / recover are 4x4 pixel patches, down / up-sample
+pair rows (2i, 2i+1), linears / LayerNorm / Mlp are per token, un-rolled windows (models/layers.py:253-262) are
+aligned to the band edges.  In a rolled block (torch.roll by (-1,-3,-6), models/layers.py:237) the h-window hw
+reads rows [6 hw + 3, 6 hw + 9): each rank runs the windows whose first source row it owns, which needs the
+FIRST 3 ROWS of its southern neighbour's qkv (exchange "up") and produces the attention output of those 3
+rows, returned to the neighbour (exchange "down").  The wrap-around window (3 pad rows + global rows 0..2) is
+isolated by the -100 shift mask (models/layers.py:187-216), so rank 0 computes it locally.
+
+The exchanges are NCCL point-to-point (`torch.distributed.batch_isend_irecv`) of 3*8*W*3C / 3*8*W*C bf16
+(about 10 MB / 3.3 MB); a `LocalComm` runs all ranks of a plan inside ONE process (tests on a single GPU:
+the banded result must equal the un-sharded forward).
+"""
+import torch
+import torch.distributed as dist
+
+from . import functional as PF
+from . import ops
+from .abi import Band, PanguError
+
+TOK_H = {"A": 181, "B": 91}
+TOK_W = {"A": 360, "B": 180}
+PIX_H, Z = 721, 8
+
+
+class BandPlan:
+    """Row ranges of one rank.  All ranges are [begin, end) in GLOBAL row coordinates."""
+
+    def __init__(self, world, rank):
+        if world not in (1, 2, 4, 8):
+            raise PanguError(f"latitude-band sharding supports 1, 2, 4 or 8 ranks, not {world}")
+        if not 0 <= rank < world:
+            raise PanguError(f"rank {rank} outside world {world}")
+        self.world, self.rank = world, rank
+        self.first, self.last = rank == 0, rank == world - 1
+        per_a = 24 * (8 // world)                      # stage-A rows per rank; a multiple of the 6-row window
+        a0 = per_a * rank
+        a1 = TOK_H["A"] if self.last else per_a * (rank + 1)
+        self.rows = {"A": (a0, a1), "B": (a0 // 2, (a1 + 1) // 2)}
+        self.pix = (4 * a0, min(4 * a1, PIX_H))
+        self.map_rows = (4 * a0, 4 * a1)               # the constant maps are stored already padded (724 rows)
+
+    def nrows(self, stage):
+        r = self.rows[stage]
+        return r[1] - r[0]
+
+    def band(self, stage, roll):
+        """pangu_band of this rank for one block of `stage` (models/layers.py:228: 5 pad rows, 6-row windows)."""
+        h0, h1 = self.rows[stage]
+        nH = (TOK_H[stage] + 5) // 6
+        hw0 = h0 // 6
+        if not roll:
+            hw1 = nH if self.last else h1 // 6
+            return Band(h0, h1 - h0, hw0, hw1 - hw0, 0, 0)
+        # rolled: regular windows [hw0, hw1); the global window nH-1 wraps around to rows 0..2 -> rank 0
+        hw1 = nH - 1 if self.last else h1 // 6
+        wrap = 1 if self.first else 0
+        halo = 0 if self.last else 3
+        return Band(h0, h1 - h0, hw0, hw1 - hw0 + wrap, wrap, halo)
+
+    def slice_inputs(self, input, input_surface, maps, const_h):
+        """Band of the full-grid arrays (contiguous copies): what this rank is handed in a sharded deployment."""
+        p0, p1 = self.pix
+        m0, m1 = self.map_rows
+        return (input[..., p0:p1, :].contiguous(), input_surface[..., p0:p1, :].contiguous(),
+                maps[..., m0:m1, :].contiguous(), const_h[..., p0:p1, :].contiguous())
+
+
+# ----------------------------------------------------------------------------------------------
+# communicators: shift_up (rank r receives what rank r+1 sends), shift_down (r receives from r-1)
+# ----------------------------------------------------------------------------------------------
+class DistComm:
+    """torch.distributed point-to-point neighbour exchange (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise PanguError("DistComm needs an initialised torch.distributed process group")
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def _peer(self, r):
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    def _exchange(self, send, recv_like, to_rank, from_rank):
+        opsl, out = [], None
+        if send is not None and 0 <= to_rank < self.world:
+            opsl.append(dist.P2POp(dist.isend, send, self._peer(to_rank), self.group))
+        if recv_like is not None and 0 <= from_rank < self.world:
+            out = torch.empty_like(recv_like)
+            opsl.append(dist.P2POp(dist.irecv, out, self._peer(from_rank), self.group))
+        if opsl:
+            for w in dist.batch_isend_irecv(opsl):
+                w.wait()
+        return out
+
+    def shift_up(self, sends, recv_like):
+        """sends[0] goes to rank-1; returns what rank+1 sent (shaped like recv_like[0]) or None on the last rank."""
+        return [self._exchange(sends[0], recv_like[0], self.rank - 1, self.rank + 1)]
+
+    def shift_down(self, sends, recv_like):
+        return [self._exchange(sends[0], recv_like[0], self.rank + 1, self.rank - 1)]
+
+
+class LocalComm:
+    """All ranks of a plan in one process: lists are indexed by rank."""
+
+    def __init__(self, world):
+        self.world, self.rank = world, None
+
+    def shift_up(self, sends, recv_like):
+        return [sends[r + 1] if r + 1 < self.world and recv_like[r] is not None else None for r in range(self.world)]
+
+    def shift_down(self, sends, recv_like):
+        return [sends[r - 1] if r >= 1 and recv_like[r] is not None else None for r in range(self.world)]
+
+
+# ----------------------------------------------------------------------------------------------
+class _Worker:
+    """State of one rank's band while it moves through the network."""
+
+    def __init__(self, model, plan):
+        self.m, self.plan = model, plan
+        self.x = self.xb = self.skip = self.qkv = self.o = self.halo_qkv = self.halo_o = None
+
+    # --- row-local stages
+    def embed(self, inp, inp_s, stats, maps, const_h):
+        self.x, self.xb = PF.patch_embed_forward(self.m._input_layer, inp, inp_s, stats, maps, const_h, "bf16")
+
+    def downsample(self):
+        self.skip = self.x
+        self.x, self.xb = self.m.downsample.forward_sample(self.x, Z, self.plan.nrows("A"), TOK_W["A"])
+
+    def upsample(self):
+        self.x, self.xb = PF.upsample_forward(self.m.upsample, self.x, "bf16", self.xb, Z=Z, H2=self.plan.nrows("B"),
+                                              W2=TOK_W["B"], H=self.plan.nrows("A"))
+
+    def recover(self):
+        lat = self.plan.pix[1] - self.plan.pix[0]
+        return PF.patch_recover_forward(self.m._output_layer, self.x, Z, self.plan.nrows("A"), TOK_W["A"], "bf16",
+                                        skip=self.skip, lat=lat)
+
+    # --- one EarthSpecificBlock in three phases around the two neighbour exchanges
+    def block_qkv(self, blk, stage):
+        att, wc = blk.attention, blk._wcache
+        if self.xb is None:
+            self.xb = ops.cast_bf16(self.x)
+        self.qkv = ops.linear(self.xb, wc.bf16("a1", att.linear1.weight), PF._f(att.linear1.bias))
+
+    def first_rows(self, t, stage, rows=3):
+        """The first `rows` latitude rows of a band tensor [Z*hrows*W, F] as a contiguous [Z*rows*W, F] block."""
+        hr, W = self.plan.nrows(stage), TOK_W[stage]
+        return t.view(Z, hr, W, t.shape[-1])[:, :rows].reshape(Z * rows * W, t.shape[-1]).contiguous()
+
+    def block_attend(self, blk, stage, roll):
+        att, wc = blk.attention, blk._wcache
+        band = self.plan.band(stage, roll)
+        self.o, self.halo_o = ops.window_attention_band(
+            self.qkv, self.halo_qkv, PF._f(att.linear1.bias), wc.bf16("eb", att.earth_specific_bias), Z, TOK_H[stage],
+            TOK_W[stage], att.head_number, band, roll)
+        self.qkv = self.halo_qkv = None
+
+    def block_finish(self, blk, stage, o_first):
+        att, mlp, wc = blk.attention, blk.linear, blk._wcache
+        if o_first is not None:                          # rows 0..2 of this band were computed by the northern neighbour
+            hr, W = self.plan.nrows(stage), TOK_W[stage]
+            self.o.view(Z, hr, W, self.o.shape[-1])[:, :3].copy_(o_first.view(Z, 3, W, self.o.shape[-1]))
+        x1, x1b = ops.linear_ln_residual_bf16(self.o, wc.bf16("a2", att.linear2.weight), PF._f(att.linear2.bias),
+                                              PF._f(blk.norm1.weight), PF._f(blk.norm1.bias), self.x, eps=blk.norm1.eps)
+        self.o = self.halo_o = None
+        self.x, self.xb = ops.mlp_ln_residual_bf16(x1b, wc.bf16("m1", mlp.linear1.weight), PF._f(mlp.linear1.bias),
+                                                   wc.f16("m2h", mlp.linear2.weight), PF._f(mlp.linear2.bias),
+                                                   PF._f(blk.norm2.weight), PF._f(blk.norm2.bias), x1, eps=blk.norm2.eps)
+
+
+def _run(model, workers, comm, inputs):
+    """Drive the workers (one per local rank) through the network; `comm` moves the halos between them."""
+    n = len(workers)
+    for w, (inp, inp_s, stats, maps, const_h) in zip(workers, inputs):
+        w.embed(inp, inp_s, stats, maps, const_h)
+    stages = ["A", "B", "B", "A"]
+    for li, layer in enumerate(model.layers):
+        stage = stages[li]
+        if li == 1:
+            for w in workers:
+                w.downsample()
+        if li == 3:
+            for w in workers:
+                w.upsample()
+        for bi, blk in enumerate(layer.blocks):
+            roll = 1 if bi % 2 == 1 else 0
+            for w in workers:
+                w.block_qkv(blk, stage)
+            exchange = roll and comm.world > 1
+            if exchange:
+                sends = [None if w.plan.first else w.first_rows(w.qkv, stage) for w in workers]
+                like = [None if w.plan.last else _halo_like(w.qkv, stage) for w in workers]
+                halos = comm.shift_up(sends, like)
+                for w, h in zip(workers, halos):
+                    w.halo_qkv = h
+            for w in workers:
+                w.block_attend(blk, stage, roll)
+            firsts = [None] * n
+            if exchange:
+                sends = [w.halo_o for w in workers]
+                like = [None if w.plan.first else _halo_like(w.o, stage) for w in workers]
+                firsts = comm.shift_down(sends, like)
+            for w, f in zip(workers, firsts):
+                w.block_finish(blk, stage, f)
+    return [w.recover() for w in workers]
+
+
+def _halo_like(t, stage, rows=3):
+    return torch.empty((Z * rows * TOK_W[stage], t.shape[-1]), dtype=t.dtype, device=t.device)
+
+
+def _check_model(model):
+    if getattr(model, "training", False) and torch.is_grad_enabled():
+        pass                                             # forward only; gradients are never recorded here
+    if model._mode() != "bf16":
+        raise PanguError("latitude-band sharding runs the bf16 tensor-core path (set_compute_dtype('bf16'))")
+
+
+class BandedPangu:
+    """This rank's band of `PanguModel.forward` inside a torch.distributed job (weights replicated).
+
+        plan = BandPlan(world, rank); band_inputs = plan.slice_inputs(input[0], input_surface[0], maps, const_h)
+        out, out_surface = BandedPangu(model)(*band_inputs[:2], statistics, *band_inputs[2:])
+
+    Inputs are ONE sample's band: input [5,13,rows,1440], input_surface [4,rows,1440], maps [.,3,4*tok_rows,1440],
+    const_h [...,13,rows,1440]; outputs [1,5,13,rows,1440] and [1,4,rows,1440] are the same rows of the forecast."""
+
+    def __init__(self, model, group=None, comm=None):
+        _check_model(model)
+        self.model = model
+        self.comm = comm if comm is not None else DistComm(group)
+        self.plan = BandPlan(self.comm.world, self.comm.rank)
+
+    @torch.no_grad()
+    def __call__(self, inp, inp_s, statistics, maps, const_h):
+        dev = inp.device
+        stats = tuple(s.to(dev) for s in statistics)
+        w = _Worker(self.model, self.plan)
+        return _run(self.model, [w], self.comm, [(inp.float().contiguous(), inp_s.float().contiguous(), stats,
+                                                  maps.float().contiguous(), const_h.float().contiguous())])[0]
+
+
+@torch.no_grad()
+def emulate_bands(model, world, input, input_surface, statistics, maps, const_h):
+    """Run all `world` bands of one full-grid sample in THIS process (LocalComm) and stitch the outputs:
+    (output [1,5,13,721,1440], output_surface [1,4,721,1440]).  Used by the single-GPU parity tests."""
+    _check_model(model)
+    dev = input.device
+    stats = tuple(s.to(dev) for s in statistics)
+    plans = [BandPlan(world, r) for r in range(world)]
+    inputs = []
+    for p in plans:
+        a, b, m, c = p.slice_inputs(input.float(), input_surface.float(), maps.float(), const_h.float())
+        inputs.append((a.reshape(5, 13, -1, 1440), b.reshape(4, -1, 1440), stats, m, c))
+    outs = _run(model, [_Worker(model, p) for p in plans], LocalComm(world), inputs)
+    return torch.cat([o[0] for o in outs], dim=3), torch.cat([o[1] for o in outs], dim=2)

@@ -144,8 +144,8 @@ def patch_embed_forward(pe, inp, inp_s, statistics, maps, const_h, mode):
     dim = pe.conv.out_channels
     dt = torch.float32 if mode == "fp32" else torch.bfloat16
     ps, pu = ops.patch_embed_gather(inp, inp_s, statistics, maps, const_h, dt)
-    x = torch.empty((8 * 181 * 360, dim), dtype=torch.float32, device=inp.device)
-    ns = 181 * 360
+    ns = ps.shape[0]                                     # token rows * 360 (181 * 360 for the full grid)
+    x = torch.empty((8 * ns, dim), dtype=torch.float32, device=inp.device)
     if mode == "fp32":
         ops.linear(ps, _w2d(pe.conv_surface.weight), _f(pe.conv_surface.bias), out=x[:ns])
         ops.linear(pu, _w2d(pe.conv.weight), _f(pe.conv.bias), out=x[ns:])
@@ -180,20 +180,21 @@ def upsample_forward(us, x, mode, xb=None, Z=8, H2=91, W2=180, H=181):
     return ops.linear(n, wc.bf16("l2", us.linear2.weight), None, out_dtype=torch.float32), None
 
 
-def patch_recover_forward(pr, x, Z, H, W, mode, skip=None):
+def patch_recover_forward(pr, x, Z, H, W, mode, skip=None, lat=721):
     """PatchRecovery_pretrain.forward (models/layers.py:582-621).  x [N, dim] fp32, or when `skip` is given
     the pair (skip, x) whose channel concat (models/pangu_model.py:98) is the input."""
-    if (Z, H, W) != (8, 181, 360):
-        raise PanguError("PatchRecovery_pretrain is hard-wired to the (8,181,360) grid, like the reference")
+    if (Z, W) != (8, 360) or H != (lat + 3) // 4:
+        raise PanguError("PatchRecovery_pretrain is hard-wired to the (8,181,360) grid, like the reference "
+                         "(or a latitude band of it)")
     ns = H * W
     if mode == "fp32":
         if skip is not None:
             x = torch.cat((skip, x), dim=-1)
         yu = ops.linear(x[ns:], _w2d(pr.conv.weight), _f(pr.conv.bias))
         ys = ops.linear(x[:ns], _w2d(pr.conv_surface.weight), _f(pr.conv_surface.bias))
-        return ops.patch_recover_scatter(yu, ys)
+        return ops.patch_recover_scatter(yu, ys, lat)
     xb = ops.concat_cast_bf16(skip, x) if skip is not None else ops.cast_bf16(x)
     wc = pr._wcache
     yu = ops.linear(xb[ns:], wc.bf16("c", pr.conv.weight), _f(pr.conv.bias), out_dtype=torch.float32)
     ys = ops.linear(xb[:ns], wc.bf16("cs", pr.conv_surface.weight), _f(pr.conv_surface.bias), out_dtype=torch.float32)
-    return ops.patch_recover_scatter(yu, ys)
+    return ops.patch_recover_scatter(yu, ys, lat)

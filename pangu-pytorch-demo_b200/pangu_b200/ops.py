@@ -2,7 +2,7 @@
 import torch
 
 from . import abi
-from .abi import ACT_GELU, ACT_NONE, BF16, F32, Geom
+from .abi import ACT_GELU, ACT_NONE, BF16, F32, Band, Geom
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -199,30 +199,67 @@ def window_attention(qkv, qkv_bias, earth_bias, Z, H, W, heads, mode):
     return out
 
 
+def window_attention_band(qkv, halo_qkv, qkv_bias, earth_bias, Z, H, W, heads, band, roll):
+    """Band-sharded window attention (bf16): qkv [Z*hrows*W, 3C] holds the band's own rows of the GLOBAL
+    (Z, H, W) grid, halo_qkv [Z*halo*W, 3C] the southern neighbour's first rows.  -> (out, halo_out)."""
+    _chk(qkv, torch.bfloat16, "qkv")
+    _chk(qkv_bias, torch.float32, "qkv_bias")
+    _chk(earth_bias, name="earth_bias")
+    C = qkv.shape[1] // 3
+    if qkv.shape[0] != Z * band.hrows * W:
+        raise abi.PanguError(f"qkv has {qkv.shape[0]} rows, band expects {Z * band.hrows * W}")
+    out = torch.empty((qkv.shape[0], C), dtype=qkv.dtype, device=qkv.device)
+    halo_out = None
+    if band.halo:
+        _chk(halo_qkv, torch.bfloat16, "halo_qkv")
+        if halo_qkv.shape[0] != Z * band.halo * W:
+            raise abi.PanguError("halo_qkv has the wrong number of rows")
+        halo_out = torch.empty((Z * band.halo * W, C), dtype=qkv.dtype, device=qkv.device)
+    g = geom(Z, H, W, C, heads)
+    nwin = (W // 12) * (Z // 2) * band.nhw
+    _call("attention_bf16[C=%d]" % C, "pangu_window_attention_band",
+          (_ptr(qkv), _ptr(halo_qkv) if band.halo else None, _ptr(qkv_bias), _ptr(earth_bias), _DT[earth_bias.dtype],
+           _ptr(out), _ptr(halo_out), g, band, int(roll), _stream(),),
+          flops=nwin * heads * 4.0 * 144 * 144 * 32,
+          nbytes=float(qkv.numel() * 2 + out.numel() * 2 + earth_bias.numel() * earth_bias.element_size() * band.nhw / ((H + 5) // 6)))
+    return out, halo_out
+
+
 # ------------------------------------------------------------------ layout
 def patch_embed_gather(inp, inp_s, statistics, maps, const_h, out_dtype):
+    """inp [5,13,lat,1440], inp_s [4,lat,1440], maps [3,map_rows,1440], const_h [13,lat,1440] (any leading 1s);
+    lat = 721 for the full grid or the pixel rows of a latitude band.  -> (surface patches, upper patches)."""
     sm, ss, um, us = statistics
     dev = inp.device
     for t, n in ((inp, "input"), (inp_s, "input_surface"), (maps, "maps"), (const_h, "const_h")):
         _chk(t, torch.float32, n)
+    lat, map_rows = inp.shape[-2], maps.shape[-2]
+    tok_rows = (lat + 3) // 4
+    if inp_s.shape[-2] != lat or const_h.shape[-2] != lat or inp.shape[-1] != 1440:
+        raise abi.PanguError("patch_embed_gather: inconsistent latitude extents")
     sm, ss = sm.reshape(-1).contiguous().float(), ss.reshape(-1).contiguous().float()
     um, us = um.reshape(13, 5).contiguous().float(), us.reshape(13, 5).contiguous().float()
-    ps = torch.empty((181 * 360, 112), dtype=out_dtype, device=dev)
-    pu = torch.empty((7 * 181 * 360, 192), dtype=out_dtype, device=dev)
-    _call("patch_embed_gather", "pangu_patch_embed_gather", (_ptr(inp), _ptr(inp_s), _ptr(sm), _ptr(ss), _ptr(um), _ptr(us),
-                                                 _ptr(maps), _ptr(const_h), _ptr(ps), _ptr(pu), _DT[out_dtype],
-                                                 _stream(),), kernels=2,
+    ps = torch.empty((tok_rows * 360, 112), dtype=out_dtype, device=dev)
+    pu = torch.empty((7 * tok_rows * 360, 192), dtype=out_dtype, device=dev)
+    _call("patch_embed_gather", "pangu_patch_embed_gather_rows",
+          (_ptr(inp), _ptr(inp_s), _ptr(sm), _ptr(ss), _ptr(um), _ptr(us), _ptr(maps), _ptr(const_h), _ptr(ps), _ptr(pu),
+           _DT[out_dtype], lat, tok_rows, map_rows, _stream(),), kernels=2,
           nbytes=float((inp.numel() + inp_s.numel() + maps.numel() + const_h.numel()) * 4 + (ps.numel() + pu.numel()) * ps.element_size()))
     return ps, pu
 
 
-def patch_recover_scatter(y_upper, y_surface):
+def patch_recover_scatter(y_upper, y_surface, lat=721):
+    """-> output [1,5,13,lat,1440], output_surface [1,4,lat,1440]; y_* hold ceil(lat/4) token rows."""
     _chk(y_upper, torch.float32, "y_upper")
     _chk(y_surface, torch.float32, "y_surface")
     dev = y_upper.device
-    out = torch.empty((1, 5, 13, 721, 1440), dtype=torch.float32, device=dev)
-    out_s = torch.empty((1, 4, 721, 1440), dtype=torch.float32, device=dev)
-    _call("patch_recover_scatter", "pangu_patch_recover_scatter", (_ptr(y_upper), _ptr(y_surface), _ptr(out), _ptr(out_s), _stream(),),
+    tok_rows = y_surface.shape[0] // 360
+    if y_surface.shape[0] != tok_rows * 360 or y_upper.shape[0] != 7 * tok_rows * 360 or (lat + 3) // 4 != tok_rows:
+        raise abi.PanguError("patch_recover_scatter: token rows do not match the latitude extent")
+    out = torch.empty((1, 5, 13, lat, 1440), dtype=torch.float32, device=dev)
+    out_s = torch.empty((1, 4, lat, 1440), dtype=torch.float32, device=dev)
+    _call("patch_recover_scatter", "pangu_patch_recover_scatter_rows",
+          (_ptr(y_upper), _ptr(y_surface), _ptr(out), _ptr(out_s), lat, tok_rows, _stream(),),
           kernels=2, nbytes=float((y_upper.numel() + y_surface.numel() + out.numel() + out_s.numel()) * 4))
     return out, out_s
 
