@@ -167,6 +167,11 @@ def main():
                          "sharded over latitude bands with NCCL halo exchange (strong scaling, BASELINE configs[3]); "
                          "auto = bands when N > 1")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--graph", default="on", choices=["on", "off"],
+                    help="replay the step from a CUDA graph (pangu_b200.graph.GraphedForward) instead of ~100 "
+                         "ctypes launches per step")
+    ap.add_argument("--scheme", default="redundant", choices=["redundant", "sendback"],
+                    help="halo exchange scheme of --mode bands (pangu_b200/dist.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-times", action="store_true")
     args = ap.parse_args()
@@ -224,7 +229,8 @@ def main():
         inp, inp_s, stats, maps, const_h = orc.synth_inputs(seed=1)
         plan = BandPlan(world, rank)
         inp, inp_s, maps, const_h = plan.slice_inputs(inp[0], inp_s[0], maps, const_h)
-        forward = BandedPangu(model) if world > 1 else model
+        forward = BandedPangu(model, scheme=args.scheme) if world > 1 else model
+        config["halo_scheme"] = args.scheme
         if world == 1:
             inp, inp_s = inp[None], inp_s[None]
     else:
@@ -243,15 +249,35 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphed = None
+    if args.graph == "on":
+        from pangu_b200.graph import GraphedForward
+        try:
+            graphed = GraphedForward(forward, (d_inp, d_inp_s, stats, maps, const_h))
+        except Exception as exc:                                  # noqa: BLE001 -- report and measure the eager path
+            sys.stderr.write(f"[bench] CUDA-graph capture failed on rank {rank} ({type(exc).__name__}: {exc}); eager launches\n")
+            graphed = None
+        if world > 1:                                             # all ranks must take the same path
+            flag = torch.tensor([1 if graphed is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                graphed = None
+    config["launch"] = "cuda-graph replay (1 graph launch per step)" if graphed is not None else "eager ctypes launches"
+
     def step_resident():
+        if graphed is not None:
+            return graphed.replay()
         with torch.no_grad():
             return forward(d_inp, d_inp_s, stats, maps, const_h)
 
     def step_e2e():
         with torch.no_grad():
-            a = h_inp.to(dev, non_blocking=True)
-            b = h_inp_s.to(dev, non_blocking=True)
-            o, os_ = forward(a, b, stats, maps, const_h)
+            if graphed is not None:
+                o, os_ = graphed(h_inp, h_inp_s)                   # H2D into the static buffers + replay
+            else:
+                a = h_inp.to(dev, non_blocking=True)
+                b = h_inp_s.to(dev, non_blocking=True)
+                o, os_ = forward(a, b, stats, maps, const_h)
             h_out.copy_(o, non_blocking=True)
             h_out_s.copy_(os_, non_blocking=True)
 
@@ -291,8 +317,10 @@ def main():
     kernels, roofline = None, None
     peaks = load_peaks()
     if not args.no_kernel_times:
-        ops.start_kernel_timing()
+        ops.start_kernel_timing()                          # per-kernel CUDA events need the eager launch path
+        _g, graphed = graphed, None
         inst_ms = timed(step_resident, args.steps)
+        graphed = _g
         table = ops.stop_kernel_timing()               # {op-class: (calls, total_ms, flops, bytes)}
         kernels = {k: {"calls_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
                        "tflops": (v[2] / (v[1] / 1000.0) / 1e12) if v[1] > 0 and v[2] > 0 else None,
@@ -321,12 +349,21 @@ def main():
                 "scaling": "weak" if mode == "replicas" else "strong", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic (seeded random-init weights, ERA5-shaped inputs)", "config": config,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / args.steps, "api": "models.pangu_model.PanguModel.forward on pinned host inputs"},
+                        "ms_per_step": e2e_ms / args.steps, "api": ("pangu_b200.graph.GraphedForward(PanguModel / BandedPangu)" if graphed is not None else
+                                "models.pangu_model.PanguModel.forward") + " on pinned host inputs"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "kernels": kernels, "tflops_model_per_gpu": FLOPS_TOTAL * value / world / 1e12}
         print(json.dumps(line))
     if world > 1:
+        # NCCL teardown while a captured graph still references the communicator can block: release the graph,
+        # drain the device, and bound the teardown (the JSON line is already out)
+        graphed = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        threading.Timer(15.0, lambda: os._exit(0)).start()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -56,7 +56,8 @@ typedef struct {
   int32_t h0, hrows;
   int32_t hw0, nhw;
   int32_t wrap;
-  int32_t halo;
+  int32_t halo;      /* rows of the southern neighbour available after the own rows  */
+  int32_t halo_lo;   /* rows of the northern neighbour available before the own rows */
 } pangu_band;
 
 const char* pangu_last_error(void);
@@ -140,13 +141,16 @@ int pangu_window_attention(const void* qkv, const float* qkv_bias, const void* e
                            int bias_dtype, void* out, const pangu_geom* g, int roll, int dtype,
                            void* stream);
 
-/* Band-sharded variant (bf16 only): qkv/out hold the band's own rows [Z*hrows*W, .], halo_qkv/halo_out the
- * `halo` rows of the southern neighbour [Z*halo*W, .] (read for the windows that straddle the band edge in a
- * rolled block; the attention output computed for them is written to halo_out and returned to the
- * neighbour).  g is the GLOBAL geometry; bias/mask types are global.  roll in {0,1}. */
-int pangu_window_attention_band(const void* qkv, const void* halo_qkv, const float* qkv_bias,
-                                const void* earth_bias, int bias_dtype, void* out, void* halo_out,
-                                const pangu_geom* g, const pangu_band* band, int roll, void* stream);
+/* Band-sharded variant (bf16 only): qkv/out hold the band's own rows [Z*hrows*W, .]; halo_qkv [Z*halo*W, .] the
+ * first rows of the southern neighbour and halo_lo_qkv [Z*halo_lo*W, .] the last rows of the northern neighbour
+ * (read by the windows that straddle a band edge in a rolled block).  Attention output of own rows goes to
+ * `out`; output of southern-halo rows goes to halo_out when it is not NULL (to be returned to the neighbour)
+ * and is dropped otherwise (both neighbours compute the straddling window).  g is the GLOBAL geometry;
+ * bias/mask types are global.  roll in {0,1}. */
+int pangu_window_attention_band(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv,
+                                const float* qkv_bias, const void* earth_bias, int bias_dtype, void* out,
+                                void* halo_out, const pangu_geom* g, const pangu_band* band, int roll,
+                                void* stream);
 
 /* ------------------------------------------------------------------ layout / bandwidth kernels */
 

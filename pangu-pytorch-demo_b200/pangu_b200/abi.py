@@ -27,7 +27,7 @@ class Geom(Structure):
 class Band(Structure):
     """pangu_band: latitude band of one stage's window grid (include/pangu_b200.h)."""
     _fields_ = [("h0", c_int32), ("hrows", c_int32), ("hw0", c_int32), ("nhw", c_int32), ("wrap", c_int32),
-                ("halo", c_int32)]
+                ("halo", c_int32), ("halo_lo", c_int32)]
 
 
 _PROTOS = {
@@ -49,8 +49,8 @@ _PROTOS = {
     "pangu_debug_mlp_trace": (c_int, [c_void_p, c_int32]),
     "pangu_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(Geom), c_int, c_int,
                                        c_void_p]),
-    "pangu_window_attention_band": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                            POINTER(Geom), POINTER(Band), c_int, c_void_p]),
+    "pangu_window_attention_band": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                            c_void_p, POINTER(Geom), POINTER(Band), c_int, c_void_p]),
     "pangu_patch_embed_gather": (c_int, [c_void_p] * 10 + [c_int, c_void_p]),
     "pangu_patch_embed_gather_rows": (c_int, [c_void_p] * 10 + [c_int, c_int32, c_int32, c_int32, c_void_p]),
     "pangu_patch_recover_scatter": (c_int, [c_void_p] * 5),

@@ -45,7 +45,7 @@ int launch_tc_mlp(const void* x, const void* w1, const float* b1, const void* w2
                   void* x_out_bf16, long long M, int C, float eps, cudaStream_t st);
 int debug_read_mlp_trace(long long* out, int n);
 // tc_attention.cu
-int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const float* qkv_bias, const void* earth_bias,
+int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias, const void* earth_bias,
                                  int bias_dtype, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
                                  int roll, cudaStream_t st);
 
@@ -111,25 +111,27 @@ extern "C" int pangu_window_attention(const void* qkv, const float* qkv_bias, co
     return launch_window_attention_f32((const float*)qkv, qkv_bias, (const float*)earth_bias, (float*)out, g, roll, as_stream(stream));
   }
   if (dtype == PANGU_BF16) {
-    const BandGeom full{0, g.H, 0, g.nH, 0, 0};
-    return launch_window_attention_bf16(qkv, nullptr, qkv_bias, earth_bias, bias_dtype, out, nullptr, g, full, roll, as_stream(stream));
+    const BandGeom full{0, g.H, 0, g.nH, 0, 0, 0};
+    return launch_window_attention_bf16(qkv, nullptr, nullptr, qkv_bias, earth_bias, bias_dtype, out, nullptr, g, full, roll, as_stream(stream));
   }
   set_error("window_attention: unknown dtype %d", dtype);
   return PANGU_ERR_BAD_ARG;
 }
 
-extern "C" int pangu_window_attention_band(const void* qkv, const void* halo_qkv, const float* qkv_bias,
-                                           const void* earth_bias, int bias_dtype, void* out, void* halo_out,
-                                           const pangu_geom* gg, const pangu_band* band, int roll, void* stream) {
+extern "C" int pangu_window_attention_band(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv,
+                                           const float* qkv_bias, const void* earth_bias, int bias_dtype,
+                                           void* out, void* halo_out, const pangu_geom* gg,
+                                           const pangu_band* band, int roll, void* stream) {
   WinGeom g;
   if (!make_geom(gg, g) || !band || !qkv || !qkv_bias || !earth_bias || !out) { set_error("window_attention_band: bad argument"); return PANGU_ERR_BAD_ARG; }
   if (g.C != g.heads * kHeadDim) { set_error("window_attention_band: C=%d must equal heads*32", g.C); return PANGU_ERR_BAD_ARG; }
   if (roll != 0 && roll != 1) { set_error("window_attention_band: roll must be 0 or 1"); return PANGU_ERR_BAD_ARG; }
-  const BandGeom bd{band->h0, band->hrows, band->hw0, band->nhw, band->wrap, band->halo};
+  const BandGeom bd{band->h0, band->hrows, band->hw0, band->nhw, band->wrap, band->halo, band->halo_lo};
   const int last_hw = bd.hw0 + bd.nhw - (bd.wrap ? 1 : 0);          // one past the last regular window
   if (bd.h0 < 0 || bd.hrows <= 0 || bd.h0 + bd.hrows > g.H || bd.hw0 < 0 || bd.nhw < 0 || last_hw > g.nH ||
-      bd.halo < 0 || (bd.halo > 0 && (!halo_qkv || !halo_out)) || (bd.wrap && (roll != 1 || bd.h0 != 0))) {
-    set_error("window_attention_band: inconsistent band (h0 %d rows %d hw0 %d nhw %d wrap %d halo %d)", bd.h0, bd.hrows, bd.hw0, bd.nhw, bd.wrap, bd.halo);
+      bd.halo < 0 || (bd.halo > 0 && !halo_qkv) || bd.halo_lo < 0 || (bd.halo_lo > 0 && !halo_lo_qkv) ||
+      (bd.wrap && (roll != 1 || bd.h0 != 0))) {
+    set_error("window_attention_band: inconsistent band (h0 %d rows %d hw0 %d nhw %d wrap %d halo %d/%d)", bd.h0, bd.hrows, bd.hw0, bd.nhw, bd.wrap, bd.halo, bd.halo_lo);
     return PANGU_ERR_BAD_ARG;
   }
   // every source row of the selected windows must be a pad row, an own row or a halo row
@@ -137,10 +139,10 @@ extern "C" int pangu_window_attention_band(const void* qkv, const void* halo_qkv
   for (int i = 0; i < bd.nhw - (bd.wrap ? 1 : 0); ++i) {
     const int lo = 6 * (bd.hw0 + i) + shift, hi = lo + 5;             // no wrap for regular windows (hi < Hp)
     const int hi_real = hi < g.H ? hi : g.H - 1;
-    if (lo < g.H && (lo < bd.h0 || hi_real >= bd.h0 + bd.hrows + bd.halo)) {
+    if (lo < g.H && (lo < bd.h0 - bd.halo_lo || hi_real >= bd.h0 + bd.hrows + bd.halo)) {
       set_error("window_attention_band: window %d needs rows [%d,%d] outside band [%d,%d)+%d", bd.hw0 + i, lo, hi_real, bd.h0, bd.h0 + bd.hrows, bd.halo);
       return PANGU_ERR_BAD_ARG;
     }
   }
-  return launch_window_attention_bf16(qkv, halo_qkv, qkv_bias, earth_bias, bias_dtype, out, halo_out, g, bd, roll, as_stream(stream));
+  return launch_window_attention_bf16(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, bias_dtype, out, halo_out, g, bd, roll, as_stream(stream));
 }

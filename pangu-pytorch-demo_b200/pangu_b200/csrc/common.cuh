@@ -29,6 +29,7 @@ struct BandGeom {
   int hw0, nhw;      // h-windows [hw0, hw0 + nhw) ; with wrap the last one is the global window nH-1
   int wrap;
   int halo;          // rows available in the halo buffers right after the own rows
+  int halo_lo;       // rows available in the northern halo buffer right before the own rows
 };
 
 inline bool make_geom(const pangu_geom* g, WinGeom& o) {

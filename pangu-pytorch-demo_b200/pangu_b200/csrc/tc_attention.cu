@@ -12,6 +12,8 @@
 #include "common.cuh"
 
 namespace pangu {
+namespace tc { int num_sms(); }
+static inline int tc_num_sms() { return tc::num_sms(); }
 namespace attn {
 
 constexpr int kWarps = 9;                         // 9 x 16 query rows = 144
@@ -59,6 +61,7 @@ __device__ __forceinline__ int tile_off(int r, int c) { return r * 64 + ((c ^ ((
 template <typename TB>
 __global__ void __launch_bounds__(kThreads, 2)
 window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ halo_qkv,
+                             const __nv_bfloat16* __restrict__ halo_lo_qkv,
                              const float* __restrict__ qkv_bias, const TB* __restrict__ earth_bias,
                              __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ halo_out, WinGeom g,
                              BandGeom bd, int roll, int lon_chunk) {
@@ -66,12 +69,13 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
   __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(smem);                       // [144][152]
   uint8_t* s_buf = smem + kWinTokens * kBiasPitch * 2;                                  // 2 x {q,k,v}
   int* s_rowbase = reinterpret_cast<int*>(s_buf + 2 * kBufBytes);                       // [144] (z*H+h)*W or -1
-  int* s_dw = s_rowbase + kWinTokens;                                                   // [144]
+  int* s_dw = s_rowbase + kWinTokens;                                                   // [144] dw | row class << 8
   uint8_t* s_gid = reinterpret_cast<uint8_t*>(s_dw + kWinTokens);                       // [144]
 
   // Latitude band (pangu_b200/dist.py): this launch covers bd.nhw h-windows starting at global window bd.hw0
   // (the last one being the global wrap window nH-1 when bd.wrap); qkv/out hold rows [bd.h0, bd.h0+bd.hrows) of
-  // the global grid, halo_qkv/halo_out the bd.halo rows that follow.  Full grid: {0, H, 0, nH, 0, 0}.
+  // the global grid, halo_qkv/halo_out the bd.halo rows that follow, halo_lo_qkv the bd.halo_lo rows that
+  // precede them.  Row classes: 0 pad, 1 own, 2 southern halo, 3 northern halo.  Full grid: {0, H, 0, nH, 0, 0, 0}.
   const int head = blockIdx.x, lchunk = blockIdx.y;
   const int zw_ = blockIdx.z / bd.nhw, hwl_ = blockIdx.z - zw_ * bd.nhw;
   const int t = zw_ * g.nH + ((bd.wrap && hwl_ == bd.nhw - 1) ? g.nH - 1 : bd.hw0 + hwl_);
@@ -88,16 +92,17 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
     if (roll == 1) { z += 1; if (z >= g.Z) z -= g.Z; h += 3; if (h >= g.Hp) h -= g.Hp; }
     if (roll == 2) {                                        // pre-partitioned windows: identity map
       s_rowbase[k] = t * kWinTokens + k;
-      s_dw[k] = 0;
+      s_dw[k] = 1 << 8;
     } else {
       const int hl = h - bd.h0;
-      int rb = -1;                                            // zero pad row (or outside this band: never selected)
+      int rb = -1, cls = 0;                                   // zero pad row (or outside this band: never selected)
       if (h < g.H) {
-        if (hl >= 0 && hl < bd.hrows) rb = (z * bd.hrows + hl) * g.W;
-        else if (hl >= bd.hrows && hl < bd.hrows + bd.halo) rb = -2 - (z * bd.halo + (hl - bd.hrows)) * g.W;
+        if (hl >= 0 && hl < bd.hrows) { rb = (z * bd.hrows + hl) * g.W; cls = 1; }
+        else if (hl >= bd.hrows && hl < bd.hrows + bd.halo) { rb = (z * bd.halo + (hl - bd.hrows)) * g.W; cls = 2; }
+        else if (hl < 0 && hl >= -bd.halo_lo) { rb = (z * bd.halo_lo + (hl + bd.halo_lo)) * g.W; cls = 3; }
       }
       s_rowbase[k] = rb;
-      s_dw[k] = dw;
+      s_dw[k] = dw | (cls << 8);
     }
     s_gid[k] = (uint8_t)shift_group(g, t, k);
   }
@@ -120,13 +125,12 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
   }
   __syncthreads();
 
-  // token of window element k in longitude window l: index into qkv/out (rb >= 0) or into the halo
-  // buffers (rb <= -2, offset -2 - rb)
+  // token of window element k in longitude window l: index into the buffer of the element's row class
   auto token_of = [&](int l, int k, int rb) -> long long {
     if (roll == 2) return (long long)l * g.T * kWinTokens + rb;
-    int w = 12 * l + (roll == 1 ? 6 : 0) + s_dw[k];
+    int w = 12 * l + (roll == 1 ? 6 : 0) + (s_dw[k] & 0xff);
     if (w >= g.W) w -= g.W;
-    return (long long)(rb >= 0 ? rb : -2 - rb) + w;
+    return (long long)rb + w;
   };
   // issue the gather of window l into buffer b: 144 tokens x {q,k,v} x 4 chunks of 16 B
   auto issue_load = [&](int l, int b) {
@@ -135,9 +139,10 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
       const int k = i / 12, part = i - k * 12, s = part >> 2, c = part & 3;
       uint8_t* dst = buf + s * kTileBytes + tile_off(k, c);
       const int rb = s_rowbase[k];
-      if (rb != -1) {
-        const __nv_bfloat16* src = (rb >= 0 ? qkv : halo_qkv) + token_of(l, k, rb) * 3 * C + s * C + head * kHeadDim + c * 8;
-        cp_async16(smem_u32(dst), src);
+      const int cls = s_dw[k] >> 8;
+      if (cls != 0) {
+        const __nv_bfloat16* base = cls == 1 ? qkv : (cls == 2 ? halo_qkv : halo_lo_qkv);
+        cp_async16(smem_u32(dst), base + token_of(l, k, rb) * 3 * C + s * C + head * kHeadDim + c * 8);
       } else {                                            // zero pad row: linear1(0) = bias (layers.py:228,419)
         const float* bsrc = qkv_bias + s * C + head * kHeadDim + c * 8;
         uint4 o;
@@ -270,9 +275,11 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
       for (int i = 0; i < 2; ++i) {
         const int idx = lane + i * 32, r = row0 + (idx >> 2), c = idx & 3;
         const int rb = s_rowbase[r];
-        if (rb != -1) {                                     // pad rows are cropped (layers.py:287-288)
+        const int cls = s_dw[r] >> 8;                       // pad rows are cropped (layers.py:287-288); halo rows
+        __nv_bfloat16* dstp = cls == 1 ? out : (cls == 2 ? halo_out : nullptr);   // belong to a neighbour
+        if (dstp != nullptr) {
           const uint4 val = *reinterpret_cast<const uint4*>(sq + tile_off(r, c));
-          *reinterpret_cast<uint4*>((rb >= 0 ? out : halo_out) + token_of(l, r, rb) * C + head * kHeadDim + c * 8) = val;
+          *reinterpret_cast<uint4*>(dstp + token_of(l, r, rb) * C + head * kHeadDim + c * 8) = val;
         }
       }
     }
@@ -283,26 +290,37 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
 
 }  // namespace attn
 
-int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const float* qkv_bias, const void* earth_bias,
+int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias, const void* earth_bias,
                                  int bias_dtype, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
                                  int roll, cudaStream_t st) {
   using namespace attn;
-  const int lon_chunk = g.nLon % 5 == 0 ? 5 : (g.nLon % 3 == 0 ? 3 : (g.nLon % 2 == 0 ? 2 : 1));
   if (bd.nhw <= 0) return PANGU_OK;
+  // longitude windows per CTA (they share the staged bias tile): as many as possible (<= 5) while the grid
+  // still fills the GPU for at least ~4 waves of 2 CTAs/SM -- small latitude bands get finer CTAs
+  int lon_chunk = 1;
+  const long long per_l = (long long)g.heads * g.nZ * bd.nhw;          // CTAs per longitude window column
+  const int cands[4] = {5, 3, 2, 1};
+  for (int c : cands) {
+    if (g.nLon % c) continue;
+    lon_chunk = c;
+    if (per_l * (g.nLon / c) >= 8LL * tc_num_sms()) break;
+  }
   dim3 grid((unsigned)g.heads, (unsigned)((g.nLon + lon_chunk - 1) / lon_chunk), (unsigned)(g.nZ * bd.nhw));
   cudaError_t e;
   if (bias_dtype == PANGU_BF16) {
     auto kern = window_attention_bf16_kernel<__nv_bfloat16>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) { set_error("attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)halo_qkv, qkv_bias,
+    kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)halo_qkv,
+                                             (const __nv_bfloat16*)halo_lo_qkv, qkv_bias,
                                              (const __nv_bfloat16*)earth_bias, (__nv_bfloat16*)out,
                                              (__nv_bfloat16*)halo_out, g, bd, roll, lon_chunk);
   } else if (bias_dtype == PANGU_F32) {
     auto kern = window_attention_bf16_kernel<float>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) { set_error("attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)halo_qkv, qkv_bias,
+    kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)halo_qkv,
+                                             (const __nv_bfloat16*)halo_lo_qkv, qkv_bias,
                                              (const float*)earth_bias, (__nv_bfloat16*)out, (__nv_bfloat16*)halo_out,
                                              g, bd, roll, lon_chunk);
   } else {

@@ -11,14 +11,21 @@ the last rank taking the remainder (up to row 180 / 90 / 720 plus the reference'
 except the shifted-window attention is row-local: patch embed / recover are 4x4 pixel patches, down / up-sample
 pair rows (2i, 2i+1), linears / LayerNorm / Mlp are per token, un-rolled windows (models/layers.py:253-262) are
 aligned to the band edges.  In a rolled block (torch.roll by (-1,-3,-6), models/layers.py:237) the h-window hw
-reads rows [6 hw + 3, 6 hw + 9): each rank runs the windows whose first source row it owns, which needs the
-FIRST 3 ROWS of its southern neighbour's qkv (exchange "up") and produces the attention output of those 3
-rows, returned to the neighbour (exchange "down").  The wrap-around window (3 pad rows + global rows 0..2) is
-isolated by the -100 shift mask (models/layers.py:187-216), so rank 0 computes it locally.
+reads rows [6 hw + 3, 6 hw + 9), so one window straddles every band edge.  Two exchange schemes:
 
-The exchanges are NCCL point-to-point (`torch.distributed.batch_isend_irecv`) of 3*8*W*3C / 3*8*W*C bf16
-(about 10 MB / 3.3 MB); a `LocalComm` runs all ranks of a plan inside ONE process (tests on a single GPU:
-the banded result must equal the un-sharded forward).
+  "redundant" (default)  ONE bidirectional exchange per rolled block: each rank receives the first 3 qkv rows of
+                         its southern neighbour and the last 3 qkv rows of its northern neighbour, BOTH ranks run
+                         the straddling window and each keeps only its own rows;
+  "sendback"             each rank runs the windows whose first source row it owns: receives the southern
+                         neighbour's first 3 qkv rows, then returns the attention output of those 3 rows
+                         (two dependent exchanges per rolled block, no duplicated window).
+
+The wrap-around window (3 pad rows + global rows 0..2) is isolated by the -100 shift mask
+(models/layers.py:187-216), so rank 0 computes it locally.
+
+The exchanges are NCCL point-to-point (`torch.distributed.batch_isend_irecv`) of 3*8*W*3C bf16 (about 10 MB per
+direction); a `LocalComm` runs all ranks of a plan inside ONE process (tests on a single GPU: the banded result
+must equal the un-sharded forward bit for bit).
 """
 import torch
 import torch.distributed as dist
@@ -53,19 +60,22 @@ class BandPlan:
         r = self.rows[stage]
         return r[1] - r[0]
 
-    def band(self, stage, roll):
+    def band(self, stage, roll, scheme="redundant"):
         """pangu_band of this rank for one block of `stage` (models/layers.py:228: 5 pad rows, 6-row windows)."""
         h0, h1 = self.rows[stage]
         nH = (TOK_H[stage] + 5) // 6
         hw0 = h0 // 6
         if not roll:
             hw1 = nH if self.last else h1 // 6
-            return Band(h0, h1 - h0, hw0, hw1 - hw0, 0, 0)
+            return Band(h0, h1 - h0, hw0, hw1 - hw0, 0, 0, 0)
         # rolled: regular windows [hw0, hw1); the global window nH-1 wraps around to rows 0..2 -> rank 0
         hw1 = nH - 1 if self.last else h1 // 6
         wrap = 1 if self.first else 0
         halo = 0 if self.last else 3
-        return Band(h0, h1 - h0, hw0, hw1 - hw0 + wrap, wrap, halo)
+        halo_lo = 0
+        if scheme == "redundant" and not self.first:      # also run the window straddling the northern edge
+            hw0, halo_lo = hw0 - 1, 3
+        return Band(h0, h1 - h0, hw0, hw1 - hw0 + wrap, wrap, halo, halo_lo)
 
     def slice_inputs(self, input, input_surface, maps, const_h):
         """Band of the full-grid arrays (contiguous copies): what this rank is handed in a sharded deployment."""
@@ -109,6 +119,23 @@ class DistComm:
     def shift_down(self, sends, recv_like):
         return [self._exchange(sends[0], recv_like[0], self.rank + 1, self.rank - 1)]
 
+    def swap_edges(self, first_rows, last_rows, like):
+        """One batched exchange: my first rows go north, my last rows go south.
+        -> [(rows received from the south, rows received from the north)] (None at the grid edges)."""
+        opsl, from_s, from_n = [], None, None
+        if self.rank > 0:
+            opsl.append(dist.P2POp(dist.isend, first_rows[0], self._peer(self.rank - 1), self.group))
+            from_n = torch.empty_like(like[0])
+            opsl.append(dist.P2POp(dist.irecv, from_n, self._peer(self.rank - 1), self.group))
+        if self.rank < self.world - 1:
+            opsl.append(dist.P2POp(dist.isend, last_rows[0], self._peer(self.rank + 1), self.group))
+            from_s = torch.empty_like(like[0])
+            opsl.append(dist.P2POp(dist.irecv, from_s, self._peer(self.rank + 1), self.group))
+        if opsl:
+            for w in dist.batch_isend_irecv(opsl):
+                w.wait()
+        return [(from_s, from_n)]
+
 
 class LocalComm:
     """All ranks of a plan in one process: lists are indexed by rank."""
@@ -122,6 +149,10 @@ class LocalComm:
     def shift_down(self, sends, recv_like):
         return [sends[r - 1] if r >= 1 and recv_like[r] is not None else None for r in range(self.world)]
 
+    def swap_edges(self, first_rows, last_rows, like):
+        return [(first_rows[r + 1] if r + 1 < self.world else None, last_rows[r - 1] if r >= 1 else None)
+                for r in range(self.world)]
+
 
 # ----------------------------------------------------------------------------------------------
 class _Worker:
@@ -129,7 +160,7 @@ class _Worker:
 
     def __init__(self, model, plan):
         self.m, self.plan = model, plan
-        self.x = self.xb = self.skip = self.qkv = self.o = self.halo_qkv = self.halo_o = None
+        self.x = self.xb = self.skip = self.qkv = self.o = self.halo_qkv = self.halo_lo_qkv = self.halo_o = None
 
     # --- row-local stages
     def embed(self, inp, inp_s, stats, maps, const_h):
@@ -160,13 +191,18 @@ class _Worker:
         hr, W = self.plan.nrows(stage), TOK_W[stage]
         return t.view(Z, hr, W, t.shape[-1])[:, :rows].reshape(Z * rows * W, t.shape[-1]).contiguous()
 
-    def block_attend(self, blk, stage, roll):
+    def last_rows(self, t, stage, rows=3):
+        hr, W = self.plan.nrows(stage), TOK_W[stage]
+        return t.view(Z, hr, W, t.shape[-1])[:, hr - rows:].reshape(Z * rows * W, t.shape[-1]).contiguous()
+
+    def block_attend(self, blk, stage, roll, scheme):
         att, wc = blk.attention, blk._wcache
-        band = self.plan.band(stage, roll)
+        band = self.plan.band(stage, roll, scheme)
         self.o, self.halo_o = ops.window_attention_band(
             self.qkv, self.halo_qkv, PF._f(att.linear1.bias), wc.bf16("eb", att.earth_specific_bias), Z, TOK_H[stage],
-            TOK_W[stage], att.head_number, band, roll)
-        self.qkv = self.halo_qkv = None
+            TOK_W[stage], att.head_number, band, roll, halo_lo_qkv=self.halo_lo_qkv,
+            return_halo=(scheme == "sendback"))
+        self.qkv = self.halo_qkv = self.halo_lo_qkv = None
 
     def block_finish(self, blk, stage, o_first):
         att, mlp, wc = blk.attention, blk.linear, blk._wcache
@@ -181,8 +217,13 @@ class _Worker:
                                                    PF._f(blk.norm2.weight), PF._f(blk.norm2.bias), x1, eps=blk.norm2.eps)
 
 
-def _run(model, workers, comm, inputs):
+SCHEMES = ("redundant", "sendback")
+
+
+def _run(model, workers, comm, inputs, scheme="redundant"):
     """Drive the workers (one per local rank) through the network; `comm` moves the halos between them."""
+    if scheme not in SCHEMES:
+        raise PanguError(f"exchange scheme {scheme!r}: expected one of {SCHEMES}")
     n = len(workers)
     for w, (inp, inp_s, stats, maps, const_h) in zip(workers, inputs):
         w.embed(inp, inp_s, stats, maps, const_h)
@@ -200,16 +241,22 @@ def _run(model, workers, comm, inputs):
             for w in workers:
                 w.block_qkv(blk, stage)
             exchange = roll and comm.world > 1
-            if exchange:
+            if exchange and scheme == "redundant":
+                firsts_ = [None if w.plan.first else w.first_rows(w.qkv, stage) for w in workers]
+                lasts_ = [None if w.plan.last else w.last_rows(w.qkv, stage) for w in workers]
+                like = [_halo_like(w.qkv, stage) for w in workers]
+                for w, (south, north) in zip(workers, comm.swap_edges(firsts_, lasts_, like)):
+                    w.halo_qkv, w.halo_lo_qkv = south, north
+            elif exchange:
                 sends = [None if w.plan.first else w.first_rows(w.qkv, stage) for w in workers]
                 like = [None if w.plan.last else _halo_like(w.qkv, stage) for w in workers]
                 halos = comm.shift_up(sends, like)
                 for w, h in zip(workers, halos):
                     w.halo_qkv = h
             for w in workers:
-                w.block_attend(blk, stage, roll)
+                w.block_attend(blk, stage, roll, scheme)
             firsts = [None] * n
-            if exchange:
+            if exchange and scheme == "sendback":
                 sends = [w.halo_o for w in workers]
                 like = [None if w.plan.first else _halo_like(w.o, stage) for w in workers]
                 firsts = comm.shift_down(sends, like)
@@ -238,9 +285,10 @@ class BandedPangu:
     Inputs are ONE sample's band: input [5,13,rows,1440], input_surface [4,rows,1440], maps [.,3,4*tok_rows,1440],
     const_h [...,13,rows,1440]; outputs [1,5,13,rows,1440] and [1,4,rows,1440] are the same rows of the forecast."""
 
-    def __init__(self, model, group=None, comm=None):
+    def __init__(self, model, group=None, comm=None, scheme="redundant"):
         _check_model(model)
         self.model = model
+        self.scheme = scheme
         self.comm = comm if comm is not None else DistComm(group)
         self.plan = BandPlan(self.comm.world, self.comm.rank)
 
@@ -250,11 +298,12 @@ class BandedPangu:
         stats = tuple(s.to(dev) for s in statistics)
         w = _Worker(self.model, self.plan)
         return _run(self.model, [w], self.comm, [(inp.float().contiguous(), inp_s.float().contiguous(), stats,
-                                                  maps.float().contiguous(), const_h.float().contiguous())])[0]
+                                                  maps.float().contiguous(), const_h.float().contiguous())],
+                    self.scheme)[0]
 
 
 @torch.no_grad()
-def emulate_bands(model, world, input, input_surface, statistics, maps, const_h):
+def emulate_bands(model, world, input, input_surface, statistics, maps, const_h, scheme="redundant"):
     """Run all `world` bands of one full-grid sample in THIS process (LocalComm) and stitch the outputs:
     (output [1,5,13,721,1440], output_surface [1,4,721,1440]).  Used by the single-GPU parity tests."""
     _check_model(model)
@@ -265,5 +314,5 @@ def emulate_bands(model, world, input, input_surface, statistics, maps, const_h)
     for p in plans:
         a, b, m, c = p.slice_inputs(input.float(), input_surface.float(), maps.float(), const_h.float())
         inputs.append((a.reshape(5, 13, -1, 1440), b.reshape(4, -1, 1440), stats, m, c))
-    outs = _run(model, [_Worker(model, p) for p in plans], LocalComm(world), inputs)
+    outs = _run(model, [_Worker(model, p) for p in plans], LocalComm(world), inputs, scheme)
     return torch.cat([o[0] for o in outs], dim=3), torch.cat([o[1] for o in outs], dim=2)

@@ -199,9 +199,12 @@ def window_attention(qkv, qkv_bias, earth_bias, Z, H, W, heads, mode):
     return out
 
 
-def window_attention_band(qkv, halo_qkv, qkv_bias, earth_bias, Z, H, W, heads, band, roll):
+def window_attention_band(qkv, halo_qkv, qkv_bias, earth_bias, Z, H, W, heads, band, roll, halo_lo_qkv=None,
+                          return_halo=True):
     """Band-sharded window attention (bf16): qkv [Z*hrows*W, 3C] holds the band's own rows of the GLOBAL
-    (Z, H, W) grid, halo_qkv [Z*halo*W, 3C] the southern neighbour's first rows.  -> (out, halo_out)."""
+    (Z, H, W) grid, halo_qkv [Z*halo*W, 3C] the southern neighbour's first rows, halo_lo_qkv the northern
+    neighbour's last rows.  -> (out, halo_out): halo_out (attention output of the southern halo rows, to be sent
+    back) only when return_halo, else None (the neighbour computes those rows itself)."""
     _chk(qkv, torch.bfloat16, "qkv")
     _chk(qkv_bias, torch.float32, "qkv_bias")
     _chk(earth_bias, name="earth_bias")
@@ -210,16 +213,18 @@ def window_attention_band(qkv, halo_qkv, qkv_bias, earth_bias, Z, H, W, heads, b
         raise abi.PanguError(f"qkv has {qkv.shape[0]} rows, band expects {Z * band.hrows * W}")
     out = torch.empty((qkv.shape[0], C), dtype=qkv.dtype, device=qkv.device)
     halo_out = None
-    if band.halo:
-        _chk(halo_qkv, torch.bfloat16, "halo_qkv")
-        if halo_qkv.shape[0] != Z * band.halo * W:
-            raise abi.PanguError("halo_qkv has the wrong number of rows")
+    for t, n, nm in ((halo_qkv, band.halo, "halo_qkv"), (halo_lo_qkv, band.halo_lo, "halo_lo_qkv")):
+        if n:
+            _chk(t, torch.bfloat16, nm)
+            if t.shape[0] != Z * n * W:
+                raise abi.PanguError(f"{nm} has the wrong number of rows")
+    if band.halo and return_halo:
         halo_out = torch.empty((Z * band.halo * W, C), dtype=qkv.dtype, device=qkv.device)
     g = geom(Z, H, W, C, heads)
     nwin = (W // 12) * (Z // 2) * band.nhw
     _call("attention_bf16[C=%d]" % C, "pangu_window_attention_band",
-          (_ptr(qkv), _ptr(halo_qkv) if band.halo else None, _ptr(qkv_bias), _ptr(earth_bias), _DT[earth_bias.dtype],
-           _ptr(out), _ptr(halo_out), g, band, int(roll), _stream(),),
+          (_ptr(qkv), _ptr(halo_qkv) if band.halo else None, _ptr(halo_lo_qkv) if band.halo_lo else None, _ptr(qkv_bias),
+           _ptr(earth_bias), _DT[earth_bias.dtype], _ptr(out), _ptr(halo_out), g, band, int(roll), _stream(),),
           flops=nwin * heads * 4.0 * 144 * 144 * 32,
           nbytes=float(qkv.numel() * 2 + out.numel() * 2 + earth_bias.numel() * earth_bias.element_size() * band.nhw / ((H + 5) // 6)))
     return out, halo_out

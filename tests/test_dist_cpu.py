@@ -27,11 +27,14 @@ def test_band_plans_tile_the_grid(world):
         for roll in (0, 1):
             seen = []
             for p in plans:
-                b = p.band(stage, roll)
+                b = p.band(stage, roll, "sendback")
                 regular = b.nhw - b.wrap
                 seen += list(range(b.hw0, b.hw0 + regular)) + ([nH - 1] if b.wrap else [])
                 assert (b.h0, b.h0 + b.hrows) == p.rows[stage]
-                assert b.halo == (3 if (roll and not p.last) else 0)
+                assert b.halo == (3 if (roll and not p.last) else 0) and b.halo_lo == 0
+                r = p.band(stage, roll, "redundant")      # additionally the window straddling the northern edge
+                extra = 1 if (roll and not p.first) else 0
+                assert (r.hw0, r.nhw, r.halo_lo, r.halo, r.wrap) == (b.hw0 - extra, b.nhw + extra, 3 * extra, b.halo, b.wrap)
             assert sorted(seen) == list(range(nH)), (stage, roll, seen)
     pix = [p.pix for p in plans]
     assert pix[0][0] == 0 and pix[-1][1] == 721 and all(pix[i][1] == pix[i + 1][0] for i in range(world - 1))
@@ -53,7 +56,7 @@ def test_rolled_windows_only_need_own_halo_or_pad_rows(world, stage, W):
         owner_of_output = {}
         for r in range(world):
             p = BandPlan(world, r)
-            b = p.band(stage, int(roll))
+            b = p.band(stage, int(roll), "sendback")
             hws = list(range(b.hw0, b.hw0 + b.nhw - b.wrap)) + ([nH - 1] if b.wrap else [])
             for hw in hws:
                 need = np.unique(rows[:, :, hw])
@@ -62,6 +65,15 @@ def test_rolled_windows_only_need_own_halo_or_pad_rows(world, stage, W):
                 assert ok.all(), (world, stage, roll, r, hw, need)
                 for h in need:
                     owner_of_output.setdefault(int(h), []).append(r)
+            # "redundant" scheme: own rows are covered by windows whose rows are own / 3-row halos / pad
+            rb = p.band(stage, int(roll), "redundant")
+            covered = set()
+            for hw in list(range(rb.hw0, rb.hw0 + rb.nhw - rb.wrap)) + ([nH - 1] if rb.wrap else []):
+                need = np.unique(rows[:, :, hw])
+                need = need[need >= 0]
+                assert ((need >= rb.h0 - rb.halo_lo) & (need < rb.h0 + rb.hrows + rb.halo)).all()
+                covered |= set(int(h) for h in need)
+            assert set(range(rb.h0, rb.h0 + rb.hrows)) <= covered
         # every real row is produced exactly once (8 z-planes share the same h)
         assert sorted(owner_of_output) == list(range(H))
         assert all(len(set(v)) == 1 for v in owner_of_output.values())
@@ -74,6 +86,16 @@ def test_local_comm_shifts():
     assert up[0][0] == 1 and up[1][0] == 2 and up[2] is None
     down = c.shift_down(sends, [None, sends[0], sends[0]])
     assert down[0] is None and down[1][0] == 0 and down[2][0] == 1
+
+
+def test_local_comm_swap_edges():
+    c = LocalComm(3)
+    first = [torch.full((1,), 10.0 + r) for r in range(3)]
+    last = [torch.full((1,), 20.0 + r) for r in range(3)]
+    got = c.swap_edges(first, last, first)
+    assert got[0][0][0] == 11 and got[0][1] is None          # rank 0: south = rank 1's first rows, no north
+    assert got[1][0][0] == 12 and got[1][1][0] == 20
+    assert got[2][0] is None and got[2][1][0] == 21
 
 
 def _free_port():
@@ -96,7 +118,9 @@ def _exchange_worker(rank, world, port, q):
         like = torch.empty(8 * 3 * W, F)
         up = comm.shift_up([None if plan.first else first], [None if plan.last else like])[0]
         down = comm.shift_down([None if plan.last else first * 2], [None if plan.first else like])[0]
-        q.put((rank, None if up is None else up.clone(), None if down is None else down.clone(), first.clone()))
+        south, north = comm.swap_edges([first], [first + 7], [like])[0]
+        q.put((rank, None if up is None else up.clone(), None if down is None else down.clone(), first.clone(),
+               None if south is None else south.clone(), None if north is None else north.clone()))
     finally:
         dist.destroy_process_group()
 
@@ -110,11 +134,13 @@ def test_dist_comm_neighbour_exchange_gloo_world2():
         p.start()
     got = {}
     for _ in range(world):
-        rank, up, down, first = q.get(timeout=120)
-        got[rank] = (up, down, first)
+        rank, up, down, first, south, north = q.get(timeout=120)
+        got[rank] = (up, down, first, south, north)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert torch.equal(got[0][0], got[1][2]), "rank 0 receives rank 1's first three rows"
     assert got[1][0] is None and got[0][1] is None
     assert torch.equal(got[1][1], got[0][2] * 2), "rank 1 receives what rank 0 computed for it"
+    assert torch.equal(got[0][3], got[1][2]) and got[0][4] is None      # swap_edges: south halo of rank 0
+    assert torch.equal(got[1][4], got[0][2] + 7) and got[1][3] is None  # north halo of rank 1

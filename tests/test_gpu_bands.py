@@ -21,11 +21,12 @@ def model_and_inputs():
     return model, args, want
 
 
-@pytest.mark.parametrize("world", [1, 2, 4, 8])
-def test_banded_forward_equals_unsharded(model_and_inputs, world):
+@pytest.mark.parametrize("world,scheme", [(1, "redundant"), (2, "redundant"), (4, "redundant"), (8, "redundant"),
+                                          (2, "sendback"), (8, "sendback")])
+def test_banded_forward_equals_unsharded(model_and_inputs, world, scheme):
     from pangu_b200.dist import emulate_bands
     model, args, want = model_and_inputs
-    out, out_s = emulate_bands(model, world, *args)
+    out, out_s = emulate_bands(model, world, *args, scheme=scheme)
     assert out.shape == want[0].shape and out_s.shape == want[1].shape
     e0, e1 = orc.rel_l2(out.cpu(), want[0].cpu()), orc.rel_l2(out_s.cpu(), want[1].cpu())
     print(f"bands={world}: rel-L2 vs un-sharded: output {e0:.2e} surface {e1:.2e}")
@@ -41,4 +42,21 @@ def test_band_attention_rejects_inconsistent_band():
     qb = torch.zeros(3 * 192, device="cuda")
     eb = torch.zeros(124, 6, 144, 144, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(PanguError):                     # rolled windows 0..3 need 3 halo rows
-        ops.window_attention_band(qkv, None, qb, eb, 8, 181, 24, 6, Band(0, 24, 0, 4, 0, 0), 1)
+        ops.window_attention_band(qkv, None, qb, eb, 8, 181, 24, 6, Band(0, 24, 0, 4, 0, 0, 0), 1)
+
+
+def test_cuda_graph_replay_equals_eager(model_and_inputs):
+    """pangu_b200.graph.GraphedForward: the captured step replays to the same bits, for new inputs too."""
+    from pangu_b200.graph import GraphedForward
+    model, args, want = model_and_inputs
+    fwd = GraphedForward(model, args)
+    out, out_s = fwd(args[0], args[1])
+    torch.cuda.synchronize()
+    assert torch.equal(out, want[0]) and torch.equal(out_s, want[1])
+    inp2, inp_s2 = args[0] * 0.5 + 0.1, args[1] * 0.5 - 0.2
+    with torch.no_grad():
+        want2 = model(inp2, inp_s2, *args[2:])
+    out2, out_s2 = fwd(inp2, inp_s2)
+    torch.cuda.synchronize()
+    assert torch.equal(out2, want2[0]) and torch.equal(out_s2, want2[1])
+    assert fwd.launches_per_replay > 50
