@@ -188,6 +188,15 @@ int pangu_patch_recover_scatter_rows(const float* y_upper, const float* y_surfac
                                      float* output_surface, int32_t lat_rows, int32_t tok_rows,
                                      void* stream);
 
+/* Same with the de-normalisation of era5_data/utils_data.py:540-546 (normBackData: x * std + mean) folded into
+ * the scatter -- the step between two chained forecasts (inference/inference_mix_multiOutput.py:238).
+ * upper_std/mean [5*13] indexed v*13 + level in DATA level order (weatherStatistics_output,
+ * era5_data/utils_data.py:395-421), surface_std/mean [4]; all four NULL = normalised output. */
+int pangu_patch_recover_scatter_denorm(const float* y_upper, const float* y_surface, float* output,
+                                       float* output_surface, int32_t lat_rows, int32_t tok_rows,
+                                       const float* upper_std, const float* upper_mean,
+                                       const float* surface_std, const float* surface_mean, void* stream);
+
 /* DownSample.forward before the linear (models/layers.py:501-519): pad H to even, 2x2 merge
  * (feature = dh*2C + dw*C + c), LayerNorm(4C).  x fp32 [Z*H*W, C] -> out [Z*ceil(H/2)*(W/2), 4C]. */
 int pangu_downsample_merge_ln(const float* x, const float* gamma, const float* beta, void* out,

@@ -55,7 +55,7 @@ class PanguModel(_B200Module):
     def set_compute_dtype(self, mode):
         return set_compute_dtype(self, mode)
 
-    def forward_sample(self, inp, inp_s, stats, maps, const_h):
+    def forward_sample(self, inp, inp_s, stats, maps, const_h, denorm=None):
         """One sample through models/pangu_model.py:61-104; the bf16 shadow of the residual stream is
         handed from kernel to kernel so that no separate cast pass is needed."""
         mode = self._mode()
@@ -67,7 +67,7 @@ class PanguModel(_B200Module):
         x, xb = self.layers[2].forward_sample(x, 8, 91, 180, xb)
         x, xb = self.upsample.forward_sample(x, xb)
         x, xb = self.layers[3].forward_sample(x, 8, 181, 360, xb)
-        return self._output_layer.forward_sample(x, 8, 181, 360, skip=skip)
+        return self._output_layer.forward_sample(x, 8, 181, 360, skip=skip, denorm=denorm)
 
     def forward(self, input, input_surface, statistics, maps, const_h):
         _no_training_graph(self, input, input_surface)

@@ -55,6 +55,7 @@ _PROTOS = {
     "pangu_patch_embed_gather_rows": (c_int, [c_void_p] * 10 + [c_int, c_int32, c_int32, c_int32, c_void_p]),
     "pangu_patch_recover_scatter": (c_int, [c_void_p] * 5),
     "pangu_patch_recover_scatter_rows": (c_int, [c_void_p] * 4 + [c_int32, c_int32, c_void_p]),
+    "pangu_patch_recover_scatter_denorm": (c_int, [c_void_p] * 4 + [c_int32, c_int32] + [c_void_p] * 5),
     "pangu_downsample_merge_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int32, c_int32, c_int32,
                                           c_int32, c_float, c_void_p]),
     "pangu_upsample_shuffle_ln": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int32, c_int32,

@@ -108,7 +108,8 @@ patch_embed_surface_kernel(const float* __restrict__ input_surface, const float*
 // Un-patchify (layers.py:593-603 upper, :609-619 surface).  One CTA = 32 tokens along w'.
 template <int kF, int kRows, bool kUpper>
 __global__ void __launch_bounds__(256)
-patch_recover_kernel(const float* __restrict__ y, float* __restrict__ out, int lat, int tokH) {
+patch_recover_kernel(const float* __restrict__ y, float* __restrict__ out, int lat, int tokH,
+                     const float* __restrict__ scale, const float* __restrict__ shift) {
   constexpr int PITCH = kF + 1;
   __shared__ float tile[kTileTok * PITCH];
   const int w0 = blockIdx.x * kTileTok, hp = blockIdx.y, zp = blockIdx.z;
@@ -131,7 +132,12 @@ patch_recover_kernel(const float* __restrict__ y, float* __restrict__ out, int l
     }
     const float* s = tile + tok * PITCH + r * 4;
     const long long plane = kUpper ? ((long long)v * kLev + lev) : (long long)v;
-    *reinterpret_cast<float4*>(out + (plane * lat + yy) * kLon + 4 * (w0 + tok)) = make_float4(s[0], s[1], s[2], s[3]);
+    float4 o = make_float4(s[0], s[1], s[2], s[3]);
+    if (scale != nullptr) {                           // physical units: x * std + mean (era5_data/utils_data.py:540-546)
+      const float a = __ldg(scale + plane), b = __ldg(shift + plane);
+      o.x = fmaf(o.x, a, b); o.y = fmaf(o.y, a, b); o.z = fmaf(o.z, a, b); o.w = fmaf(o.w, a, b);
+    }
+    *reinterpret_cast<float4*>(out + (plane * lat + yy) * kLon + 4 * (w0 + tok)) = o;
   }
 }
 
@@ -270,16 +276,27 @@ extern "C" int pangu_patch_embed_gather(const float* input, const float* input_s
                                        const_h, patches_surface, patches_upper, out_dtype, kLat, kTokH, kLatPad, stream);
 }
 
-extern "C" int pangu_patch_recover_scatter_rows(const float* y_upper, const float* y_surface, float* output,
-                                                float* output_surface, int32_t lat_rows, int32_t tok_rows,
-                                                void* stream) {
+extern "C" int pangu_patch_recover_scatter_denorm(const float* y_upper, const float* y_surface, float* output,
+                                                  float* output_surface, int32_t lat_rows, int32_t tok_rows,
+                                                  const float* upper_std, const float* upper_mean,
+                                                  const float* surface_std, const float* surface_mean,
+                                                  void* stream) {
   if (!y_upper || !y_surface || !output || !output_surface) { set_error("patch_recover_scatter: null pointer"); return PANGU_ERR_BAD_ARG; }
   if (lat_rows <= 0 || tok_rows <= 0 || 4 * tok_rows < lat_rows) { set_error("patch_recover_scatter: inconsistent rows"); return PANGU_ERR_BAD_ARG; }
   cudaStream_t st = as_stream(stream);
   dim3 gu((kTokW + kTileTok - 1) / kTileTok, tok_rows, 7), gs((kTokW + kTileTok - 1) / kTileTok, tok_rows, 1);
-  patch_recover_kernel<160, 40, true><<<gu, 256, 0, st>>>(y_upper, output, lat_rows, tok_rows);
-  patch_recover_kernel<64, 16, false><<<gs, 256, 0, st>>>(y_surface, output_surface, lat_rows, tok_rows);
+  if ((upper_std == nullptr) != (upper_mean == nullptr) || (surface_std == nullptr) != (surface_mean == nullptr) ||
+      (upper_std == nullptr) != (surface_std == nullptr)) { set_error("patch_recover_scatter: give all four statistics or none"); return PANGU_ERR_BAD_ARG; }
+  patch_recover_kernel<160, 40, true><<<gu, 256, 0, st>>>(y_upper, output, lat_rows, tok_rows, upper_std, upper_mean);
+  patch_recover_kernel<64, 16, false><<<gs, 256, 0, st>>>(y_surface, output_surface, lat_rows, tok_rows, surface_std, surface_mean);
   return check_launch("patch_recover_scatter");
+}
+
+extern "C" int pangu_patch_recover_scatter_rows(const float* y_upper, const float* y_surface, float* output,
+                                                float* output_surface, int32_t lat_rows, int32_t tok_rows,
+                                                void* stream) {
+  return pangu_patch_recover_scatter_denorm(y_upper, y_surface, output, output_surface, lat_rows, tok_rows, nullptr,
+                                            nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int pangu_patch_recover_scatter(const float* y_upper, const float* y_surface, float* output,

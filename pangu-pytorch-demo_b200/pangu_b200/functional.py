@@ -180,7 +180,7 @@ def upsample_forward(us, x, mode, xb=None, Z=8, H2=91, W2=180, H=181):
     return ops.linear(n, wc.bf16("l2", us.linear2.weight), None, out_dtype=torch.float32), None
 
 
-def patch_recover_forward(pr, x, Z, H, W, mode, skip=None, lat=721):
+def patch_recover_forward(pr, x, Z, H, W, mode, skip=None, lat=721, denorm=None):
     """PatchRecovery_pretrain.forward (models/layers.py:582-621).  x [N, dim] fp32, or when `skip` is given
     the pair (skip, x) whose channel concat (models/pangu_model.py:98) is the input."""
     if (Z, W) != (8, 360) or H != (lat + 3) // 4:
@@ -192,9 +192,9 @@ def patch_recover_forward(pr, x, Z, H, W, mode, skip=None, lat=721):
             x = torch.cat((skip, x), dim=-1)
         yu = ops.linear(x[ns:], _w2d(pr.conv.weight), _f(pr.conv.bias))
         ys = ops.linear(x[:ns], _w2d(pr.conv_surface.weight), _f(pr.conv_surface.bias))
-        return ops.patch_recover_scatter(yu, ys, lat)
+        return ops.patch_recover_scatter(yu, ys, lat, denorm)
     xb = ops.concat_cast_bf16(skip, x) if skip is not None else ops.cast_bf16(x)
     wc = pr._wcache
     yu = ops.linear(xb[ns:], wc.bf16("c", pr.conv.weight), _f(pr.conv.bias), out_dtype=torch.float32)
     ys = ops.linear(xb[:ns], wc.bf16("cs", pr.conv_surface.weight), _f(pr.conv_surface.bias), out_dtype=torch.float32)
-    return ops.patch_recover_scatter(yu, ys, lat)
+    return ops.patch_recover_scatter(yu, ys, lat, denorm)

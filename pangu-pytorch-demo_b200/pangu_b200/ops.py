@@ -253,8 +253,10 @@ def patch_embed_gather(inp, inp_s, statistics, maps, const_h, out_dtype):
     return ps, pu
 
 
-def patch_recover_scatter(y_upper, y_surface, lat=721):
-    """-> output [1,5,13,lat,1440], output_surface [1,4,lat,1440]; y_* hold ceil(lat/4) token rows."""
+def patch_recover_scatter(y_upper, y_surface, lat=721, denorm=None):
+    """-> output [1,5,13,lat,1440], output_surface [1,4,lat,1440]; y_* hold ceil(lat/4) token rows.
+    denorm = (surface_mean [4], surface_std [4], upper_mean [5*13], upper_std [5*13]) fp32 device tensors in the
+    order of era5_data.utils_data.weatherStatistics_output: outputs are x * std + mean (physical units)."""
     _chk(y_upper, torch.float32, "y_upper")
     _chk(y_surface, torch.float32, "y_surface")
     dev = y_upper.device
@@ -263,8 +265,14 @@ def patch_recover_scatter(y_upper, y_surface, lat=721):
         raise abi.PanguError("patch_recover_scatter: token rows do not match the latitude extent")
     out = torch.empty((1, 5, 13, lat, 1440), dtype=torch.float32, device=dev)
     out_s = torch.empty((1, 4, lat, 1440), dtype=torch.float32, device=dev)
-    _call("patch_recover_scatter", "pangu_patch_recover_scatter_rows",
-          (_ptr(y_upper), _ptr(y_surface), _ptr(out), _ptr(out_s), lat, tok_rows, _stream(),),
+    sm = ss = um = us = None
+    if denorm is not None:
+        sm, ss, um, us = (_chk(t.reshape(-1), torch.float32, "statistics") for t in denorm)
+        if sm.numel() != 4 or ss.numel() != 4 or um.numel() != 65 or us.numel() != 65:
+            raise abi.PanguError("patch_recover_scatter: statistics must have 4 / 4 / 65 / 65 elements")
+    _call("patch_recover_scatter", "pangu_patch_recover_scatter_denorm",
+          (_ptr(y_upper), _ptr(y_surface), _ptr(out), _ptr(out_s), lat, tok_rows, _ptr(us), _ptr(um), _ptr(ss), _ptr(sm),
+           _stream(),),
           kernels=2, nbytes=float((y_upper.numel() + y_surface.numel() + out.numel() + out_s.numel()) * 4))
     return out, out_s
 
