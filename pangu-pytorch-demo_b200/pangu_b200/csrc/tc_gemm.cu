@@ -9,6 +9,8 @@
 // TMEM holds two accumulator tiles when 2*BN <= 512 columns, so the epilogue of tile i overlaps the
 // mainloop of tile i+1.  Tiles are enumerated m-major, so the N tiles that share an A tile run on
 // neighbouring CTAs at the same time and A is fetched from HBM once (the rest hits L2).
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace pangu {
@@ -390,11 +392,21 @@ static int launch_gemm_t(const void* A, long long lda, const void* W, GemmArgs& 
 
 }  // namespace tc
 
+int launch_tc_linear_pair(const void* A, long long lda, const void* W, const float* bias, void* out,
+                          long long ldo, long long M, int K, int N, int act, int out_dtype, cudaStream_t st);
+
 int launch_tc_linear(const void* A, long long lda, const void* W, const float* bias, void* out,
                      long long ldo, long long M, int K, int N, int act, int out_dtype, cudaStream_t st) {
   if (M == 0) return PANGU_OK;
   if (K % 8 || lda % 8 || ldo % 8) { set_error("linear(bf16): K, lda, ldo must be multiples of 8 (K=%d lda=%lld ldo=%lld)", K, lda, ldo); return PANGU_ERR_BAD_ARG; }
   if (out_dtype != PANGU_BF16 && out_dtype != PANGU_F32) { set_error("linear(bf16): bad out_dtype"); return PANGU_ERR_BAD_ARG; }
+  {   // skinny-K shapes: A-resident CTA-pair kernel (tc_gemm2.cu); $PANGU_B200_GEMM2=0 keeps the tiled kernel
+    static const bool use_pair = []() { const char* e = getenv("PANGU_B200_GEMM2"); return e == nullptr || atoi(e) != 0; }();
+    if (use_pair) {
+      const int rc = launch_tc_linear_pair(A, lda, W, bias, out, ldo, M, K, N, act, out_dtype, st);
+      if (rc != PANGU_ERR_UNSUPPORTED) return rc;
+    }
+  }
   tc::GemmArgs a{};
   a.M = M; a.K = K; a.N = N; a.bias = bias; a.out = out; a.ldo = ldo; a.out_dtype = out_dtype; a.act = act;
   if (N % 256 == 0) return tc::launch_gemm_t<256, false>(A, lda, W, a, st);

@@ -19,7 +19,9 @@ def L():
 
 @pytest.mark.parametrize("M,K,N", [(128, 64, 64), (128, 192, 192), (1000, 192, 576), (333, 112, 192),
                                    (4133, 384, 1152), (640, 768, 384), (257, 1536, 256), (129, 384, 160),
-                                   (300, 384, 64), (521, 192, 768)])
+                                   (300, 384, 64), (521, 192, 768),
+                                   # M >= 2048, K in {192, 384}, N % 192 == 0: the A-resident CTA-pair kernel (tc_gemm2.cu)
+                                   (2048, 192, 192), (3001, 192, 576), (2500, 384, 768), (40000, 384, 1152)])
 def test_tc_linear(M, K, N):
     from pangu_b200 import ops
     g = torch.Generator().manual_seed(M + K + N)
