@@ -146,11 +146,14 @@ int pangu_window_attention(const void* qkv, const float* qkv_bias, const void* e
  * (read by the windows that straddle a band edge in a rolled block).  Attention output of own rows goes to
  * `out`; output of southern-halo rows goes to halo_out when it is not NULL (to be returned to the neighbour)
  * and is dropped otherwise (both neighbours compute the straddling window).  g is the GLOBAL geometry;
- * bias/mask types are global.  roll in {0,1}. */
+ * bias/mask types are global.  roll in {0,1}.
+ * prescaled != 0: the caller folded scale*log2(e) = 32^-0.5 * 1.442695 into the q rows of linear1 (weights AND
+ * the qkv_bias given here) and log2(e) into earth_bias, i.e. q k^T + bias is already the exponent in log2 units
+ * (the host mirror does this once per weight update); 0 = plain reference semantics (models/layers.py:431-453). */
 int pangu_window_attention_band(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv,
                                 const float* qkv_bias, const void* earth_bias, int bias_dtype, void* out,
                                 void* halo_out, const pangu_geom* g, const pangu_band* band, int roll,
-                                void* stream);
+                                int prescaled, void* stream);
 
 /* ------------------------------------------------------------------ layout / bandwidth kernels */
 

@@ -50,7 +50,7 @@ _PROTOS = {
     "pangu_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(Geom), c_int, c_int,
                                        c_void_p]),
     "pangu_window_attention_band": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
-                                            c_void_p, POINTER(Geom), POINTER(Band), c_int, c_void_p]),
+                                            c_void_p, POINTER(Geom), POINTER(Band), c_int, c_int, c_void_p]),
     "pangu_patch_embed_gather": (c_int, [c_void_p] * 10 + [c_int, c_void_p]),
     "pangu_patch_embed_gather_rows": (c_int, [c_void_p] * 10 + [c_int, c_int32, c_int32, c_int32, c_void_p]),
     "pangu_patch_recover_scatter": (c_int, [c_void_p] * 5),

@@ -47,7 +47,7 @@ int debug_read_mlp_trace(long long* out, int n);
 // tc_attention.cu
 int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias, const void* earth_bias,
                                  int bias_dtype, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
-                                 int roll, cudaStream_t st);
+                                 int roll, int prescaled, cudaStream_t st);
 
 }  // namespace pangu
 
@@ -112,7 +112,7 @@ extern "C" int pangu_window_attention(const void* qkv, const float* qkv_bias, co
   }
   if (dtype == PANGU_BF16) {
     const BandGeom full{0, g.H, 0, g.nH, 0, 0, 0};
-    return launch_window_attention_bf16(qkv, nullptr, nullptr, qkv_bias, earth_bias, bias_dtype, out, nullptr, g, full, roll, as_stream(stream));
+    return launch_window_attention_bf16(qkv, nullptr, nullptr, qkv_bias, earth_bias, bias_dtype, out, nullptr, g, full, roll, 0, as_stream(stream));
   }
   set_error("window_attention: unknown dtype %d", dtype);
   return PANGU_ERR_BAD_ARG;
@@ -121,7 +121,7 @@ extern "C" int pangu_window_attention(const void* qkv, const float* qkv_bias, co
 extern "C" int pangu_window_attention_band(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv,
                                            const float* qkv_bias, const void* earth_bias, int bias_dtype,
                                            void* out, void* halo_out, const pangu_geom* gg,
-                                           const pangu_band* band, int roll, void* stream) {
+                                           const pangu_band* band, int roll, int prescaled, void* stream) {
   WinGeom g;
   if (!make_geom(gg, g) || !band || !qkv || !qkv_bias || !earth_bias || !out) { set_error("window_attention_band: bad argument"); return PANGU_ERR_BAD_ARG; }
   if (g.C != g.heads * kHeadDim) { set_error("window_attention_band: C=%d must equal heads*32", g.C); return PANGU_ERR_BAD_ARG; }
@@ -144,5 +144,5 @@ extern "C" int pangu_window_attention_band(const void* qkv, const void* halo_qkv
       return PANGU_ERR_BAD_ARG;
     }
   }
-  return launch_window_attention_bf16(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, bias_dtype, out, halo_out, g, bd, roll, as_stream(stream));
+  return launch_window_attention_bf16(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, bias_dtype, out, halo_out, g, bd, roll, prescaled != 0, as_stream(stream));
 }

@@ -58,7 +58,10 @@ __device__ __forceinline__ float ex2(float x) {
 // cp.async fills and the ldmatrix reads (8 consecutive rows, same chunk) bank-conflict free.
 __device__ __forceinline__ int tile_off(int r, int c) { return r * 64 + ((c ^ ((r >> 1) & 3)) << 4); }
 
-template <typename TB>
+// PRE: the caller folded scale*log2(e) into the q projection (weights and bias) and log2(e) into the bias table,
+// so q k^T + bias is already the softmax exponent in log2 units: the bias tile initialises the MMA accumulator
+// and no per-score FMA is needed.
+template <typename TB, bool PRE>
 __global__ void __launch_bounds__(kThreads, 2)
 window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ halo_qkv,
                              const __nv_bfloat16* __restrict__ halo_lo_qkv,
@@ -126,9 +129,9 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
   __syncthreads();
 
   // token of window element k in longitude window l: index into the buffer of the element's row class
-  auto token_of = [&](int l, int k, int rb) -> long long {
+  auto token_of = [&](int l, int dwc, int rb) -> long long {      // dwc = s_dw[k]
     if (roll == 2) return (long long)l * g.T * kWinTokens + rb;
-    int w = 12 * l + (roll == 1 ? 6 : 0) + (s_dw[k] & 0xff);
+    int w = 12 * l + (roll == 1 ? 6 : 0) + (dwc & 0xff);
     if (w >= g.W) w -= g.W;
     return (long long)rb + w;
   };
@@ -139,10 +142,10 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
       const int k = i / 12, part = i - k * 12, s = part >> 2, c = part & 3;
       uint8_t* dst = buf + s * kTileBytes + tile_off(k, c);
       const int rb = s_rowbase[k];
-      const int cls = s_dw[k] >> 8;
+      const int dwc = s_dw[k], cls = dwc >> 8;
       if (cls != 0) {
         const __nv_bfloat16* base = cls == 1 ? qkv : (cls == 2 ? halo_qkv : halo_lo_qkv);
-        cp_async16(smem_u32(dst), base + token_of(l, k, rb) * 3 * C + s * C + head * kHeadDim + c * 8);
+        cp_async16(smem_u32(dst), base + token_of(l, dwc, rb) * 3 * C + s * C + head * kHeadDim + c * 8);
       } else {                                            // zero pad row: linear1(0) = bias (layers.py:228,419)
         const float* bsrc = qkv_bias + s * C + head * kHeadDim + c * 8;
         uint4 o;
@@ -188,14 +191,23 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) o_acc[i][j] = 0.f;
-    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+    float m_lo = -INFINITY, m_hi = -INFINITY;
+    float l_acc[4] = {0.f, 0.f, 0.f, 0.f};                  // row sums of the bf16 P, from a ones-column MMA
 
 #pragma unroll 1
     for (int kv0 = 0; kv0 < kWinTokens; kv0 += kKvBlock) {
       float s_acc[6][4];
 #pragma unroll
       for (int nt = 0; nt < 6; ++nt) {
-        s_acc[nt][0] = s_acc[nt][1] = s_acc[nt][2] = s_acc[nt][3] = 0.f;
+        if (PRE) {                                          // accumulate on top of the (pre-scaled) bias
+          const int j = kv0 + nt * 8 + 2 * tq;
+          const __nv_bfloat162 b_lo = *reinterpret_cast<const __nv_bfloat162*>(s_bias + (row0 + gq) * kBiasPitch + j);
+          const __nv_bfloat162 b_hi = *reinterpret_cast<const __nv_bfloat162*>(s_bias + (row0 + gq + 8) * kBiasPitch + j);
+          s_acc[nt][0] = __low2float(b_lo); s_acc[nt][1] = __high2float(b_lo);
+          s_acc[nt][2] = __low2float(b_hi); s_acc[nt][3] = __high2float(b_hi);
+        } else {
+          s_acc[nt][0] = s_acc[nt][1] = s_acc[nt][2] = s_acc[nt][3] = 0.f;
+        }
         uint32_t k0, k1, k2, k3;                            // b0,b1 of k-step 0 ; b0,b1 of k-step 1
         ldmatrix_x4(smem_u32(sk + tile_off(kv0 + nt * 8 + mr, mi)), k0, k1, k2, k3);
         mma_bf16(s_acc[nt], qa[0], k0, k1);
@@ -206,12 +218,14 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
 #pragma unroll
       for (int nt = 0; nt < 6; ++nt) {
         const int j = kv0 + nt * 8 + 2 * tq;
-        const __nv_bfloat162 b_lo = *reinterpret_cast<const __nv_bfloat162*>(s_bias + (row0 + gq) * kBiasPitch + j);
-        const __nv_bfloat162 b_hi = *reinterpret_cast<const __nv_bfloat162*>(s_bias + (row0 + gq + 8) * kBiasPitch + j);
-        s_acc[nt][0] = fmaf(s_acc[nt][0], sl2, __low2float(b_lo) * kLog2e);
-        s_acc[nt][1] = fmaf(s_acc[nt][1], sl2, __high2float(b_lo) * kLog2e);
-        s_acc[nt][2] = fmaf(s_acc[nt][2], sl2, __low2float(b_hi) * kLog2e);
-        s_acc[nt][3] = fmaf(s_acc[nt][3], sl2, __high2float(b_hi) * kLog2e);
+        if (!PRE) {
+          const __nv_bfloat162 b_lo = *reinterpret_cast<const __nv_bfloat162*>(s_bias + (row0 + gq) * kBiasPitch + j);
+          const __nv_bfloat162 b_hi = *reinterpret_cast<const __nv_bfloat162*>(s_bias + (row0 + gq + 8) * kBiasPitch + j);
+          s_acc[nt][0] = fmaf(s_acc[nt][0], sl2, __low2float(b_lo) * kLog2e);
+          s_acc[nt][1] = fmaf(s_acc[nt][1], sl2, __high2float(b_lo) * kLog2e);
+          s_acc[nt][2] = fmaf(s_acc[nt][2], sl2, __low2float(b_hi) * kLog2e);
+          s_acc[nt][3] = fmaf(s_acc[nt][3], sl2, __high2float(b_hi) * kLog2e);
+        }
         if (masked_type) {
           const int g0 = s_gid[j], g1 = s_gid[j + 1];
           if (g0 != gid_lo) s_acc[nt][0] += mask_l2;
@@ -228,7 +242,7 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
       mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
       const float a_lo = ex2(m_lo - mx_lo), a_hi = ex2(m_hi - mx_hi);     // 0 on the first block (m = -inf)
       m_lo = mx_lo; m_hi = mx_hi;
-      l_lo *= a_lo; l_hi *= a_hi;
+      l_acc[0] *= a_lo; l_acc[2] *= a_hi;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         o_acc[nt][0] *= a_lo; o_acc[nt][1] *= a_lo; o_acc[nt][2] *= a_hi; o_acc[nt][3] *= a_hi;
@@ -238,13 +252,14 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
       for (int nt = 0; nt < 6; ++nt) {
         const float p0 = ex2(s_acc[nt][0] - m_lo), p1 = ex2(s_acc[nt][1] - m_lo);
         const float p2 = ex2(s_acc[nt][2] - m_hi), p3 = ex2(s_acc[nt][3] - m_hi);
-        l_lo += p0 + p1; l_hi += p2 + p3;
         pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
         pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
       }
-      // O += P V : 3 k-steps x 4 d-tiles; V fragments via transposed ldmatrix
+      // O += P V : 3 k-steps x 4 d-tiles; V fragments via transposed ldmatrix.  A fifth "d-tile" of ones
+      // (bf16 1.0 pairs, a register constant) accumulates the row sums of P on the tensor pipe.
 #pragma unroll
       for (int kk = 0; kk < 3; ++kk) {
+        mma_bf16(l_acc, pa[kk], 0x3F803F80u, 0x3F803F80u);
 #pragma unroll
         for (int dp = 0; dp < 2; ++dp) {
           uint32_t v0, v1, v2, v3;                          // (b0,b1) of d-tile 2dp ; (b0,b1) of d-tile 2dp+1
@@ -255,11 +270,7 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
         }
       }
     }
-    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
-    l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
-    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
-    l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
-    const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;
+    const float inv_lo = 1.0f / l_acc[0], inv_hi = 1.0f / l_acc[2];   // every column of the ones tile holds the row sum
 
     // stage O (bf16) into this warp's own, now dead, Q rows; then 64-byte coalesced row stores
     __syncwarp();
@@ -275,11 +286,11 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
       for (int i = 0; i < 2; ++i) {
         const int idx = lane + i * 32, r = row0 + (idx >> 2), c = idx & 3;
         const int rb = s_rowbase[r];
-        const int cls = s_dw[r] >> 8;                       // pad rows are cropped (layers.py:287-288); halo rows
+        const int dwc = s_dw[r], cls = dwc >> 8;            // pad rows are cropped (layers.py:287-288); halo rows
         __nv_bfloat16* dstp = cls == 1 ? out : (cls == 2 ? halo_out : nullptr);   // belong to a neighbour
         if (dstp != nullptr) {
           const uint4 val = *reinterpret_cast<const uint4*>(sq + tile_off(r, c));
-          *reinterpret_cast<uint4*>(dstp + token_of(l, r, rb) * C + head * kHeadDim + c * 8) = val;
+          *reinterpret_cast<uint4*>(dstp + token_of(l, dwc, rb) * C + head * kHeadDim + c * 8) = val;
         }
       }
     }
@@ -290,9 +301,23 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
 
 }  // namespace attn
 
+template <typename TB, bool PRE>
+static int launch_attn_t(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias,
+                         const void* earth_bias, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
+                         int roll, int lon_chunk, dim3 grid, cudaStream_t st) {
+  using namespace attn;
+  auto kern = window_attention_bf16_kernel<TB, PRE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) { set_error("attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
+  kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)halo_qkv,
+                                           (const __nv_bfloat16*)halo_lo_qkv, qkv_bias, (const TB*)earth_bias,
+                                           (__nv_bfloat16*)out, (__nv_bfloat16*)halo_out, g, bd, roll, lon_chunk);
+  return check_launch("window_attention_bf16");
+}
+
 int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias, const void* earth_bias,
                                  int bias_dtype, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
-                                 int roll, cudaStream_t st) {
+                                 int roll, int prescaled, cudaStream_t st) {
   using namespace attn;
   if (bd.nhw <= 0) return PANGU_OK;
   // longitude windows per CTA (they share the staged bias tile): as many as possible (<= 5) while the grid
@@ -306,28 +331,14 @@ int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const vo
     if (per_l * (g.nLon / c) >= 8LL * tc_num_sms()) break;
   }
   dim3 grid((unsigned)g.heads, (unsigned)((g.nLon + lon_chunk - 1) / lon_chunk), (unsigned)(g.nZ * bd.nhw));
-  cudaError_t e;
-  if (bias_dtype == PANGU_BF16) {
-    auto kern = window_attention_bf16_kernel<__nv_bfloat16>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) { set_error("attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)halo_qkv,
-                                             (const __nv_bfloat16*)halo_lo_qkv, qkv_bias,
-                                             (const __nv_bfloat16*)earth_bias, (__nv_bfloat16*)out,
-                                             (__nv_bfloat16*)halo_out, g, bd, roll, lon_chunk);
-  } else if (bias_dtype == PANGU_F32) {
-    auto kern = window_attention_bf16_kernel<float>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) { set_error("attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)halo_qkv,
-                                             (const __nv_bfloat16*)halo_lo_qkv, qkv_bias,
-                                             (const float*)earth_bias, (__nv_bfloat16*)out, (__nv_bfloat16*)halo_out,
-                                             g, bd, roll, lon_chunk);
-  } else {
-    set_error("attention_bf16: unknown bias dtype %d", bias_dtype);
-    return PANGU_ERR_BAD_ARG;
-  }
-  return check_launch("window_attention_bf16");
+  if (bias_dtype == PANGU_BF16)
+    return prescaled ? launch_attn_t<__nv_bfloat16, true>(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, lon_chunk, grid, st)
+                     : launch_attn_t<__nv_bfloat16, false>(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, lon_chunk, grid, st);
+  if (bias_dtype == PANGU_F32)
+    return prescaled ? launch_attn_t<float, true>(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, lon_chunk, grid, st)
+                     : launch_attn_t<float, false>(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, lon_chunk, grid, st);
+  set_error("attention_bf16: unknown bias dtype %d", bias_dtype);
+  return PANGU_ERR_BAD_ARG;
 }
 
 }  // namespace pangu

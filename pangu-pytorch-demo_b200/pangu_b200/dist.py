@@ -184,7 +184,8 @@ class _Worker:
         att, wc = blk.attention, blk._wcache
         if self.xb is None:
             self.xb = ops.cast_bf16(self.x)
-        self.qkv = ops.linear(self.xb, wc.bf16("a1", att.linear1.weight), PF._f(att.linear1.bias))
+        w_qkv, b_qkv, _ = PF.attention_operands(att, wc)
+        self.qkv = ops.linear(self.xb, w_qkv, b_qkv)
 
     def first_rows(self, t, stage, rows=3):
         """The first `rows` latitude rows of a band tensor [Z*hrows*W, F] as a contiguous [Z*rows*W, F] block."""
@@ -198,10 +199,10 @@ class _Worker:
     def block_attend(self, blk, stage, roll, scheme):
         att, wc = blk.attention, blk._wcache
         band = self.plan.band(stage, roll, scheme)
+        _, b_qkv, eb = PF.attention_operands(att, wc)
         self.o, self.halo_o = ops.window_attention_band(
-            self.qkv, self.halo_qkv, PF._f(att.linear1.bias), wc.bf16("eb", att.earth_specific_bias), Z, TOK_H[stage],
-            TOK_W[stage], att.head_number, band, roll, halo_lo_qkv=self.halo_lo_qkv,
-            return_halo=(scheme == "sendback"))
+            self.qkv, self.halo_qkv, b_qkv, eb, Z, TOK_H[stage], TOK_W[stage], att.head_number, band, roll,
+            halo_lo_qkv=self.halo_lo_qkv, return_halo=(scheme == "sendback"), prescaled=True)
         self.qkv = self.halo_qkv = self.halo_lo_qkv = None
 
     def block_finish(self, blk, stage, o_first):

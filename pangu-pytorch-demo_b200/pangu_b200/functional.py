@@ -47,8 +47,43 @@ class WeightCache:
             self._c[key] = ent
         return ent[1]
 
+    def derived(self, key, params, fn):
+        """Cache fn(*params) until one of the parameters is updated in place or replaced."""
+        ent = self._c.get(key)
+        tag = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        if ent is None or ent[0] != tag:
+            with torch.no_grad():
+                ent = (tag, fn(*[p.detach() for p in params]))
+            self._c[key] = ent
+        return ent[1]
+
     def clear(self):
         self._c.clear()
+
+
+LOG2E = 1.4426950408889634
+
+
+def attention_operands(att, wc):
+    """bf16 tensor-core operands of one EarthAttention3D with the softmax scaling folded in once per weight
+    update: the q rows of linear1 (weight and bias) carry scale * log2(e) and the Earth-specific bias carries
+    log2(e), so that the kernel's q k^T + bias is directly the exp2 exponent (models/layers.py:431-453).
+    -> (w_qkv bf16 [3C, C], b_qkv fp32 [3C], bias table bf16 [T, heads, 144, 144])"""
+    C = att.dim
+    qs = att.scale * LOG2E
+
+    def scaled_w(w):
+        w = w.float().clone()
+        w[:C] *= qs
+        return w.to(torch.bfloat16).contiguous()
+
+    def scaled_b(b):
+        b = b.float().clone()
+        b[:C] *= qs
+        return b.contiguous()
+
+    return (wc.derived("a1s", (att.linear1.weight,), scaled_w), wc.derived("b1s", (att.linear1.bias,), scaled_b),
+            wc.derived("ebs", (att.earth_specific_bias,), lambda e: (e[0].float() * LOG2E).to(torch.bfloat16).contiguous()))
 
 
 def _w2d(p):
@@ -84,8 +119,10 @@ def block_forward(blk, x, Z, H, W, roll, mode, xb=None):
     wc = blk._wcache
     if xb is None:
         xb = ops.cast_bf16(x)
-    qkv = ops.linear(xb, wc.bf16("a1", att.linear1.weight), _f(att.linear1.bias))
-    o = ops.window_attention(qkv, _f(att.linear1.bias), wc.bf16("eb", att.earth_specific_bias), Z, H, W, heads, rmode)
+    w_qkv, b_qkv, eb = attention_operands(att, wc)
+    qkv = ops.linear(xb, w_qkv, b_qkv)
+    o, _ = ops.window_attention_band(qkv, None, b_qkv, eb, Z, H, W, heads, ops.full_band(H), 1 if roll else 0,
+                                     prescaled=True)
     del qkv
     x1, x1b = ops.linear_ln_residual_bf16(o, wc.bf16("a2", att.linear2.weight), _f(att.linear2.bias),
                                           _f(blk.norm1.weight), _f(blk.norm1.bias), x, eps=blk.norm1.eps)

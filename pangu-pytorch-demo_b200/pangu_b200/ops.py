@@ -199,8 +199,13 @@ def window_attention(qkv, qkv_bias, earth_bias, Z, H, W, heads, mode):
     return out
 
 
+def full_band(H):
+    """The whole grid as one band."""
+    return Band(0, H, 0, (H + 5) // 6, 0, 0, 0)
+
+
 def window_attention_band(qkv, halo_qkv, qkv_bias, earth_bias, Z, H, W, heads, band, roll, halo_lo_qkv=None,
-                          return_halo=True):
+                          return_halo=True, prescaled=False):
     """Band-sharded window attention (bf16): qkv [Z*hrows*W, 3C] holds the band's own rows of the GLOBAL
     (Z, H, W) grid, halo_qkv [Z*halo*W, 3C] the southern neighbour's first rows, halo_lo_qkv the northern
     neighbour's last rows.  -> (out, halo_out): halo_out (attention output of the southern halo rows, to be sent
@@ -224,7 +229,8 @@ def window_attention_band(qkv, halo_qkv, qkv_bias, earth_bias, Z, H, W, heads, b
     nwin = (W // 12) * (Z // 2) * band.nhw
     _call("attention_bf16[C=%d]" % C, "pangu_window_attention_band",
           (_ptr(qkv), _ptr(halo_qkv) if band.halo else None, _ptr(halo_lo_qkv) if band.halo_lo else None, _ptr(qkv_bias),
-           _ptr(earth_bias), _DT[earth_bias.dtype], _ptr(out), _ptr(halo_out), g, band, int(roll), _stream(),),
+           _ptr(earth_bias), _DT[earth_bias.dtype], _ptr(out), _ptr(halo_out), g, band, int(roll), int(prescaled),
+           _stream(),),
           flops=nwin * heads * 4.0 * 144 * 144 * 32,
           nbytes=float(qkv.numel() * 2 + out.numel() * 2 + earth_bias.numel() * earth_bias.element_size() * band.nhw / ((H + 5) // 6)))
     return out, halo_out

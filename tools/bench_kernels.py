@@ -66,6 +66,9 @@ def main():
             eb = (torch.randn(T, heads, 144, 144, device="cuda", generator=g) * 0.02).bfloat16()
             nwin = (W // 12) * T
             for roll in (0, 1):
+                ms = timeit(lambda: ops.window_attention_band(qkv, None, qb, eb, Z, H, W, heads, ops.full_band(H), roll, prescaled=True))
+                print(f"[{tag}] attention roll={roll} pre {ms:7.3f} ms  {nwin * heads * 4.0 * 144 * 144 * 32 / ms / 1e9:7.0f} TF/s  "
+                      f"{(M * C * 8 + eb.numel() * 2) / ms / 1e6:6.0f} GB/s")
                 ms = timeit(lambda: ops.window_attention(qkv, qb, eb, Z, H, W, heads, roll))
                 print(f"[{tag}] attention roll={roll}     {ms:7.3f} ms  {nwin * heads * 4.0 * 144 * 144 * 32 / ms / 1e9:7.0f} TF/s  "
                       f"{(M * C * 8 + eb.numel() * 2) / ms / 1e6:6.0f} GB/s")
