@@ -79,6 +79,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 2-D tiled store smem -> global (bulk async group of the issuing thread); rows/cols outside the tensor are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMEM
 // One full warp allocates `cols` (power of two >= 32) columns; base address lands in *dst_smem.
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
@@ -255,6 +265,10 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 // dim0 = inner (contiguous) extent in elements, dim1 = rows, row pitch in bytes; 128-byte swizzle.
 bool encode_tmap_2d_bf16(CUtensorMap* map, const void* gptr, uint64_t inner, uint64_t rows,
                          uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows);
+// general form: bf16 or fp32 elements, swizzle span 128 / 64 / 32 bytes (0 = none); box_inner * element size
+// must not exceed the swizzle span
+bool encode_tmap_2d(CUtensorMap* map, int is_bf16, const void* gptr, uint64_t inner, uint64_t rows,
+                    uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows, int swizzle_bytes);
 
 int num_sms();
 

@@ -335,6 +335,11 @@ static PFN_tmapEncodeTiled get_encode_fn() {
 
 bool encode_tmap_2d_bf16(CUtensorMap* map, const void* gptr, uint64_t inner, uint64_t rows,
                          uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows) {
+  return encode_tmap_2d(map, 1, gptr, inner, rows, row_pitch_bytes, box_inner, box_rows, 128);
+}
+
+bool encode_tmap_2d(CUtensorMap* map, int is_bf16, const void* gptr, uint64_t inner, uint64_t rows,
+                    uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows, int swizzle_bytes) {
   PFN_tmapEncodeTiled fn = get_encode_fn();
   if (!fn) return false;
   if ((reinterpret_cast<uintptr_t>(gptr) & 15) || (row_pitch_bytes & 15)) {
@@ -346,9 +351,12 @@ bool encode_tmap_2d_bf16(CUtensorMap* map, const void* gptr, uint64_t inner, uin
   cuuint64_t gstride[1] = {row_pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                               : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(gptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu pitch=%llu box=%ux%u)", (int)r,
               (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)row_pitch_bytes, box_inner, box_rows);

@@ -18,7 +18,9 @@
 //   warps 4..11 epilogue: per hidden chunk  H(TMEM) -> +b1, GELU -> bf16 P(TMEM);
 //               per row tile  Y(TMEM) -> +b2, LayerNorm, +residual -> fp32 + bf16, row-contiguous stores
 //
-// TMEM columns: Y [0,C) | HP0 [C,C+64) | HP1 [C+64,C+128)   (C = 384 uses all 512).  HP_b holds the fp32
+// TMEM columns: Y [0,384) (one accumulator at C = 384, TWO at C = 192) | HP0 [384,448) | HP1 [448,512).  With two
+// Y accumulators the LayerNorm/store phase of row tile i is spread, one 16-column unit at a time, between the
+// hidden chunks of row tile i+1, so its HBM traffic overlaps the MMAs instead of bursting.  HP_b holds the fp32
 // hidden chunk H_j (j & 1 == b); each epilogue warp overwrites the first half of ITS OWN 32 columns with
 // the packed bf16 P_j, which GEMM2 then reads as its A operand.  Because the tensor pipe executes MMAs in
 // issue order, G1(j+2) (which overwrites HP_b) needs no barrier against G2(j) (which reads it).
@@ -26,6 +28,7 @@
 #include <cstdlib>
 
 #include "tc_common.cuh"
+#include "tc_ln_epilogue.cuh"
 
 namespace pangu {
 namespace tc {
@@ -45,10 +48,10 @@ struct MlpArgs {
   float* x_out;
   __nv_bfloat16* x_out_bf16;
   float eps;
-  int dbg;   // bring-up knobs ($PANGU_MLP_DBG): 2 no LN pass 2, 32 no LN stores, 64 no residual loads, 4 G1 issues 1 of 4 k-steps, 8 G2 1 of 4
+  int dbg;   // bring-up knobs ($PANGU_MLP_DBG): 2 no LN pass 2 (C=384), 32 no LN stores, 4 G1 issues 1 of 4 k-steps, 8 G2 1 of 4
 };
 
-// Bring-up timeline: with dbg bit 16 set, CTA 0 records clock64() at pipeline events of its first tile.
+// Bring-up timeline: with dbg bit 16 set, CTA 0 records clock64() at pipeline events of its SECOND row tile (steady state).
 // Layout: [64 chunks][8 events]; events 0-3 = MMA thread (p_full passed, G2 issued, G1 issued, -),
 // 4-7 = epilogue warp 4 (h_full passed, H loaded, GELU packed, P stored).  Read with pangu_debug_trace().
 __device__ long long g_mlp_trace[64 * 8];
@@ -60,23 +63,32 @@ struct MlpCfg {
   static constexpr int NSPLIT = C / 192;         // GEMM2: N = C issued as NSPLIT MMAs of N = 192
   static constexpr int X_BYTES = 128 * C * 2;    // this CTA's rows of the x tile
   static constexpr int SLOT_BYTES = C * 64;      // half W1 chunk [32 x C] == half W2 chunk [C/2 x 64] (bf16)
-  static constexpr int EPI_BYTES = kMlpEpiWarps * 2048 + 2 * 2 * 128 * 8;
+  static constexpr int LN_UW = C == 192 ? 32 : 16;   // LayerNorm unit width (columns): 32 where smem allows
+  static constexpr int LN_D = C == 192 ? 1 : 3;      // residual prefetch depth: the interleaved schedule at C = 192
+                                                     // leaves thousands of cycles between a fetch and its use
+  static constexpr bool LN_ASYNC = C == 192;         // cp.async residual prefetch (two staging tiles per warp)
+  static constexpr int STG_BYTES = LN_UW * 128 * (LN_ASYNC ? 2 : 1);   // per epilogue warp: fp32 staging tile(s)
+  static constexpr int STGB_BYTES = LN_UW * 64;      // per epilogue warp: bf16 staging tile of the TMA store
+  static constexpr int PART_BYTES = 2 * 2 * 128 * 8; // LayerNorm partial sums
+  static constexpr int PARAM_BYTES = 3 * C * 4;      // b2, gamma, beta
+  static constexpr int EPI_BYTES = kMlpEpiWarps * (STG_BYTES + STGB_BYTES) + PART_BYTES + PARAM_BYTES;
   static constexpr int BAR_BYTES = 512;
   static constexpr int AVAIL = 227 * 1024 - 1024 - BAR_BYTES - X_BYTES - EPI_BYTES;
   static constexpr int NSLOT = AVAIL / SLOT_BYTES > 8 ? 8 : AVAIL / SLOT_BYTES;
   static constexpr int SMEM_BYTES = 1024 + X_BYTES + NSLOT * SLOT_BYTES + EPI_BYTES + BAR_BYTES;
-  static constexpr int COL_HP = C;               // two 64-column H/P buffers
+  static constexpr int NY = C == 192 ? 2 : 1;    // output accumulators: double-buffered when TMEM has room
+  static constexpr int COL_HP = 384;             // two 64-column H/P buffers behind the Y accumulator(s)
   static_assert(C % 192 == 0 && C + 128 <= 512, "C must be 192 or 384");
   static_assert(NSLOT >= 3, "weight ring too shallow");
 };
 
-__device__ __forceinline__ int stg16_f32(int r, int cc) { return r * 64 + ((cc ^ ((r >> 1) & 3)) << 4); }
-__device__ __forceinline__ void mlp_epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kMlpEpiWarps * 32) : "memory"); }
 
 template <int C>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                 const __grid_constant__ CUtensorMap tmW2, const MlpArgs a) {
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
+                 const __grid_constant__ CUtensorMap tmXb, const __grid_constant__ CUtensorMap tmRes,
+                 const MlpArgs a) {
   using Cfg = MlpCfg<C>;
   constexpr int NSLOT = Cfg::NSLOT, NCH = Cfg::NCH, KB1 = Cfg::KB1, NSPLIT = Cfg::NSPLIT;
   extern __shared__ uint8_t smem_raw[];
@@ -84,17 +96,20 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* sX = smem;                                         // [KB1][128 rows x 128 B]   (SW128 K-major)
   uint8_t* sW = smem + Cfg::X_BYTES;                          // [NSLOT][SLOT_BYTES]
   uint8_t* epi_smem = sW + NSLOT * Cfg::SLOT_BYTES;           // 8 x 2 KiB staging + LN partial sums
-  float2* ln_part = reinterpret_cast<float2*>(epi_smem + kMlpEpiWarps * 2048);
+  uint8_t* stgb_smem = epi_smem + kMlpEpiWarps * Cfg::STG_BYTES;
+  float2* ln_part = reinterpret_cast<float2*>(stgb_smem + kMlpEpiWarps * Cfg::STGB_BYTES);
+  float* sparams = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ln_part) + Cfg::PART_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
   uint64_t* x_full = bars + 0;
   uint64_t* x_empty = bars + 1;
   uint64_t* h_full = bars + 2;       // [2]  MMA -> epilogue: H_j complete in HP[j&1]   (both CTAs)
   uint64_t* p_full = bars + 4;       // [2]  epilogue -> MMA: P_j written to HP[j&1]    (leader's copy)
-  uint64_t* y_full = bars + 8;
-  uint64_t* y_empty = bars + 9;
+  uint64_t* y_full = bars + 6;       // [2]  MMA -> epilogue: Y accumulator complete    (both CTAs)
+  uint64_t* y_empty = bars + 8;      // [2]  epilogue -> MMA: Y accumulator drained     (leader's copy)
   uint64_t* w_full = bars + 10;      // [NSLOT]
   uint64_t* w_empty = bars + 10 + NSLOT;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * NSLOT);
+  uint64_t* ln_bar = bars + 10 + 2 * NSLOT;      // [8] per-epilogue-warp barrier of the residual tile loads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18 + 2 * NSLOT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                    // 0 = leader of the pair
@@ -104,13 +119,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmOut);
+    if (a.x_out_bf16 != nullptr) tma_prefetch_desc(&tmXb);
   }
+  for (int i = threadIdx.x; i < 3 * C; i += kMlpThreads)      // affine parameters of the row-tile epilogue -> smem
+    sparams[i] = i < C ? a.b2[i] : (i < 2 * C ? a.gamma[i - C] : a.beta[i - 2 * C]);
   if (warp == 1 && lane == 0) {
     mbar_init(x_full, 1); mbar_init(x_empty, 1);
     mbar_init(&h_full[0], 1); mbar_init(&h_full[1], 1);
     mbar_init(&p_full[0], 2 * kMlpEpiWarps); mbar_init(&p_full[1], 2 * kMlpEpiWarps);
-    mbar_init(y_full, 1); mbar_init(y_empty, 2 * kMlpEpiWarps);
+    for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 2 * kMlpEpiWarps); }
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int i = 0; i < kMlpEpiWarps; ++i) mbar_init(&ln_bar[i], 1);
     fence_barrier_init();
   }
   cluster_sync_all();                                         // barrier inits visible to the peer CTA
@@ -172,7 +192,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (rank == 0) {
       constexpr uint32_t idesc1 = make_idesc_bf16(256, NH, 0, 0);
       constexpr uint32_t idesc2 = make_idesc_f16(256, 192);       // P (TMEM) and W2 (smem) are fp16
-      const uint32_t tY = tmem_base, tHP = tmem_base + Cfg::COL_HP;
+      const uint32_t tHP = tmem_base + Cfg::COL_HP;
+      int yb = 0;                                             // Y accumulator of the current row tile
       int slot = 0;
       uint32_t wphase = 0, xphase = 0, yphase = 0, pphase = 0;   // pphase: bit b = phase of p_full[b]
       auto advance = [&]() { if (++slot == NSLOT) { slot = 0; wphase ^= 1; } };
@@ -203,9 +224,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int b = j & 1;
           mbar_wait(&p_full[b], (pphase >> b) & 1);           // GELU(H_j) written to TMEM by both CTAs
           pphase ^= 1u << b;
-          const bool tr = (a.dbg & 16) && blockIdx.x == 0 && pt == pair0 && j < 64 && lane == 0;
+          const bool tr = (a.dbg & 16) && blockIdx.x == 0 && pt == pair0 + npairs && j < 64 && lane == 0;
           if (tr) g_mlp_trace[j * 8 + 0] = clock64();
-          if (j == 0) { mbar_wait(y_empty, yphase ^ 1); yphase ^= 1; }   // previous tile's Y drained
+          if (j == 0) { mbar_wait(&y_empty[yb], ((yphase >> yb) & 1) ^ 1); yphase ^= 1u << yb; }   // this Y buffer drained
           mbar_wait(&w_full[slot], wphase);
           tcgen05_after_sync();
           const uint32_t sw = smem_u32(sW + slot * Cfg::SLOT_BYTES);
@@ -214,7 +235,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const uint64_t db = make_desc_k_sw128(sw + h * 12288);
 #pragma unroll
             for (int k = 0; k < 4; ++k)                        // Y += P_j . W2chunk^T ; K-step k lives at columns (k>>1)*32 + (k&1)*8
-              if (!((a.dbg & 8) && k) && elect_one()) umma2_bf16_ts(tY + h * 192, tHP + b * 64 + (k >> 1) * 32 + (k & 1) * 8, db + 2 * k, idesc2, (j | k) != 0);
+              if (!((a.dbg & 8) && k) && elect_one()) umma2_bf16_ts(tmem_base + yb * 192 + h * 192, tHP + b * 64 + (k >> 1) * 32 + (k & 1) * 8, db + 2 * k, idesc2, (j | k) != 0);
           }
           if (elect_one()) umma2_commit_mc(&w_empty[slot]);
           advance();
@@ -225,7 +246,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (j + 2 == NCH - 1 && elect_one()) umma2_commit_mc(x_empty);   // last read of the x tile
           }
         }
-        if (elect_one()) umma2_commit_mc(y_full);
+        if (elect_one()) umma2_commit_mc(&y_full[yb]);
+        __syncwarp();
+        if (Cfg::NY == 2) yb ^= 1;
       }
     }
     __syncwarp();
@@ -233,143 +256,111 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // ------------------------------------------------------------ epilogue warps (both CTAs)
     const int q = warp & 3, hf = (warp - 4) >> 2;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t y_empty_L = mapa_u32(smem_u32(y_empty), 0);
+    const uint32_t y_empty_L0 = mapa_u32(smem_u32(&y_empty[0]), 0), y_empty_L1 = mapa_u32(smem_u32(&y_empty[1]), 0);
     const uint32_t p_full_L0 = mapa_u32(smem_u32(&p_full[0]), 0), p_full_L1 = mapa_u32(smem_u32(&p_full[1]), 0);
-    uint8_t* stg = epi_smem + (warp - 4) * 2048;
-    uint32_t hphase = 0, yphase = 0, tile_par = 0;            // hphase: bit b = phase of h_full[b]
+    uint32_t hphase = 0, yphase = 0;                          // bit b = phase of h_full[b] / y_full[b]
     uint32_t v[32];
-    for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
-      const long long m_base = (long long)pt * 256 + rank * 128 + q * 32;
-#pragma unroll 1
-      for (int j = 0; j < NCH; ++j) {
-        const int b = j & 1;
-        float4 bb[8];                                          // b1 of this warp's 32 hidden units: fetched before the wait
-        {
-          const float4* b1 = reinterpret_cast<const float4*>(a.b1 + j * NH + hf * 32);
+    using Ln = LnTileEpilogue<C, Cfg::LN_UW, Cfg::LN_D, Cfg::LN_ASYNC, true>;
+    Ln ln;
+    ln.bias = a.b2; ln.gamma = a.gamma; ln.beta = a.beta; ln.residual = a.residual;
+    ln.x_out = a.x_out; ln.xb = a.x_out_bf16; ln.M = a.M; ln.eps = a.eps;
+    ln.tm_out = &tmOut; ln.tm_xb = a.x_out_bf16 != nullptr ? &tmXb : nullptr;
+    ln.stg_b = stgb_smem + (warp - 4) * Cfg::STGB_BYTES; ln.sparams = sparams;
+    ln.tm_res = &tmRes; ln.ld_bar = &ln_bar[warp - 4];
+    ln.stg = epi_smem + (warp - 4) * Cfg::STG_BYTES; ln.ln_part = ln_part; ln.q = q; ln.hf = hf; ln.lane = lane; ln.tile_par = 0;
+    const bool ln_store = !(a.dbg & 32);
+
+    // one hidden chunk: H_j (TMEM) -> +b1, GELU (packed fp16) -> P_j (TMEM, over the warp's own columns)
+    auto gelu_chunk = [&](int pt, int j) {
+      const int b = j & 1;
+      float4 bb[8];                                            // b1 of this warp's 32 hidden units: fetched before the wait
+      {
+        const float4* b1 = reinterpret_cast<const float4*>(a.b1 + j * NH + hf * 32);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bb[i] = __ldg(b1 + i);
-        }
-        mbar_wait(&h_full[b], (hphase >> b) & 1);
-        hphase ^= 1u << b;
-        tcgen05_after_sync();
-        const bool tr = (a.dbg & 16) && blockIdx.x == 0 && warp == 4 && lane == 0 && pt == pair0 && j < 64;
-        if (tr) g_mlp_trace[j * 8 + 4] = clock64();
-        const uint32_t t_own = lane_base + Cfg::COL_HP + b * 64 + hf * 32;   // this warp's 32 columns of H_j
-        tmem_ld_32x32(t_own, v);
-        tmem_ld_wait();
-        if (tr) g_mlp_trace[j * 8 + 5] = clock64();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          pk[2 * i] = gelu_fast_h2(__uint_as_float(v[4 * i]) + bb[i].x, __uint_as_float(v[4 * i + 1]) + bb[i].y);
-          pk[2 * i + 1] = gelu_fast_h2(__uint_as_float(v[4 * i + 2]) + bb[i].z, __uint_as_float(v[4 * i + 3]) + bb[i].w);
-        }
-        if (tr) g_mlp_trace[j * 8 + 6] = clock64();
-        tmem_st_32x16(t_own, pk);                             // P_j over the first 16 of the warp's own columns
-        tmem_st_wait();
-        if (tr) g_mlp_trace[j * 8 + 7] = clock64();
-        tcgen05_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(b ? p_full_L1 : p_full_L0);
+        for (int i = 0; i < 8; ++i) bb[i] = __ldg(b1 + i);
       }
-
-      // ---- row-tile epilogue: +b2, LayerNorm, +residual, stores.  The fp32 residual is fetched
-      // row-contiguously three 16-column units ahead (first fetches are issued before the accumulator
-      // is even complete), so that enough bytes are in flight to use the HBM share of this SM.
-      constexpr int NU = C / 32;                              // 16-column units handled by this warp
-      const int rcc = lane & 3, rr0 = lane >> 2;              // row-contiguous view: 16-byte chunk rcc of rows rr0 + 8i
-      float4 rg[3][4];
-      auto load_residual = [&](int idx, float4 (&dst)[4]) {
-        const int u = hf + 2 * idx;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const long long m = m_base + rr0 + 8 * i;
-          dst[i] = (a.residual != nullptr && m < a.M && !(a.dbg & 64))
-                       ? __ldg(reinterpret_cast<const float4*>(a.residual + m * C + u * 16 + rcc * 4))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      load_residual(0, rg[0]);
-      load_residual(1, rg[1]);
-      load_residual(2, rg[2]);
-
-      mbar_wait(y_full, yphase);
-      yphase ^= 1;
+      mbar_wait(&h_full[b], (hphase >> b) & 1);
+      hphase ^= 1u << b;
       tcgen05_after_sync();
-      float s = 0.f, ss = 0.f;
-#pragma unroll 1
-      for (int c = hf; c < C / 32; c += 2) {
-        tmem_ld_32x32(lane_base + c * 32, v);
-        tmem_ld_wait();
+      const bool tr = (a.dbg & 16) && blockIdx.x == 0 && warp == 4 && lane == 0 && pt == pair0 + npairs && j < 64;
+      if (tr) g_mlp_trace[j * 8 + 4] = clock64();
+      const uint32_t t_own = lane_base + Cfg::COL_HP + b * 64 + hf * 32;   // this warp's 32 columns of H_j
+      tmem_ld_32x32(t_own, v);
+      tmem_ld_wait();
+      if (tr) g_mlp_trace[j * 8 + 5] = clock64();
+      uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(a.b2 + c * 32 + i));
-          const float x0 = __uint_as_float(v[i]) + b.x, x1 = __uint_as_float(v[i + 1]) + b.y;
-          const float x2 = __uint_as_float(v[i + 2]) + b.z, x3 = __uint_as_float(v[i + 3]) + b.w;
-          s += (x0 + x1) + (x2 + x3);
-          ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
-        }
+      for (int i = 0; i < 8; ++i) {
+        pk[2 * i] = gelu_fast_h2(__uint_as_float(v[4 * i]) + bb[i].x, __uint_as_float(v[4 * i + 1]) + bb[i].y);
+        pk[2 * i + 1] = gelu_fast_h2(__uint_as_float(v[4 * i + 2]) + bb[i].z, __uint_as_float(v[4 * i + 3]) + bb[i].w);
       }
-      float2* part = ln_part + tile_par * 256;
-      part[hf * 128 + q * 32 + lane] = make_float2(s, ss);
-      mlp_epi_bar_sync();
-      const float2 p0 = part[q * 32 + lane], p1 = part[128 + q * 32 + lane];
-      const float mean = (p0.x + p1.x) * (1.0f / C);
-      const float var = fmaxf((p0.y + p1.y) * (1.0f / C) - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + a.eps);
-      tile_par ^= 1;
-
-      auto ln_unit = [&](int idx, float4 (&cur)[4]) {
-        const int u = hf + 2 * idx;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(stg + stg16_f32(rr0 + 8 * i, rcc)) = cur[i];
-        __syncwarp();
-        if (idx + 3 < NU) load_residual(idx + 3, cur);
-        uint32_t w[16];
-        tmem_ld_32x16(lane_base + u * 16, w);
-        tmem_ld_wait();
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int i = cc * 4;
-          float4* p = reinterpret_cast<float4*>(stg + stg16_f32(lane, cc));
-          float4 r = *p;
-          const float4 b = __ldg(reinterpret_cast<const float4*>(a.b2 + u * 16 + i));
-          const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + u * 16 + i));
-          const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta + u * 16 + i));
-          r.x += fmaf((__uint_as_float(w[i]) + b.x - mean) * rstd, g.x, be.x);
-          r.y += fmaf((__uint_as_float(w[i + 1]) + b.y - mean) * rstd, g.y, be.y);
-          r.z += fmaf((__uint_as_float(w[i + 2]) + b.z - mean) * rstd, g.z, be.z);
-          r.w += fmaf((__uint_as_float(w[i + 3]) + b.w - mean) * rstd, g.w, be.w);
-          *p = r;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = rr0 + 8 * i;
-          const long long m = m_base + rr;
-          const float4 val = *reinterpret_cast<const float4*>(stg + stg16_f32(rr, rcc));
-          if (m < a.M && !(a.dbg & 32)) {
-            const long long off = m * C + u * 16 + rcc * 4;
-            *reinterpret_cast<float4*>(a.x_out + off) = val;
-            if (a.x_out_bf16 != nullptr)
-              *reinterpret_cast<uint2*>(a.x_out_bf16 + off) = make_uint2(pack_bf16(val.x, val.y), pack_bf16(val.z, val.w));
-          }
-        }
-        __syncwarp();
-      };
-      static_assert(NU % 3 == 0, "unit loop is unrolled by the prefetch depth");
-      if (!(a.dbg & 2)) {
-#pragma unroll 1
-        for (int base = 0; base < NU; base += 3) {
-          ln_unit(base, rg[0]);
-          ln_unit(base + 1, rg[1]);
-          ln_unit(base + 2, rg[2]);
-        }
-      }
+      if (tr) g_mlp_trace[j * 8 + 6] = clock64();
+      tmem_st_32x16(t_own, pk);                               // P_j over the first 16 of the warp's own columns
+      tmem_st_wait();
+      if (tr) g_mlp_trace[j * 8 + 7] = clock64();
       tcgen05_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(y_empty_L);
+      if (lane == 0) mbar_arrive_cluster(b ? p_full_L1 : p_full_L0);
+    };
+    auto y_wait = [&](int yb) {                               // accumulator yb complete
+      mbar_wait(&y_full[yb], (yphase >> yb) & 1);
+      yphase ^= 1u << yb;
+      tcgen05_after_sync();
+    };
+    auto y_release = [&](int yb) {                            // all TMEM reads of accumulator yb done
+      tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(yb ? y_empty_L1 : y_empty_L0);
+    };
+
+    if constexpr (Cfg::NY == 1) {
+      for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
+#pragma unroll 1
+        for (int j = 0; j < NCH; ++j) gelu_chunk(pt, j);
+        // row-tile epilogue: the first residual fetches are issued before the accumulator is even complete
+        ln.m_base = (long long)pt * 256 + rank * 128 + q * 32;
+        ln.prefetch();
+        y_wait(0);
+        ln.stats(lane_base);
+        if (!(a.dbg & 2)) ln.all_units(lane_base, ln_store);
+        y_release(0);
+      }
+    } else {
+      // two accumulators: the LayerNorm units of the PREVIOUS row tile run between the hidden chunks of the
+      // current one (NCH = 12 chunks, NU = 3 units of 32 columns per warp: one unit after every fourth chunk)
+      static_assert(Cfg::NY == 1 || (NCH == 12 && Ln::NU == 3 && Cfg::LN_D == 1), "interleave schedule assumes C = 192");
+      int yb = 0;
+      bool pending = false;                                   // ln.* describes a finished tile in accumulator yb ^ 1
+      for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
+        const uint32_t y_prev = lane_base + (yb ^ 1) * 192;
+        gelu_chunk(pt, 0);
+        if (pending) { y_wait(yb ^ 1); ln.stats(y_prev); }
+#pragma unroll 1
+        for (int jb = 0; jb < NCH; jb += 4) {
+          if (jb) gelu_chunk(pt, jb);
+          gelu_chunk(pt, jb + 1);
+          gelu_chunk(pt, jb + 2);
+          gelu_chunk(pt, jb + 3);
+          if (pending) {
+            ln.dbg = ((a.dbg & 16) && blockIdx.x == 0 && warp == 4 && lane == 0 && pt == pair0 + npairs) ? g_mlp_trace + 400 + (jb / 4) * 8 : nullptr;
+            ln.template unit<0>(y_prev, jb / 4, ln_store);
+          }
+        }
+        if (pending) y_release(yb ^ 1);
+        ln.m_base = (long long)pt * 256 + rank * 128 + q * 32;   // this tile becomes the pending one
+        ln.prefetch();
+        pending = true;
+        yb ^= 1;
+      }
+      if (pending) {                                          // drain the last row tile
+        const uint32_t y_prev = lane_base + (yb ^ 1) * 192;
+        y_wait(yb ^ 1);
+        ln.stats(y_prev);
+        ln.all_units(y_prev, ln_store);
+        y_release(yb ^ 1);
+      }
     }
+    ln.drain_stores();
   }
 
   tcgen05_before_sync();
@@ -385,6 +376,17 @@ static int launch_mlp_t(const void* x, const void* w1, const void* w2, MlpArgs& 
   if (!encode_tmap_2d_bf16(&tmX, x, C, (uint64_t)a.M, (uint64_t)C * 2, 64, 128)) return PANGU_ERR_CUDA;
   if (!encode_tmap_2d_bf16(&tmW1, w1, C, 4 * C, (uint64_t)C * 2, 64, 32)) return PANGU_ERR_CUDA;
   if (!encode_tmap_2d_bf16(&tmW2, w2, 4 * C, C, (uint64_t)4 * C * 2, 64, 96)) return PANGU_ERR_CUDA;
+  CUtensorMap tmOut, tmXb;
+  constexpr int UW = Cfg::LN_UW;
+  if (!encode_tmap_2d(&tmOut, 0, a.x_out, C, (uint64_t)a.M, (uint64_t)C * 4, UW, 32, UW * 4)) return PANGU_ERR_CUDA;
+  if (a.x_out_bf16 != nullptr) {
+    if (!encode_tmap_2d(&tmXb, 1, a.x_out_bf16, C, (uint64_t)a.M, (uint64_t)C * 2, UW, 32, UW * 2)) return PANGU_ERR_CUDA;
+  } else {
+    tmXb = tmOut;
+  }
+  CUtensorMap tmRes = tmOut;
+  if (a.residual != nullptr && !encode_tmap_2d(&tmRes, 0, a.residual, C, (uint64_t)a.M, (uint64_t)C * 4, UW, 32, UW * 4)) return PANGU_ERR_CUDA;
+  if (a.residual == nullptr && Cfg::LN_ASYNC) { set_error("mlp_fused<%d>: a residual tensor is required", C); return PANGU_ERR_BAD_ARG; }
   a.pair_tiles = (int)((a.M + 255) / 256);
   auto kern = mlp_fused_kernel<C>;
   static bool configured = false;
@@ -395,7 +397,7 @@ static int launch_mlp_t(const void* x, const void* w1, const void* w2, MlpArgs& 
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = a.pair_tiles < max_pairs ? a.pair_tiles : max_pairs;
-  kern<<<2 * pairs, kMlpThreads, Cfg::SMEM_BYTES, st>>>(tmX, tmW1, tmW2, a);
+  kern<<<2 * pairs, kMlpThreads, Cfg::SMEM_BYTES, st>>>(tmX, tmW1, tmW2, tmOut, tmXb, tmRes, a);
   return check_launch("mlp_fused");
 }
 

@@ -30,3 +30,9 @@ print("chunk | mma: p_full  g2_issued g1_issued | epi: h_full  loaded  gelu_done
 for j in range(nch):
     r = [buf[j * 8 + k] - t0 if buf[j * 8 + k] else -1 for k in range(8)]
     print(f"{j:3d}   | {r[0]:8d} {r[1]:8d} {r[2]:8d} | {r[4]:8d} {r[5]:8d} {r[6]:8d} {r[7]:8d}")
+
+if C == 192:
+    print("LN units (interleaved): stamps = start, tile landed, prefetch issued, tmem loaded, math done, staged, fenced, stores issued")
+    for u in range(3):
+        r = [buf[400 + u * 8 + k] - t0 for k in (0, 1, 2, 3, 6, 7, 4, 5)]
+        print(f"  unit {u}: " + " ".join(f"{x:8d}" for x in r))
