@@ -307,9 +307,32 @@ def main():
     jobs = world if mode == "replicas" else 1              # forecasts completed per step across the job
     value = jobs * args.steps / (total_ms / 1000.0)
 
-    for _ in range(2):
-        step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
+    streamer = None
+    if graphed is not None:
+        # public streaming API: H2D of sample i+1, forward of sample i and D2H of sample i-1 overlap
+        # (every sample still pays both of its transfers inside the timed region)
+        from pangu_b200.pipeline import StreamedForecaster
+        try:
+            streamer = StreamedForecaster(forward, (d_inp, d_inp_s, stats, maps, const_h))
+        except Exception as exc:                                  # noqa: BLE001
+            sys.stderr.write(f"[bench] StreamedForecaster unavailable on rank {rank} ({type(exc).__name__}: {exc})\n")
+        if world > 1:
+            flag = torch.tensor([1 if streamer is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                streamer = None
+
+    def e2e_run(steps):
+        if streamer is None:
+            for _ in range(steps):
+                step_e2e()
+        else:
+            for _ in range(steps):
+                streamer.submit(h_inp, h_inp_s)
+            streamer.flush()                                      # last results are on the host when timing stops
+
+    e2e_run(2)
+    e2e_ms = timed(lambda: e2e_run(args.steps), 1)
     e2e_value = jobs * args.steps / (e2e_ms / 1000.0)
     h2d = (h_inp.numel() + h_inp_s.numel()) * 4            # per rank
     d2h = (h_out.numel() + h_out_s.numel()) * 4
@@ -349,8 +372,9 @@ def main():
                 "scaling": "weak" if mode == "replicas" else "strong", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic (seeded random-init weights, ERA5-shaped inputs)", "config": config,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / args.steps, "api": ("pangu_b200.graph.GraphedForward(PanguModel / BandedPangu)" if graphed is not None else
-                                "models.pangu_model.PanguModel.forward") + " on pinned host inputs"},
+                        "ms_per_step": e2e_ms / args.steps, "api": ("pangu_b200.pipeline.StreamedForecaster(PanguModel / BandedPangu): pinned host in -> pinned host out, "
+                                "transfers of neighbouring samples overlap the forward" if streamer is not None else
+                                "models.pangu_model.PanguModel.forward on pinned host inputs, serial H2D / forward / D2H")},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "kernels": kernels, "tflops_model_per_gpu": FLOPS_TOTAL * value / world / 1e12}
         print(json.dumps(line))

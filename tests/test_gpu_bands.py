@@ -60,3 +60,26 @@ def test_cuda_graph_replay_equals_eager(model_and_inputs):
     torch.cuda.synchronize()
     assert torch.equal(out2, want2[0]) and torch.equal(out_s2, want2[1])
     assert fwd.launches_per_replay > 50
+
+
+def test_streamed_forecaster_matches_eager(model_and_inputs):
+    """pangu_b200.pipeline.StreamedForecaster: overlapped H2D / forward / D2H returns each sample's own result."""
+    from pangu_b200.pipeline import StreamedForecaster
+    model, args, want = model_and_inputs
+    sf = StreamedForecaster(model, args)
+    hosts = []
+    for k in range(4):
+        a = (args[0] * (1.0 - 0.1 * k)).cpu().pin_memory()
+        b = (args[1] * (1.0 + 0.05 * k)).cpu().pin_memory()
+        hosts.append((a, b))
+    got = []
+    for a, b in hosts:
+        r = sf.submit(a, b)
+        if r is not None:
+            got.append(tuple(t.clone() for t in r))
+    got += [tuple(t.clone() for t in r) for r in sf.flush()]
+    assert len(got) == 4
+    for (a, b), (o, os_) in zip(hosts, got):
+        with torch.no_grad():
+            w, ws = model(a.cuda(), b.cuda(), *args[2:])
+        assert torch.equal(o, w.cpu()) and torch.equal(os_, ws.cpu())
