@@ -34,6 +34,22 @@ FLOPS_TOTAL = 8.421e12            # algorithmic FLOPs of one forwar
 FLOPS_ATTN_MLP = 8.132e12         # attention + MLP blocks
 
 
+def ncu_traffic(kernel_tag):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r1_ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    want = {"mlp_fused_bf16[C=384]": ("tc::mlp_fused_kernel<384>", 148), "mlp_fused_bf16[C=192]": ("tc::mlp_fused_kernel<192>", 148)}
+    if kernel_tag not in want or not os.path.exists(p):
+        return None
+    name, grid = want[kernel_tag]
+    for k, lst in json.load(open(p))["kernels"].items():
+        if name in k:
+            for e in lst:
+                if e["grid"] == grid:
+                    return e["dram_read_bytes"] + e["dram_write_bytes"]
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -355,7 +371,9 @@ def main():
             calls, tms, fl, _ = gemm[dom]
             ach = fl / (tms / 1000.0) / 1e12
             roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tf_sust"], "traffic": None, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
+                        "frac": ach / peaks["tf_sust"], "traffic": ncu_traffic(dom),
+                        "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, full-grid launch)" if ncu_traffic(dom) else None,
+                        "algorithmic_bytes_per_launch": gemm[dom][3] / calls, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
                         "avg_launch_ms": tms / calls, "flops_per_launch": fl / calls,
                         "all_gemm_tflops": sum(v[2] for v in gemm.values()) / (sum(v[1] for v in gemm.values()) / 1000.0) / 1e12,
                         "model_attn_mlp_frac": FLOPS_ATTN_MLP * value / world / 1e12 / peaks["tf_sust"],
