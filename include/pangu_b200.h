@@ -95,6 +95,15 @@ int pangu_linear(const void* A, int64_t lda, const void* W, const float* bias, v
                  int64_t ldo, int64_t M, int32_t K, int32_t N, int act, int dtype,
                  int out_dtype, void* stream);
 
+/* bf16 tensor-core linear with two fusions around it (both optional):
+ *   - A2 != NULL: the A operand is the channel concat cat(A[M,K1], A2[M,K-K1]) read from the two tensors -- the skip
+ *     concat in front of the output layer (models/pangu_model.py:98, models/layers.py:591,608); K1 % 64 == 0;
+ *   - out_bf16_shadow != NULL (out_dtype fp32): a bf16 copy of the output is written as well (operand of the next
+ *     tensor-core GEMM), same row pitch ldo -- replaces the cast pass after embed / down-sample / up-sample. */
+int pangu_linear_bf16_ex(const void* A, int64_t lda, const void* A2, int64_t lda2, int32_t K1, const void* W,
+                         const float* bias, void* out, void* out_bf16_shadow, int64_t ldo, int64_t M,
+                         int32_t K, int32_t N, int act, int out_dtype, void* stream);
+
 /* x_out = residual + LayerNorm_C(y) * gamma + beta   (post-norm residual, models/layers.py:296-297;
  * eps 1e-5).  y is fp32 or bf16 (y_dtype); residual/x_out fp32; x_out_bf16 optional shadow copy
  * (operand of the next GEMM) or NULL.  residual may be NULL (plain LayerNorm). */

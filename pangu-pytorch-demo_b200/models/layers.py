@@ -309,8 +309,8 @@ class PatchRecovery_pretrain(_B200Module):
         self.conv = nn.Conv1d(in_channels=dim, out_channels=160, kernel_size=1, stride=1)
         self.conv_surface = nn.Conv1d(in_channels=dim, out_channels=64, kernel_size=1, stride=1)
 
-    def forward_sample(self, x, Z, H, W, skip=None, denorm=None):
-        return PF.patch_recover_forward(self, x, Z, H, W, self._mode(), skip, denorm=denorm)
+    def forward_sample(self, x, Z, H, W, skip=None, denorm=None, xb=None, skip_b=None):
+        return PF.patch_recover_forward(self, x, Z, H, W, self._mode(), skip, denorm=denorm, xb=xb, skip_b=skip_b)
 
     def forward(self, x, Z, H, W):
         _no_training_graph(self, x)

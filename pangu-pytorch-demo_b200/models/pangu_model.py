@@ -61,13 +61,13 @@ class PanguModel(_B200Module):
         mode = self._mode()
         x, xb = PF.patch_embed_forward(self._input_layer, inp, inp_s, stats, maps, const_h, mode)
         x, xb = self.layers[0].forward_sample(x, 8, 181, 360, xb)
-        skip = x
+        skip, skip_b = x, xb
         x, xb = self.downsample.forward_sample(x, 8, 181, 360)
         x, xb = self.layers[1].forward_sample(x, 8, 91, 180, xb)
         x, xb = self.layers[2].forward_sample(x, 8, 91, 180, xb)
         x, xb = self.upsample.forward_sample(x, xb)
         x, xb = self.layers[3].forward_sample(x, 8, 181, 360, xb)
-        return self._output_layer.forward_sample(x, 8, 181, 360, skip=skip, denorm=denorm)
+        return self._output_layer.forward_sample(x, 8, 181, 360, skip=skip, denorm=denorm, xb=xb, skip_b=skip_b)
 
     def forward(self, input, input_surface, statistics, maps, const_h):
         _no_training_graph(self, input, input_surface)

@@ -41,6 +41,8 @@ _PROTOS = {
     "pangu_position_index": (c_int, [c_void_p, c_void_p]),
     "pangu_linear": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
                              c_int, c_int, c_int, c_void_p]),
+    "pangu_linear_bf16_ex": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_int64, c_int64, c_int32, c_int32, c_int, c_int, c_void_p]),
     "pangu_ln_residual": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_int32, c_float, c_void_p]),
     "pangu_linear_ln_residual_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -35,7 +35,8 @@ int launch_window_attention_f32(const float* qkv, const float* qkv_bias, const f
                                 float* out, const WinGeom& g, int roll, cudaStream_t st);
 // tc_gemm.cu
 int launch_tc_linear(const void* A, long long lda, const void* W, const float* bias, void* out,
-                     long long ldo, long long M, int K, int N, int act, int out_dtype, cudaStream_t st);
+                     long long ldo, long long M, int K, int N, int act, int out_dtype, cudaStream_t st,
+                     void* shadow = nullptr, const void* A2 = nullptr, long long lda2 = 0, int K1 = 0);
 int launch_tc_linear_ln(const void* A, long long lda, const void* W, const float* bias,
                         const float* gamma, const float* beta, const float* residual, float* x_out,
                         void* x_out_bf16, long long M, int K, int C, float eps, cudaStream_t st);
@@ -70,6 +71,15 @@ extern "C" int pangu_linear(const void* A, int64_t lda, const void* W, const flo
     return launch_tc_linear(A, lda, W, bias, out, ldo, M, K, N, act, out_dtype, as_stream(stream));
   set_error("linear: unknown dtype %d", dtype);
   return PANGU_ERR_BAD_ARG;
+}
+
+extern "C" int pangu_linear_bf16_ex(const void* A, int64_t lda, const void* A2, int64_t lda2, int32_t K1,
+                                    const void* W, const float* bias, void* out, void* out_bf16_shadow,
+                                    int64_t ldo, int64_t M, int32_t K, int32_t N, int act, int out_dtype,
+                                    void* stream) {
+  if (!A || !W || !out || M < 0 || K <= 0 || N <= 0) { set_error("linear_ex: bad argument"); return PANGU_ERR_BAD_ARG; }
+  if (act != PANGU_ACT_NONE && act != PANGU_ACT_GELU_ERF) { set_error("linear_ex: unknown activation %d", act); return PANGU_ERR_BAD_ARG; }
+  return launch_tc_linear(A, lda, W, bias, out, ldo, M, K, N, act, out_dtype, as_stream(stream), out_bf16_shadow, A2, lda2, K1);
 }
 
 extern "C" int pangu_ln_residual(const void* y, int y_dtype, const float* gamma, const float* beta,

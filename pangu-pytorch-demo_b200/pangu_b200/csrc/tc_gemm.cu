@@ -29,6 +29,8 @@ struct GemmArgs {
   long long ldo;
   int out_dtype;
   int act;
+  __nv_bfloat16* shadow;        // optional bf16 copy of an fp32 output (operand of the next GEMM), row pitch ldo
+  int k_blocks_a1;              // k-blocks taken from the first A tensor; the rest come from the second (channel concat)
   // LayerNorm + residual epilogue
   const float* gamma;
   const float* beta;
@@ -68,8 +70,8 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 
 template <int BN, bool LN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmArgs a) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES, NACC = Cfg::NACC;
   extern __shared__ uint8_t smem_raw[];
@@ -113,7 +115,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint8_t* sb = sa + A_STAGE_BYTES;
         if (elect_one()) {
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          if (kb < a.k_blocks_a1) tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+          else tma_load_2d(sa, &tmA2, &full_bar[stage], (kb - a.k_blocks_a1) * BK, m0);   // second half of cat(A1, A2)
 #pragma unroll
           for (int h = 0; h < Cfg::N_SPLIT; ++h)
             tma_load_2d(sb + h * Cfg::UMMA_N * BK * 2, &tmB, &full_bar[stage], kb * BK, n0 + h * Cfg::UMMA_N);
@@ -215,7 +218,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int rr = (lane >> 3) + 4 * i, cc = lane & 7;
               const float4 val = *reinterpret_cast<const float4*>(stg + stg_f32(rr, cc));
               const long long m = m_base + rr;
-              if (m < a.M) *reinterpret_cast<float4*>(out + m * a.ldo + n + cc * 4) = val;
+              if (m < a.M) {
+                *reinterpret_cast<float4*>(out + m * a.ldo + n + cc * 4) = val;
+                if (a.shadow != nullptr)
+                  *reinterpret_cast<uint2*>(a.shadow + m * a.ldo + n + cc * 4) = make_uint2(pack_bf16(val.x, val.y), pack_bf16(val.z, val.w));
+              }
             }
           }
           __syncwarp();
@@ -377,10 +384,19 @@ int num_sms() {
 }
 
 template <int BN, bool LN>
-static int launch_gemm_t(const void* A, long long lda, const void* W, GemmArgs& a, cudaStream_t st) {
+static int launch_gemm_t(const void* A, long long lda, const void* W, GemmArgs& a, cudaStream_t st,
+                         const void* A2 = nullptr, long long lda2 = 0, int K1 = 0) {
   using Cfg = GemmCfg<BN>;
-  CUtensorMap tmA, tmB;
-  if (!encode_tmap_2d_bf16(&tmA, A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)lda * 2, BK, BM)) return PANGU_ERR_CUDA;
+  CUtensorMap tmA, tmA2, tmB;
+  const int Ka = A2 ? K1 : a.K;                      // columns of the first A tensor
+  if (!encode_tmap_2d_bf16(&tmA, A, (uint64_t)Ka, (uint64_t)a.M, (uint64_t)lda * 2, BK, BM)) return PANGU_ERR_CUDA;
+  if (A2) {
+    if (!encode_tmap_2d_bf16(&tmA2, A2, (uint64_t)(a.K - K1), (uint64_t)a.M, (uint64_t)lda2 * 2, BK, BM)) return PANGU_ERR_CUDA;
+    a.k_blocks_a1 = K1 / BK;
+  } else {
+    tmA2 = tmA;
+    a.k_blocks_a1 = 1 << 30;
+  }
   if (!encode_tmap_2d_bf16(&tmB, W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K * 2, BK, Cfg::UMMA_N)) return PANGU_ERR_CUDA;
   a.m_tiles = (int)((a.M + BM - 1) / BM);
   a.n_tiles = a.N / BN;
@@ -394,33 +410,39 @@ static int launch_gemm_t(const void* A, long long lda, const void* W, GemmArgs& 
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmB, a);
+  kern<<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, a);
   return check_launch("gemm_bf16");
 }
 
 }  // namespace tc
 
 int launch_tc_linear_pair(const void* A, long long lda, const void* W, const float* bias, void* out,
-                          long long ldo, long long M, int K, int N, int act, int out_dtype, cudaStream_t st);
+                          long long ldo, long long M, int K, int N, int act, int out_dtype, void* shadow, cudaStream_t st);
 
+// A2 != nullptr: the A operand is the channel concat cat(A[M,K1], A2[M,K-K1]) (models/pangu_model.py:98), read
+// from the two tensors directly.  shadow != nullptr (fp32 output only): also write a bf16 copy of the output.
 int launch_tc_linear(const void* A, long long lda, const void* W, const float* bias, void* out,
-                     long long ldo, long long M, int K, int N, int act, int out_dtype, cudaStream_t st) {
+                     long long ldo, long long M, int K, int N, int act, int out_dtype, cudaStream_t st,
+                     void* shadow, const void* A2, long long lda2, int K1) {
   if (M == 0) return PANGU_OK;
+  if (shadow && out_dtype != PANGU_F32) { set_error("linear(bf16): a bf16 shadow needs an fp32 output"); return PANGU_ERR_BAD_ARG; }
+  if (A2 && (K1 <= 0 || K1 >= K || K1 % tc::BK || (K - K1) % tc::BK || lda2 % 8)) { set_error("linear(bf16): concat split K1=%d of K=%d must be a multiple of 64", K1, K); return PANGU_ERR_BAD_ARG; }
   if (K % 8 || lda % 8 || ldo % 8) { set_error("linear(bf16): K, lda, ldo must be multiples of 8 (K=%d lda=%lld ldo=%lld)", K, lda, ldo); return PANGU_ERR_BAD_ARG; }
   if (out_dtype != PANGU_BF16 && out_dtype != PANGU_F32) { set_error("linear(bf16): bad out_dtype"); return PANGU_ERR_BAD_ARG; }
   {   // skinny-K shapes: A-resident CTA-pair kernel (tc_gemm2.cu); $PANGU_B200_GEMM2=0 keeps the tiled kernel
     static const bool use_pair = []() { const char* e = getenv("PANGU_B200_GEMM2"); return e == nullptr || atoi(e) != 0; }();
-    if (use_pair) {
-      const int rc = launch_tc_linear_pair(A, lda, W, bias, out, ldo, M, K, N, act, out_dtype, st);
+    if (use_pair && !A2) {
+      const int rc = launch_tc_linear_pair(A, lda, W, bias, out, ldo, M, K, N, act, out_dtype, shadow, st);
       if (rc != PANGU_ERR_UNSUPPORTED) return rc;
     }
   }
   tc::GemmArgs a{};
   a.M = M; a.K = K; a.N = N; a.bias = bias; a.out = out; a.ldo = ldo; a.out_dtype = out_dtype; a.act = act;
-  if (N % 256 == 0) return tc::launch_gemm_t<256, false>(A, lda, W, a, st);
-  if (N % 192 == 0) return tc::launch_gemm_t<192, false>(A, lda, W, a, st);
-  if (N % 160 == 0) return tc::launch_gemm_t<160, false>(A, lda, W, a, st);
-  if (N % 64 == 0) return tc::launch_gemm_t<64, false>(A, lda, W, a, st);
+  a.shadow = reinterpret_cast<__nv_bfloat16*>(shadow);
+  if (N % 256 == 0) return tc::launch_gemm_t<256, false>(A, lda, W, a, st, A2, lda2, K1);
+  if (N % 192 == 0) return tc::launch_gemm_t<192, false>(A, lda, W, a, st, A2, lda2, K1);
+  if (N % 160 == 0) return tc::launch_gemm_t<160, false>(A, lda, W, a, st, A2, lda2, K1);
+  if (N % 64 == 0) return tc::launch_gemm_t<64, false>(A, lda, W, a, st, A2, lda2, K1);
   set_error("linear(bf16): N=%d is not a multiple of 256/192/160/64", N);
   return PANGU_ERR_UNSUPPORTED;
 }

@@ -29,6 +29,7 @@ struct Gemm2Args {
   void* out;
   long long ldo;
   int out_dtype, act;
+  __nv_bfloat16* shadow;      // optional bf16 copy of an fp32 output
 };
 
 template <int KB>                                 // K / 64
@@ -209,7 +210,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const int rr = (lane >> 3) + 4 * i, cc = lane & 7;
               const float4 val = *reinterpret_cast<const float4*>(stg + g2_stg_f32(rr, cc));
               const long long m = m_base + rr;
-              if (m < a.M) *reinterpret_cast<float4*>(out + m * a.ldo + n + cc * 4) = val;
+              if (m < a.M) {
+                *reinterpret_cast<float4*>(out + m * a.ldo + n + cc * 4) = val;
+                if (a.shadow != nullptr)
+                  *reinterpret_cast<uint2*>(a.shadow + m * a.ldo + n + cc * 4) = make_uint2(pack_bf16(val.x, val.y), pack_bf16(val.z, val.w));
+              }
             }
           }
           __syncwarp();
@@ -255,10 +260,11 @@ static int launch_gemm2_t(const void* A, long long lda, const void* W, Gemm2Args
 // Returns PANGU_ERR_UNSUPPORTED (without touching the error string) when the shape is not one this kernel
 // covers; the caller then uses the generic tiled GEMM.
 int launch_tc_linear_pair(const void* A, long long lda, const void* W, const float* bias, void* out,
-                          long long ldo, long long M, int K, int N, int act, int out_dtype, cudaStream_t st) {
+                          long long ldo, long long M, int K, int N, int act, int out_dtype, void* shadow, cudaStream_t st) {
   if ((K != 192 && K != 384) || N % tc::G2_BN != 0 || M < 2048 || lda % 8 || ldo % 8) return PANGU_ERR_UNSUPPORTED;
   tc::Gemm2Args a{};
   a.M = M; a.N = N; a.bias = bias; a.out = out; a.ldo = ldo; a.out_dtype = out_dtype; a.act = act;
+  a.shadow = reinterpret_cast<__nv_bfloat16*>(shadow);
   return K == 192 ? tc::launch_gemm2_t<3>(A, lda, W, a, st) : tc::launch_gemm2_t<6>(A, lda, W, a, st);
 }
 

@@ -160,14 +160,14 @@ class _Worker:
 
     def __init__(self, model, plan):
         self.m, self.plan = model, plan
-        self.x = self.xb = self.skip = self.qkv = self.o = self.halo_qkv = self.halo_lo_qkv = self.halo_o = None
+        self.x = self.xb = self.skip = self.skip_b = self.qkv = self.o = self.halo_qkv = self.halo_lo_qkv = self.halo_o = None
 
     # --- row-local stages
     def embed(self, inp, inp_s, stats, maps, const_h):
         self.x, self.xb = PF.patch_embed_forward(self.m._input_layer, inp, inp_s, stats, maps, const_h, "bf16")
 
     def downsample(self):
-        self.skip = self.x
+        self.skip, self.skip_b = self.x, self.xb
         self.x, self.xb = self.m.downsample.forward_sample(self.x, Z, self.plan.nrows("A"), TOK_W["A"])
 
     def upsample(self):
@@ -177,7 +177,7 @@ class _Worker:
     def recover(self):
         lat = self.plan.pix[1] - self.plan.pix[0]
         return PF.patch_recover_forward(self.m._output_layer, self.x, Z, self.plan.nrows("A"), TOK_W["A"], "bf16",
-                                        skip=self.skip, lat=lat)
+                                        skip=self.skip, lat=lat, xb=self.xb, skip_b=self.skip_b)
 
     # --- one EarthSpecificBlock in three phases around the two neighbour exchanges
     def block_qkv(self, blk, stage):

@@ -188,9 +188,10 @@ def patch_embed_forward(pe, inp, inp_s, statistics, maps, const_h, mode):
         ops.linear(pu, _w2d(pe.conv.weight), _f(pe.conv.bias), out=x[ns:])
         return x, None
     wc = pe._wcache
-    ops.linear(ps, wc.bf16("cs", pe.conv_surface.weight), _f(pe.conv_surface.bias), out=x[:ns])
-    ops.linear(pu, wc.bf16("c", pe.conv.weight), _f(pe.conv.bias), out=x[ns:])
-    return x, None
+    xb = torch.empty((8 * ns, dim), dtype=torch.bfloat16, device=inp.device)      # bf16 shadow written by the GEMMs
+    ops.linear_ex(ps, wc.bf16("cs", pe.conv_surface.weight), _f(pe.conv_surface.bias), out=x[:ns], shadow=xb[:ns])
+    ops.linear_ex(pu, wc.bf16("c", pe.conv.weight), _f(pe.conv.bias), out=x[ns:], shadow=xb[ns:])
+    return x, xb
 
 
 def downsample_forward(ds, x, Z, H, W, mode):
@@ -199,8 +200,7 @@ def downsample_forward(ds, x, Z, H, W, mode):
         m = ops.downsample_merge_ln(x, _f(ds.norm.weight), _f(ds.norm.bias), Z, H, W, torch.float32, ds.norm.eps)
         return ops.linear(m, _w2d(ds.linear.weight), None), None
     m = ops.downsample_merge_ln(x, _f(ds.norm.weight), _f(ds.norm.bias), Z, H, W, torch.bfloat16, ds.norm.eps)
-    y = ops.linear(m, ds._wcache.bf16("l", ds.linear.weight), None, out_dtype=torch.float32)
-    return y, None
+    return ops.linear_ex(m, ds._wcache.bf16("l", ds.linear.weight), None, want_shadow=True)
 
 
 def upsample_forward(us, x, mode, xb=None, Z=8, H2=91, W2=180, H=181):
@@ -214,10 +214,10 @@ def upsample_forward(us, x, mode, xb=None, Z=8, H2=91, W2=180, H=181):
         xb = ops.cast_bf16(x)
     y = ops.linear(xb, wc.bf16("l1", us.linear1.weight), None)
     n = ops.upsample_shuffle_ln(y, _f(us.norm.weight), _f(us.norm.bias), Z, H2, W2, H, torch.bfloat16, us.norm.eps)
-    return ops.linear(n, wc.bf16("l2", us.linear2.weight), None, out_dtype=torch.float32), None
+    return ops.linear_ex(n, wc.bf16("l2", us.linear2.weight), None, want_shadow=True)
 
 
-def patch_recover_forward(pr, x, Z, H, W, mode, skip=None, lat=721, denorm=None):
+def patch_recover_forward(pr, x, Z, H, W, mode, skip=None, lat=721, denorm=None, xb=None, skip_b=None):
     """PatchRecovery_pretrain.forward (models/layers.py:582-621).  x [N, dim] fp32, or when `skip` is given
     the pair (skip, x) whose channel concat (models/pangu_model.py:98) is the input."""
     if (Z, W) != (8, 360) or H != (lat + 3) // 4:
@@ -230,8 +230,13 @@ def patch_recover_forward(pr, x, Z, H, W, mode, skip=None, lat=721, denorm=None)
         yu = ops.linear(x[ns:], _w2d(pr.conv.weight), _f(pr.conv.bias))
         ys = ops.linear(x[:ns], _w2d(pr.conv_surface.weight), _f(pr.conv_surface.bias))
         return ops.patch_recover_scatter(yu, ys, lat, denorm)
-    xb = ops.concat_cast_bf16(skip, x) if skip is not None else ops.cast_bf16(x)
     wc = pr._wcache
+    if skip is not None and xb is not None and skip_b is not None:
+        # the skip concat (models/pangu_model.py:98) is read by the GEMMs from the two bf16 shadows directly
+        yu = ops.linear_ex(skip_b[ns:], wc.bf16("c", pr.conv.weight), _f(pr.conv.bias), a2=xb[ns:])
+        ys = ops.linear_ex(skip_b[:ns], wc.bf16("cs", pr.conv_surface.weight), _f(pr.conv_surface.bias), a2=xb[:ns])
+        return ops.patch_recover_scatter(yu, ys, lat, denorm)
+    xb = ops.concat_cast_bf16(skip, x) if skip is not None else ops.cast_bf16(x)
     yu = ops.linear(xb[ns:], wc.bf16("c", pr.conv.weight), _f(pr.conv.bias), out_dtype=torch.float32)
     ys = ops.linear(xb[:ns], wc.bf16("cs", pr.conv_surface.weight), _f(pr.conv_surface.bias), out_dtype=torch.float32)
     return ops.patch_recover_scatter(yu, ys, lat, denorm)

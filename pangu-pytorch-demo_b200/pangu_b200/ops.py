@@ -136,6 +136,33 @@ def linear(a, w, bias=None, act=ACT_NONE, out_dtype=None, out=None):
     return out
 
 
+def linear_ex(a, w, bias=None, a2=None, act=ACT_NONE, out_dtype=torch.float32, out=None, shadow=None, want_shadow=False):
+    """bf16 tensor-core linear: out = act(cat(a, a2) @ w.T + bias); optionally also a bf16 shadow of an fp32 output.
+    a [M,K1], a2 [M,K-K1] or None, w [N,K].  -> out, or (out, shadow) when want_shadow / shadow is given."""
+    _chk(a, torch.bfloat16, "a")
+    _chk(w, torch.bfloat16, "w")
+    M, K1 = a.shape
+    N, K = w.shape
+    if a2 is not None:
+        _chk(a2, torch.bfloat16, "a2")
+        if a2.shape != (M, K - K1):
+            raise abi.PanguError(f"linear_ex: a2 must be [{M}, {K - K1}]")
+    elif K1 != K:
+        raise abi.PanguError("linear_ex: a and w disagree on K")
+    if bias is not None:
+        _chk(bias, torch.float32, "bias")
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    if want_shadow and shadow is None:
+        shadow = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    tag = "gemm_bf16[K=%d,N=%d%s%s]" % (K, N, ",cat" if a2 is not None else "", ",shadow" if shadow is not None else "")
+    _call(tag, "pangu_linear_bf16_ex",
+          (_ptr(a), K1, _ptr(a2), (K - K1) if a2 is not None else 0, K1 if a2 is not None else 0, _ptr(w), _ptr(bias),
+           _ptr(out), _ptr(shadow), N, M, K, N, act, _DT[out.dtype], _stream(),), flops=2.0 * M * K * N,
+          nbytes=float(M * K * 2 + out.numel() * out.element_size() + w.numel() * 2 + (M * N * 2 if shadow is not None else 0)))
+    return (out, shadow) if shadow is not None else out
+
+
 def ln_residual(y, gamma, beta, residual=None, want_f32=True, want_bf16=False, eps=1e-5):
     """residual + LayerNorm(y)*gamma + beta -> (fp32 or None, bf16 or None)."""
     _chk(y, name="y")
