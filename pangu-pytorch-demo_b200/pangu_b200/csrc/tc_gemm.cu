@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "tc_common.cuh"
+#include "tc_ln_epilogue.cuh"
 
 namespace pangu {
 namespace tc {
@@ -44,17 +45,27 @@ constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter,
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kStageEpiBytes = 4096;         // per epilogue warp: 32 rows x 128 B staging tile
 
-template <int BN>
+// LayerNorm epilogue configuration (tc_ln_epilogue.cuh): 32-column units with 2 residual tiles in flight at
+// C = 192, 16-column units with 3 in flight at C = 384 (shared memory is tighter there).
+template <int BN> struct LnCfg {
+  static constexpr int UW = BN == 192 ? 32 : 16;
+  static constexpr int D = BN == 192 ? 2 : 3;
+  static constexpr int STG = UW * 128 * (D + 1);              // fp32 staging tiles per warp
+  static constexpr int STGB = UW * 64;                        // bf16 staging tile per warp
+  static constexpr int BYTES = kEpiWarps * (STG + STGB) + 2 * 2 * 128 * 8 + 3 * BN * 4;
+};
+
+template <int BN, bool LN = false>
 struct GemmCfg {
   static constexpr int UMMA_N = BN <= 256 ? BN : BN / 2;      // 384 -> 2 x 192
   static constexpr int N_SPLIT = BN / UMMA_N;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int EPI_BYTES = kEpiWarps * kStageEpiBytes + 2 * 2 * 128 * 8 /*LN partial sums*/;
-  static constexpr int AVAIL = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - EPI_BYTES;
+  static constexpr int EPI_BYTES = LN ? LnCfg<BN>::BYTES : kEpiWarps * kStageEpiBytes;
+  static constexpr int AVAIL = 227 * 1024 - 1024 /*align slack*/ - 512 /*barriers*/ - EPI_BYTES;
   static constexpr int STAGES = AVAIL / STAGE_BYTES > 6 ? 6 : AVAIL / STAGE_BYTES;
   static constexpr int NACC = 2 * BN <= 512 ? 2 : 1;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
   static_assert(BN % 32 == 0, "epilogue works in 32-column chunks");
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
@@ -71,19 +82,24 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 template <int BN, bool LN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                 const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
-  using Cfg = GemmCfg<BN>;
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                 const __grid_constant__ CUtensorMap tmXb, const __grid_constant__ CUtensorMap tmRes, const GemmArgs a) {
+  using Cfg = GemmCfg<BN, LN>;
   constexpr int STAGES = Cfg::STAGES, NACC = Cfg::NACC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES;
-  float2* ln_part = reinterpret_cast<float2*>(epi_smem + kEpiWarps * kStageEpiBytes);   // [2 parity][2 half][128]
+  using LC = LnCfg<LN ? BN : 192>;
+  uint8_t* stgb_smem = epi_smem + kEpiWarps * LC::STG;                                    // LN only
+  float2* ln_part = reinterpret_cast<float2*>(stgb_smem + kEpiWarps * LC::STGB);         // [2 parity][2 half][128]
+  float* sparams = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ln_part) + 2 * 2 * 128 * 8);
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;      // [NACC]
   uint64_t* tempty_bar = tfull_bar + NACC;      // [NACC]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + NACC);
+  uint64_t* ln_bar = tempty_bar + NACC;         // [8 warps][4] residual tile loads of the LN epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ln_bar + 32);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = a.m_tiles * a.n_tiles;
@@ -95,7 +111,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int i = 0; i < NACC; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiWarps); }
+    if (LN) for (int i = 0; i < 32; ++i) mbar_init(&ln_bar[i], 1);
     fence_barrier_init();
+  }
+  if constexpr (LN) {
+    for (int i = threadIdx.x; i < 3 * BN; i += kThreads)      // affine parameters of the LN epilogue -> smem
+      sparams[i] = i < BN ? a.bias[i] : (i < 2 * BN ? a.gamma[i - BN] : a.beta[i - 2 * BN]);
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmRes); }
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tcgen05_before_sync();
@@ -163,11 +185,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int hf = (warp - 4) >> 2;
     uint8_t* stg = epi_smem + (warp - 4) * kStageEpiBytes;
     int acc = 0;
-    uint32_t acc_phase = 0, tile_par = 0;
+    uint32_t acc_phase = 0;
     uint32_t v[32];
+    LnTileEpilogue<LN ? BN : 192, LC::UW, LC::D, true, true> ln;
+    if constexpr (LN) {
+      ln.bias = a.bias; ln.gamma = a.gamma; ln.beta = a.beta; ln.residual = a.residual;
+      ln.x_out = a.x_out; ln.xb = a.x_out_bf16; ln.M = a.M; ln.eps = a.eps;
+      ln.stg = epi_smem + (warp - 4) * LC::STG; ln.stg_b = stgb_smem + (warp - 4) * LC::STGB;
+      ln.ln_part = ln_part; ln.sparams = sparams; ln.q = q; ln.hf = hf; ln.lane = lane; ln.tile_par = 0;
+      ln.tm_out = &tmOut; ln.tm_xb = a.x_out_bf16 != nullptr ? &tmXb : nullptr; ln.tm_res = &tmRes;
+      ln.ld_bar = &ln_bar[(warp - 4) * 4];
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long m_base = (long long)(tile / a.n_tiles) * BM + q * 32;
       const int n0 = (tile % a.n_tiles) * BN;
+      if constexpr (LN) { ln.m_base = m_base; ln.prefetch(); }     // residual tiles fly while the MMAs finish
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -228,81 +260,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
         }
       } else {
-        // LayerNorm over the full row (BN == C).  Pass 1: row sums of x and x^2 (fp32) over this warp's
-        // chunks, combined with the sibling warp through smem.  Pass 2: normalise, affine, add the fp32
-        // residual (fetched row-contiguously, staged), write fp32 + bf16 row-contiguously.
-        float s = 0.f, ss = 0.f;
-#pragma unroll 1
-        for (int c = hf; c < BN / 32; c += 2) {
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c * 32 + j));
-            const float x0 = __uint_as_float(v[j]) + b.x, x1 = __uint_as_float(v[j + 1]) + b.y;
-            const float x2 = __uint_as_float(v[j + 2]) + b.z, x3 = __uint_as_float(v[j + 3]) + b.w;
-            s += (x0 + x1) + (x2 + x3);
-            ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
-          }
-        }
-        float2* part = ln_part + tile_par * 256;
-        part[hf * 128 + q * 32 + lane] = make_float2(s, ss);
-        epi_bar_sync();
-        const float2 p0 = part[q * 32 + lane], p1 = part[128 + q * 32 + lane];
-        const float mean = (p0.x + p1.x) * (1.0f / BN);
-        const float var = fmaxf((p0.y + p1.y) * (1.0f / BN) - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + a.eps);
-        tile_par ^= 1;
-
-        const int rcc = lane & 7;               // row-contiguous view: chunk rcc of rows (lane>>3) + 4i
-        float4 rg[8];
-        auto load_residual = [&](int c) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const long long m = m_base + (lane >> 3) + 4 * i;
-            rg[i] = (a.residual != nullptr && m < a.M)
-                        ? __ldg(reinterpret_cast<const float4*>(a.residual + m * BN + c * 32 + rcc * 4))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        };
-        load_residual(hf);
-#pragma unroll 1
-        for (int c = hf; c < BN / 32; c += 2) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(stg + stg_f32((lane >> 3) + 4 * i, rcc)) = rg[i];
-          __syncwarp();
-          if (c + 2 < BN / 32) load_residual(c + 2);
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            const int j = cc * 4;
-            float4* p = reinterpret_cast<float4*>(stg + stg_f32(lane, cc));
-            float4 r = *p;
-            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + c * 32 + j));
-            const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + c * 32 + j));
-            const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta + c * 32 + j));
-            r.x += fmaf((__uint_as_float(v[j]) + b.x - mean) * rstd, g.x, be.x);
-            r.y += fmaf((__uint_as_float(v[j + 1]) + b.y - mean) * rstd, g.y, be.y);
-            r.z += fmaf((__uint_as_float(v[j + 2]) + b.z - mean) * rstd, g.z, be.z);
-            r.w += fmaf((__uint_as_float(v[j + 3]) + b.w - mean) * rstd, g.w, be.w);
-            *p = r;
-          }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = (lane >> 3) + 4 * i;
-            const long long m = m_base + rr;
-            const float4 val = *reinterpret_cast<const float4*>(stg + stg_f32(rr, rcc));
-            if (m < a.M) {
-              const long long off = m * BN + c * 32 + rcc * 4;
-              *reinterpret_cast<float4*>(a.x_out + off) = val;
-              if (a.x_out_bf16 != nullptr)
-                *reinterpret_cast<uint2*>(a.x_out_bf16 + off) = make_uint2(pack_bf16(val.x, val.y), pack_bf16(val.z, val.w));
-            }
-          }
-          __syncwarp();
+        // LayerNorm over the full row (BN == C) + residual (tc_ln_epilogue.cuh): residual tiles arrive by TMA
+        // (issued before the accumulator was complete), results leave through TMA bulk stores.
+        if constexpr (LN) {
+          ln.stats(taddr);
+          ln.all_units(taddr);
         }
       }
       // all of this warp's TMEM reads are done -> hand the accumulator back to the MMA warp
@@ -311,6 +273,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
     }
+    if constexpr (LN) ln.drain_stores();
   }
 
   tcgen05_before_sync();
@@ -386,7 +349,7 @@ int num_sms() {
 template <int BN, bool LN>
 static int launch_gemm_t(const void* A, long long lda, const void* W, GemmArgs& a, cudaStream_t st,
                          const void* A2 = nullptr, long long lda2 = 0, int K1 = 0) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, LN>;
   CUtensorMap tmA, tmA2, tmB;
   const int Ka = A2 ? K1 : a.K;                      // columns of the first A tensor
   if (!encode_tmap_2d_bf16(&tmA, A, (uint64_t)Ka, (uint64_t)a.M, (uint64_t)lda * 2, BK, BM)) return PANGU_ERR_CUDA;
@@ -398,6 +361,14 @@ static int launch_gemm_t(const void* A, long long lda, const void* W, GemmArgs& 
     a.k_blocks_a1 = 1 << 30;
   }
   if (!encode_tmap_2d_bf16(&tmB, W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K * 2, BK, Cfg::UMMA_N)) return PANGU_ERR_CUDA;
+  CUtensorMap tmOut = tmA, tmXb = tmA, tmRes = tmA;
+  if constexpr (LN) {
+    constexpr int UW = LnCfg<BN>::UW;
+    if (!a.residual) { set_error("linear_ln(bf16): a residual tensor is required"); return PANGU_ERR_BAD_ARG; }
+    if (!encode_tmap_2d(&tmOut, 0, a.x_out, BN, (uint64_t)a.M, (uint64_t)BN * 4, UW, 32, UW * 4)) return PANGU_ERR_CUDA;
+    if (!encode_tmap_2d(&tmRes, 0, a.residual, BN, (uint64_t)a.M, (uint64_t)BN * 4, UW, 32, UW * 4)) return PANGU_ERR_CUDA;
+    if (a.x_out_bf16 && !encode_tmap_2d(&tmXb, 1, a.x_out_bf16, BN, (uint64_t)a.M, (uint64_t)BN * 2, UW, 32, UW * 2)) return PANGU_ERR_CUDA;
+  }
   a.m_tiles = (int)((a.M + BM - 1) / BM);
   a.n_tiles = a.N / BN;
   a.k_blocks = (a.K + BK - 1) / BK;
@@ -410,7 +381,7 @@ static int launch_gemm_t(const void* A, long long lda, const void* W, GemmArgs& 
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, a);
+  kern<<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmOut, tmXb, tmRes, a);
   return check_launch("gemm_bf16");
 }
 

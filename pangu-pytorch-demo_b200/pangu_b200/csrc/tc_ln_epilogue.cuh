@@ -22,9 +22,9 @@ __device__ __forceinline__ int ln_stg16(int r, int cc) { return r * 64 + ((cc ^ 
 
 // UW = unit width in columns (16: 64-byte row segments, 2 KiB staging per warp; 32: 128-byte segments, 4 KiB --
 // fewer instructions per byte), D = prefetch depth in units (register slots).
-// ASYNC (needs D == 1 and 2 staging tiles per warp): the residual tile is prefetched by ONE TMA load per warp
-// straight into the (hardware-swizzled) staging tile, completion on a per-warp mbarrier -- no registers held
-// across the interleaved GELU chunks of tc_mlp.cu and no per-lane address arithmetic.
+// ASYNC: the residual tiles are prefetched by ONE TMA load per warp and unit straight into (hardware-swizzled)
+// staging tiles -- NBUF = D + 1 tiles and mbarriers per warp, D units in flight -- no registers held across
+// other work (the interleaved GELU chunks of tc_mlp.cu) and no per-lane address arithmetic.
 // TMASTORE: results leave through TMA bulk stores issued by one lane from the (hardware-swizzle-compatible) staging
 // tiles -- fp32 tile in place, bf16 tile in `stg_b` -- instead of 2 x NV st.global per lane; the affine parameters
 // (bias, gamma, beta) are then read from a shared-memory copy `sparams` [3][C] (broadcast LDS) rather than __ldg.
@@ -35,18 +35,18 @@ struct LnTileEpilogue {
   uint8_t* stg_b = nullptr;                          // per warp: 32 rows x UW bf16
   const float* sparams = nullptr;                    // smem [3][C]: bias, gamma, beta
   const CUtensorMap* tm_res = nullptr;               // ASYNC: fp32 residual [M, C], same box / swizzle as tm_out
-  uint64_t* ld_bar = nullptr;                        // ASYNC: this warp's mbarrier (count 1) for the tile loads
-  uint32_t ld_phase = 0;
+  uint64_t* ld_bar = nullptr;                        // ASYNC: this warp's NBUF mbarriers (count 1) for the tile loads
+  uint32_t ld_phase = 0;                             // bit b = phase of ld_bar[b]
   __device__ __forceinline__ static int stg_b_off(int r, int cc) {   // 16-byte chunk cc of bf16 row r
     return UW == 32 ? r * 64 + ((cc ^ ((r >> 1) & 3)) << 4) : r * 32 + ((cc ^ ((r >> 2) & 1)) << 4);
   }
   static constexpr int UNIT_BYTES = UW * 128;        // one staging tile: 32 rows x UW fp32
-  static_assert(!ASYNC || D == 1, "cp.async prefetch keeps exactly one unit in flight");
+  static constexpr int NBUF = ASYNC ? D + 1 : 1;     // staging tiles per warp (ASYNC: D landing tiles + the one being consumed)
   static constexpr int NU = C / (2 * UW);            // units per warp
   static constexpr int NV = UW / 4;                  // float4 per lane per unit
   static constexpr int RPI = 128 / UW;               // rows covered by one warp-wide 16-byte access (8 or 4)
   static_assert(UW == 16 || UW == 32, "unit width");
-  static_assert(NU % D == 0, "units are processed in groups of the prefetch depth");
+  static_assert(ASYNC || NU % D == 0, "register prefetch: units are processed in groups of the prefetch depth");
   __device__ __forceinline__ static int stg_off(int r, int cc) {
     return UW == 16 ? r * 64 + ((cc ^ ((r >> 1) & 3)) << 4) : r * 128 + ((cc ^ (r & 7)) << 4);
   }
@@ -69,9 +69,10 @@ struct LnTileEpilogue {
   __device__ __forceinline__ void load_residual(int idx) {
     const int u = hf + 2 * idx, rcc = lane & (NV - 1), rr0 = lane / NV;
     if constexpr (ASYNC) {                             // one TMA tile load per warp (rows >= M are zero-filled)
+      const int b = idx % NBUF;
       if (lane == 0) {
-        mbar_expect_tx(ld_bar, UNIT_BYTES);
-        tma_load_2d(stg + (idx & 1) * UNIT_BYTES, tm_res, ld_bar, u * UW, (int)m_base);
+        mbar_expect_tx(&ld_bar[b], UNIT_BYTES);
+        tma_load_2d(stg + b * UNIT_BYTES, tm_res, &ld_bar[b], u * UW, (int)m_base);
       }
       __syncwarp();
       return;
@@ -84,6 +85,16 @@ struct LnTileEpilogue {
     }
   }
   __device__ __forceinline__ void prefetch() {
+    if constexpr (ASYNC) {
+      if constexpr (TMASTORE) {                        // the previous tile's bulk stores still read the staging tiles
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+        if (i < NU) load_residual<0>(i);
+      return;
+    }
     load_residual<0>(0);
     if constexpr (D > 1) load_residual<(D > 1 ? 1 : 0)>(1);
     if constexpr (D > 2) load_residual<(D > 2 ? 2 : 0)>(2);
@@ -124,16 +135,21 @@ struct LnTileEpilogue {
       __syncwarp();
     }
     if constexpr (ASYNC) {
-      stg_u = stg + (idx & 1) * UNIT_BYTES;
-      mbar_wait(ld_bar, ld_phase);
-      ld_phase ^= 1;
+      // the tile that unit idx-1 consumed (and stored from) is free again: refill it with unit idx+D
+      if (idx + D < NU) load_residual<0>(idx + D);     // lands in tile (idx - 1) mod NBUF
+      const int b = idx % NBUF;
+      stg_u = stg + b * UNIT_BYTES;
+      mbar_wait(&ld_bar[b], (ld_phase >> b) & 1);
+      ld_phase ^= 1u << b;
     } else {
 #pragma unroll
       for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(stg + stg_off(rr0 + RPI * i, rcc)) = rg[S][i];
     }
     __syncwarp();
     if (dbg) dbg[1] = clock64();
-    if (idx + D < NU) load_residual<S>(idx + D);
+    if constexpr (!ASYNC) {
+      if (idx + D < NU) load_residual<S>(idx + D);
+    }
     if (dbg) dbg[2] = clock64();
     uint32_t w[UW];
     if constexpr (UW == 16) tmem_ld_32x16(y + u * 16, reinterpret_cast<uint32_t(&)[16]>(w));
@@ -211,6 +227,11 @@ struct LnTileEpilogue {
   }
   // all of pass 2 back to back
   __device__ __forceinline__ void all_units(uint32_t y, bool store = true) {
+    if constexpr (ASYNC) {
+#pragma unroll 1
+      for (int idx = 0; idx < NU; ++idx) unit<0>(y, idx, store);
+      return;
+    }
 #pragma unroll 1
     for (int base = 0; base < NU; base += D) {
       unit<0>(y, base, store);

@@ -108,8 +108,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* y_empty = bars + 8;      // [2]  epilogue -> MMA: Y accumulator drained     (leader's copy)
   uint64_t* w_full = bars + 10;      // [NSLOT]
   uint64_t* w_empty = bars + 10 + NSLOT;
-  uint64_t* ln_bar = bars + 10 + 2 * NSLOT;      // [8] per-epilogue-warp barrier of the residual tile loads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18 + 2 * NSLOT);
+  uint64_t* ln_bar = bars + 10 + 2 * NSLOT;      // [8 warps][2] barriers of the residual tile loads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26 + 2 * NSLOT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                    // 0 = leader of the pair
@@ -130,7 +130,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     mbar_init(&p_full[0], 2 * kMlpEpiWarps); mbar_init(&p_full[1], 2 * kMlpEpiWarps);
     for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 2 * kMlpEpiWarps); }
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int i = 0; i < kMlpEpiWarps; ++i) mbar_init(&ln_bar[i], 1);
+    for (int i = 0; i < 2 * kMlpEpiWarps; ++i) mbar_init(&ln_bar[i], 1);
     fence_barrier_init();
   }
   cluster_sync_all();                                         // barrier inits visible to the peer CTA
@@ -266,7 +266,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     ln.x_out = a.x_out; ln.xb = a.x_out_bf16; ln.M = a.M; ln.eps = a.eps;
     ln.tm_out = &tmOut; ln.tm_xb = a.x_out_bf16 != nullptr ? &tmXb : nullptr;
     ln.stg_b = stgb_smem + (warp - 4) * Cfg::STGB_BYTES; ln.sparams = sparams;
-    ln.tm_res = &tmRes; ln.ld_bar = &ln_bar[warp - 4];
+    ln.tm_res = &tmRes; ln.ld_bar = &ln_bar[(warp - 4) * 2];
+    static_assert(Ln::NBUF <= 2, "two load barriers per epilogue warp");
     ln.stg = epi_smem + (warp - 4) * Cfg::STG_BYTES; ln.ln_part = ln_part; ln.q = q; ln.hf = hf; ln.lane = lane; ln.tile_par = 0;
     const bool ln_store = !(a.dbg & 32);
 
