@@ -228,6 +228,72 @@ int pangu_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
 int pangu_concat_cast_bf16(const float* a, const float* b, void* out, int64_t n, int32_t C1,
                            int32_t C2, void* stream);
 
+/* ------------------------------------------------------------------ fine-tune backward (autograd of the above)
+ * The reference obtains these by torch.autograd over models/layers.py (loss.backward(), models/pangu_sample.py:226,
+ * under DDP, finetune/finetune_fully.py:220); each entry cites the forward lines it differentiates.  bf16 operands,
+ * fp32 accumulation; parameter gradients are fp32 and ACCUMULATED (+=) into caller-zeroed buffers. */
+
+/* out = A . W^T + bias + addend (fp32 out; addend fp32 [M,N] with the pitch of out, or NULL): a dgrad GEMM
+ * (dX = dY . W, with W given transposed) fused with the residual-gradient add of models/layers.py:296-297. */
+int pangu_linear_bf16_add(const void* A, int64_t lda, const void* W, const float* bias, const float* addend,
+                          float* out, int64_t ldo, int64_t M, int32_t K, int32_t N, void* stream);
+
+/* dW[n_out, k_in] += dY[M, n_out]^T . X[M, k_in] -- weight gradient of nn.Linear / Conv1d(k=1)
+ * (models/layers.py:88,113,312,315,419,481,522,542,566,591,608).  dY, X bf16 row-major [tokens, channels] exactly as
+ * the passes leave them (read MN-major by tcgen05.mma; no transposes), dW fp32 with row pitch ldw.  Split over
+ * token ranges, reduced with red.global.add.v4.f32. */
+int pangu_linear_wgrad_bf16(const void* dy, int64_t ldy, const void* x, int64_t ldx, float* dw, int64_t ldw,
+                            int64_t M, int32_t n_out, int32_t k_in, void* stream);
+
+/* out[c] += sum_m x[m, c] -- bias gradients.  dtype of x: PANGU_F32 / PANGU_BF16; ld in elements. */
+int pangu_colsum(const void* x, int dtype, int64_t ld, int64_t M, int32_t C, float* out, void* stream);
+
+/* Backward of out = scale * (LayerNorm_C(y) * gamma + beta) (models/layers.py:296-297 with the DropPath factor):
+ *   dy (bf16) = d out / d y applied to dout (+ dout2 when not NULL: the two gradient streams that meet at a residual),
+ *   dgamma += scale * sum dout * yhat, dbeta += scale * sum dout, dcolsum += sum dy (bias gradient of the linear
+ *   that produced y); any of the three may be NULL.  y fp32 or bf16 [M, C], C in {192, 384}. */
+int pangu_ln_backward(const float* dout, const float* dout2, const void* y, int y_dtype, const float* gamma,
+                      float scale, void* dy, float* dgamma, float* dbeta, float* dcolsum, int64_t M, int32_t C,
+                      float eps, void* stream);
+
+/* Backward of pangu_upsample_shuffle_ln (models/layers.py:546-563): dout fp32 [Z*H*2*W2, Cout], y bf16 [Z*H2*W2, 4*Cout]
+ * -> dy bf16 (same layout as y; the caller zero-fills it: the cropped row gets no gradient), dgamma/dbeta +=. */
+int pangu_upsample_shuffle_ln_backward(const float* dout, const void* y, const float* gamma, void* dy, float* dgamma,
+                                       float* dbeta, int32_t Z, int32_t H2, int32_t W2, int32_t H, int32_t Cout,
+                                       float eps, void* stream);
+
+/* Backward of pangu_downsample_merge_ln (models/layers.py:501-519): dout fp32 [Z*ceil(H/2)*(W/2), 4C], x fp32
+ * [Z*H*W, C] -> dx fp32 (every real token is written exactly once; the pad row is dropped), dgamma/dbeta +=. */
+int pangu_downsample_merge_ln_backward(const float* dout, const float* x, const float* gamma, float* dx,
+                                       float* dgamma, float* dbeta, int32_t Z, int32_t H, int32_t W, int32_t C,
+                                       float eps, void* stream);
+
+/* h = GELU(h_pre), exact erf form, bf16, n % 8 == 0 (recompute of models/layers.py:313 for the backward). */
+int pangu_gelu_bf16(const void* h_pre, void* h, int64_t n, void* stream);
+/* dh_pre = dh * GELU'(h_pre) (bf16 [M, F]; dh_pre may alias dh), dcolsum[F] += sum_m dh_pre (or NULL). */
+int pangu_gelu_backward_bf16(const void* dh, const void* h_pre, void* dh_pre, float* dcolsum, int64_t M, int32_t F,
+                             void* stream);
+
+/* pangu_window_attention_band on the whole grid with pre-scaled operands (see there), additionally writing
+ * lse [nLon, T, heads, 144] fp32 = log2-sum-exp of every score row, which the backward kernel consumes. */
+int pangu_window_attention_train(const void* qkv, const float* qkv_bias, const void* earth_bias, void* out,
+                                 float* lse, const pangu_geom* g, int roll, void* stream);
+
+/* Backward of the window attention (models/layers.py:431-478 inside :224-293).  qkv / qkv_bias / earth_bias (bf16)
+ * pre-scaled exactly as given to pangu_window_attention_train, out its output, d_out bf16 [N, C] the incoming
+ * gradient, lse from the forward.  Writes d_qkv bf16 [N, 3C] (w.r.t. the UN-scaled linear1 output, token order);
+ * accumulates d_earth_bias fp32 [T, heads, 144, 144] (sum over longitude windows of dS; gradient of the fp32
+ * earth_specific_bias parameter) and d_qkv_bias_pad fp32 [3C] (the zero-pad rows' share of linear1's bias gradient:
+ * those rows equal the bias in the forward, models/layers.py:228,419).  roll as in pangu_window_attention. */
+int pangu_window_attention_backward(const void* qkv, const float* qkv_bias, const void* earth_bias, const void* out,
+                                    const void* d_out, const float* lse, void* d_qkv, float* d_earth_bias,
+                                    float* d_qkv_bias_pad, const pangu_geom* g, int roll, void* stream);
+
+/* Inverse of pangu_patch_recover_scatter_rows (models/layers.py:593-619): gradients of the output fields ->
+ * gradients of the two conv outputs as bf16 [7*tok_rows*360, 160] / [tok_rows*360, 64]; cropped positions get 0. */
+int pangu_patch_recover_gather_backward(const float* d_output, const float* d_output_surface, void* dy_upper,
+                                        void* dy_surface, int32_t lat_rows, int32_t tok_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -206,21 +206,24 @@ def layer_norm(x, params, prefix):
     return F.layer_norm(x, (x.shape[-1],), params[prefix + "weight"], params[prefix + "bias"], 1e-5)
 
 
-def earth_block(x, Z, H, W, roll, params, prefix, heads):
-    """EarthSpecificBlock.forward in eval mode (DropPath = identity), models/layers.py:218-299."""
+def earth_block(x, Z, H, W, roll, params, prefix, heads, s1=1.0, s2=1.0):
+    """EarthSpecificBlock.forward, models/layers.py:218-299.  s1 / s2: what DropPath multiplies the two residual
+    branches of this (single) sample by -- 1 in eval mode; in training 0 or 1/keep (timm DropPath, per-sample
+    Bernoulli mask divided by keep, models/layers.py:171,296-297).  Differentiable torch code: the fine-tune
+    gradients of the reference are torch.autograd over exactly these ops."""
     assert x.shape[0] == 1
     C = x.shape[-1]
-    src = torch.from_numpy(window_source_index(Z, H, W, roll))           # [nLon, T, 144]
+    src = torch.from_numpy(window_source_index(Z, H, W, roll)).to(x.device)   # [nLon, T, 144]
     padded = torch.cat((x[0], x.new_zeros(1, C)), dim=0)                 # index -1 -> zero row
     xw = padded[src]                                                     # gather == pad+roll+partition
-    mask = torch.from_numpy(shift_mask(Z, H, W)) if roll else None
+    mask = torch.from_numpy(shift_mask(Z, H, W)).to(x.device) if roll else None
     aw = window_attention(xw, mask, params, prefix + "attention.", heads)
     keep = src >= 0                                                      # reverse+unroll+crop (:269-293)
     y = torch.empty_like(x[0])
     y[src[keep]] = aw[keep]
     y = y.unsqueeze(0)
-    x = x + layer_norm(y, params, prefix + "norm1.")                     # :296 (post-norm)
-    x = x + layer_norm(mlp(x, params, prefix + "linear."), params, prefix + "norm2.")   # :297
+    x = x + s1 * layer_norm(y, params, prefix + "norm1.")                # :296 (post-norm)
+    x = x + s2 * layer_norm(mlp(x, params, prefix + "linear."), params, prefix + "norm2.")   # :297
     return x
 
 
@@ -391,6 +394,18 @@ def synth_inputs(seed: int = 1):
     maps = torch.randn(1, 3, 724, 1440, generator=g)
     const_h = torch.randn(1, 1, 1, 13, 721, 1440, generator=g)
     return inp, inp_s, (surface_mean, surface_std, upper_mean, upper_std), maps, const_h
+
+
+def grads(fn, tensors, gouts):
+    """torch.autograd of `fn(*leaves)` (one of the functions above, closed over the rest) -- the reference's
+    loss.backward() (models/pangu_sample.py:226) for a loss whose output gradients are `gouts`.
+    tensors: dict name -> tensor; -> dict name -> gradient."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in tensors.items()}
+    outs = fn(leaves)
+    if isinstance(outs, torch.Tensor):
+        outs, gouts = (outs,), (gouts,)
+    gs = torch.autograd.grad(outs, list(leaves.values()), grad_outputs=list(gouts), allow_unused=True)
+    return {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(leaves, gs)}
 
 
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:

@@ -6,6 +6,10 @@ sub-modules are real nn.Linear) behave as with the reference.  The math runs in 
 kernels for sm_100a through the C ABI in include/pangu_b200.h (see pangu_b200/functional.py); there is
 no eager-PyTorch or CPU fallback: tensors must live on a CUDA device.
 
+Training: when grad mode is on and a parameter (or the input) requires grad, the forward builds an autograd
+graph out of the Functions in pangu_b200/autograd.py, whose backward runs on the B200 backward kernels
+(bf16 mode; the reference's per-block checkpoint re-computation, models/layers.py:143-149, is kept).
+
 Numeric mode: `module.compute_dtype` in {"bf16", "fp32"} (default from $PANGU_B200_COMPUTE, "bf16");
 `set_compute_dtype(module, mode)` switches a whole tree.
 """
@@ -20,6 +24,7 @@ _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if _PKG not in sys.path:
     sys.path.insert(0, _PKG)
 
+from pangu_b200 import autograd as AG  # noqa: E402
 from pangu_b200 import functional as PF  # noqa: E402
 from pangu_b200.abi import PanguError  # noqa: E402
 
@@ -102,9 +107,10 @@ def _need_cuda(x, who):
 
 
 def _no_training_graph(mod, *tensors):
-    if mod.training and torch.is_grad_enabled() and any(t.requires_grad for t in tensors if t is not None):
-        raise PanguError(f"{type(mod).__name__}: the backward kernels are not part of this build; "
-                         "call under torch.no_grad() or in eval() mode")
+    """Mlp / EarthAttention3D called on their own: forward only (inside a block they are differentiated by BlockFn)."""
+    if AG.wants_graph(mod, *tensors):
+        raise PanguError(f"{type(mod).__name__}: called stand-alone this module is forward-only; differentiate it through "
+                         "EarthSpecificBlock / PanguModel, or call it under torch.no_grad()")
 
 
 class PatchEmbedding_pretrain(_B200Module):
@@ -124,8 +130,12 @@ class PatchEmbedding_pretrain(_B200Module):
         stats = tuple(s.to(inp.device) for s in statistics)
         maps_c = maps.to(inp.device).float().contiguous()
         ch = const_h.to(inp.device).float().contiguous()
-        outs = [PF.patch_embed_forward(self, inp[b], inp_s[b], stats, maps_c, ch, self._mode())[0]
-                for b in range(inp.shape[0])]
+        if AG.wants_graph(self):
+            AG.require_bf16(self)
+            outs = [AG.embed_apply(self, inp[b], inp_s[b], stats, maps_c, ch)[0] for b in range(inp.shape[0])]
+        else:
+            outs = [PF.patch_embed_forward(self, inp[b], inp_s[b], stats, maps_c, ch, self._mode())[0]
+                    for b in range(inp.shape[0])]
         return torch.stack(outs, 0)
 
 
@@ -222,17 +232,26 @@ class EarthSpecificBlock(_B200Module):
             raise PanguError(f"EarthSpecificBlock(dim={self.attention.dim}): grid ({Z},{H},{W}) does not give "
                              f"{self.type_of_windows} window types")
 
-    def forward_sample(self, x, Z, H, W, roll, xb=None):
-        if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0.0:
-            raise PanguError("EarthSpecificBlock: stochastic depth needs train mode, which needs the backward "
-                             "kernels (not part of this build); use eval()")
-        return PF.block_forward(self, x, Z, H, W, roll, self._mode(), xb)
+    def branch_scales(self):
+        """DropPath factors of the attention and the Mlp branch for ONE sample (two independent draws, as the two
+        self.drop_path(...) calls of models/layers.py:296-297 make): 1 in eval, else 0 or 1/keep."""
+        if isinstance(self.drop_path, DropPath):
+            return self.drop_path.branch_scale(), self.drop_path.branch_scale()
+        return 1.0, 1.0
+
+    def forward_sample(self, x, Z, H, W, roll, xb=None, graph=False):
+        if graph:
+            return AG.block_apply(self, x, xb, Z, H, W, roll)
+        s1, s2 = self.branch_scales()
+        return PF.block_forward(self, x, Z, H, W, roll, self._mode(), xb, s1, s2)
 
     def forward(self, x, Z, H, W, roll):
-        _no_training_graph(self, x)
         self._check_grid(Z, H, W)
         xs = _need_cuda(x, "EarthSpecificBlock")
-        return torch.stack([self.forward_sample(xs[b], Z, H, W, roll)[0] for b in range(xs.shape[0])], 0)
+        graph = AG.wants_graph(self, x)
+        if graph:
+            AG.require_bf16(self)
+        return torch.stack([self.forward_sample(xs[b], Z, H, W, roll, graph=graph)[0] for b in range(xs.shape[0])], 0)
 
 
 class EarthSpecificLayer(_B200Module):
@@ -247,19 +266,21 @@ class EarthSpecificLayer(_B200Module):
             block_list['EarthSpecificBlock{}'.format(i_layer)] = EarthSpecificBlock(
                 dim, drop_path_ratio_list[i_layer], heads, device=self.device)
         self.blocks = nn.Sequential(block_list)
-        self.use_checkpoint = use_checkpoint     # kept for API parity; nothing to recompute here
+        self.use_checkpoint = use_checkpoint     # API parity; BlockFn always re-computes the block in its backward
 
-    def forward_sample(self, x, Z, H, W, xb=None):
+    def forward_sample(self, x, Z, H, W, xb=None, graph=False):
         for i, blk in enumerate(self.blocks):
-            x, xb = blk.forward_sample(x, Z, H, W, i % 2 == 1, xb)
+            x, xb = blk.forward_sample(x, Z, H, W, i % 2 == 1, xb, graph)
         return x, xb
 
     def forward(self, x, Z, H, W):
-        _no_training_graph(self, x)
         xs = _need_cuda(x, "EarthSpecificLayer")
         for blk in self.blocks:
             blk._check_grid(Z, H, W)
-        return torch.stack([self.forward_sample(xs[b], Z, H, W)[0] for b in range(xs.shape[0])], 0)
+        graph = AG.wants_graph(self, x)
+        if graph:
+            AG.require_bf16(self)
+        return torch.stack([self.forward_sample(xs[b], Z, H, W, graph=graph)[0] for b in range(xs.shape[0])], 0)
 
 
 class DownSample(_B200Module):
@@ -270,13 +291,17 @@ class DownSample(_B200Module):
         self.linear = nn.Linear(in_features=4 * dim, out_features=2 * dim, bias=False)
         self.norm = nn.LayerNorm(4 * dim)
 
-    def forward_sample(self, x, Z, H, W):
+    def forward_sample(self, x, Z, H, W, graph=False):
+        if graph:
+            return AG.downsample_apply(self, x, Z, H, W)
         return PF.downsample_forward(self, x, Z, H, W, self._mode())
 
     def forward(self, x, Z, H, W):
-        _no_training_graph(self, x)
         xs = _need_cuda(x, "DownSample")
-        return torch.stack([self.forward_sample(xs[b], Z, H, W)[0] for b in range(xs.shape[0])], 0)
+        graph = AG.wants_graph(self, x)
+        if graph:
+            AG.require_bf16(self)
+        return torch.stack([self.forward_sample(xs[b], Z, H, W, graph)[0] for b in range(xs.shape[0])], 0)
 
 
 class UpSample(_B200Module):
@@ -288,15 +313,19 @@ class UpSample(_B200Module):
         self.linear2 = nn.Linear(output_dim, output_dim, bias=False)
         self.norm = nn.LayerNorm(output_dim)
 
-    def forward_sample(self, x, xb=None):
+    def forward_sample(self, x, xb=None, graph=False):
+        if graph:
+            return AG.upsample_apply(self, x, xb)
         return PF.upsample_forward(self, x, self._mode(), xb)
 
     def forward(self, x):
-        _no_training_graph(self, x)
         xs = _need_cuda(x, "UpSample")
         if xs.shape[1] != 8 * 91 * 180:
             raise PanguError("UpSample is hard-wired to 8x91x180 tokens, like the reference (models/layers.py:546)")
-        return torch.stack([self.forward_sample(xs[b])[0] for b in range(xs.shape[0])], 0)
+        graph = AG.wants_graph(self, x)
+        if graph:
+            AG.require_bf16(self)
+        return torch.stack([self.forward_sample(xs[b], graph=graph)[0] for b in range(xs.shape[0])], 0)
 
 
 class PatchRecovery_pretrain(_B200Module):
@@ -309,13 +338,21 @@ class PatchRecovery_pretrain(_B200Module):
         self.conv = nn.Conv1d(in_channels=dim, out_channels=160, kernel_size=1, stride=1)
         self.conv_surface = nn.Conv1d(in_channels=dim, out_channels=64, kernel_size=1, stride=1)
 
-    def forward_sample(self, x, Z, H, W, skip=None, denorm=None, xb=None, skip_b=None):
+    def forward_sample(self, x, Z, H, W, skip=None, denorm=None, xb=None, skip_b=None, graph=False):
+        if graph:
+            if denorm is not None:
+                raise PanguError("PatchRecovery: the fused de-normalisation is an inference feature")
+            if (Z, H, W) != (8, 181, 360):
+                raise PanguError("PatchRecovery_pretrain is hard-wired to the (8,181,360) grid, like the reference")
+            return AG.recover_apply(self, x, xb, Z, H, W, skip, skip_b)
         return PF.patch_recover_forward(self, x, Z, H, W, self._mode(), skip, denorm=denorm, xb=xb, skip_b=skip_b)
 
     def forward(self, x, Z, H, W):
-        _no_training_graph(self, x)
         xs = _need_cuda(x, "PatchRecovery")
-        outs = [self.forward_sample(xs[b], Z, H, W) for b in range(xs.shape[0])]
+        graph = AG.wants_graph(self, x)
+        if graph:
+            AG.require_bf16(self)
+        outs = [self.forward_sample(xs[b], Z, H, W, graph=graph) for b in range(xs.shape[0])]
         return torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)
 
 

@@ -12,7 +12,8 @@ if _PKG not in sys.path:
 
 from models.layers import *  # noqa: E402,F401,F403
 from models.layers import (DownSample, EarthSpecificLayer, PatchEmbedding_pretrain, PatchRecovery_pretrain,  # noqa: E402
-                           UpSample, _B200Module, _need_cuda, _no_training_graph, set_compute_dtype, trunc_normal_)
+                           UpSample, _B200Module, _need_cuda, set_compute_dtype, trunc_normal_)
+from pangu_b200 import autograd as AG  # noqa: E402
 from pangu_b200 import functional as PF  # noqa: E402
 
 
@@ -55,27 +56,34 @@ class PanguModel(_B200Module):
     def set_compute_dtype(self, mode):
         return set_compute_dtype(self, mode)
 
-    def forward_sample(self, inp, inp_s, stats, maps, const_h, denorm=None):
+    def forward_sample(self, inp, inp_s, stats, maps, const_h, denorm=None, graph=False):
         """One sample through models/pangu_model.py:61-104; the bf16 shadow of the residual stream is
-        handed from kernel to kernel so that no separate cast pass is needed."""
+        handed from kernel to kernel so that no separate cast pass is needed.  graph=True chains the autograd
+        Functions of pangu_b200/autograd.py instead (fine-tuning; the skip connection's two gradient streams are
+        summed by autograd)."""
         mode = self._mode()
-        x, xb = PF.patch_embed_forward(self._input_layer, inp, inp_s, stats, maps, const_h, mode)
-        x, xb = self.layers[0].forward_sample(x, 8, 181, 360, xb)
+        if graph:
+            x, xb = AG.embed_apply(self._input_layer, inp, inp_s, stats, maps, const_h)
+        else:
+            x, xb = PF.patch_embed_forward(self._input_layer, inp, inp_s, stats, maps, const_h, mode)
+        x, xb = self.layers[0].forward_sample(x, 8, 181, 360, xb, graph)
         skip, skip_b = x, xb
-        x, xb = self.downsample.forward_sample(x, 8, 181, 360)
-        x, xb = self.layers[1].forward_sample(x, 8, 91, 180, xb)
-        x, xb = self.layers[2].forward_sample(x, 8, 91, 180, xb)
-        x, xb = self.upsample.forward_sample(x, xb)
-        x, xb = self.layers[3].forward_sample(x, 8, 181, 360, xb)
-        return self._output_layer.forward_sample(x, 8, 181, 360, skip=skip, denorm=denorm, xb=xb, skip_b=skip_b)
+        x, xb = self.downsample.forward_sample(x, 8, 181, 360, graph)
+        x, xb = self.layers[1].forward_sample(x, 8, 91, 180, xb, graph)
+        x, xb = self.layers[2].forward_sample(x, 8, 91, 180, xb, graph)
+        x, xb = self.upsample.forward_sample(x, xb, graph)
+        x, xb = self.layers[3].forward_sample(x, 8, 181, 360, xb, graph)
+        return self._output_layer.forward_sample(x, 8, 181, 360, skip=skip, denorm=denorm, xb=xb, skip_b=skip_b, graph=graph)
 
     def forward(self, input, input_surface, statistics, maps, const_h):
-        _no_training_graph(self, input, input_surface)
         inp, inp_s = _need_cuda(input, "PanguModel"), _need_cuda(input_surface, "PanguModel")
         stats = tuple(s.to(inp.device) for s in statistics)
         maps_c = maps.to(inp.device).float().contiguous()
         ch = const_h.to(inp.device).float().contiguous()
-        outs = [self.forward_sample(inp[b], inp_s[b], stats, maps_c, ch) for b in range(inp.shape[0])]
+        graph = AG.wants_graph(self)
+        if graph:
+            AG.require_bf16(self)
+        outs = [self.forward_sample(inp[b], inp_s[b], stats, maps_c, ch, graph=graph) for b in range(inp.shape[0])]
         if len(outs) == 1:
             return outs[0]
         return torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)

@@ -64,6 +64,22 @@ _PROTOS = {
                                           c_int32, c_int32, c_int32, c_float, c_void_p]),
     "pangu_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "pangu_concat_cast_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
+    # fine-tune backward
+    "pangu_linear_bf16_add": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+                                      c_int32, c_void_p]),
+    "pangu_linear_wgrad_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int32, c_int32,
+                                        c_void_p]),
+    "pangu_colsum": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int32, c_void_p, c_void_p]),
+    "pangu_ln_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int64, c_int32, c_float, c_void_p]),
+    "pangu_upsample_shuffle_ln_backward": (c_int, [c_void_p] * 6 + [c_int32] * 5 + [c_float, c_void_p]),
+    "pangu_downsample_merge_ln_backward": (c_int, [c_void_p] * 6 + [c_int32] * 4 + [c_float, c_void_p]),
+    "pangu_gelu_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "pangu_gelu_backward_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
+    "pangu_window_attention_train": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(Geom), c_int,
+                                             c_void_p]),
+    "pangu_window_attention_backward": (c_int, [c_void_p] * 9 + [POINTER(Geom), c_int, c_void_p]),
+    "pangu_patch_recover_gather_backward": (c_int, [c_void_p] * 4 + [c_int32, c_int32, c_void_p]),
 }
 
 _lib = None

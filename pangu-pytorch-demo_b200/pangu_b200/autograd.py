@@ -1,0 +1,349 @@
+"""Fine-tune path: torch.autograd.Function wrappers whose backward runs on the B200 kernels.
+
+The reference trains `PanguModel` with plain autograd (`loss.backward()`, models/pangu_sample.py:226) under DDP
+(finetune/finetune_fully.py:220) and re-computes every block in the backward pass (checkpoint.checkpoint,
+models/layers.py:143-149).  This module keeps that shape: one Function per EarthSpecificBlock / PatchEmbedding /
+DownSample / UpSample / PatchRecovery; a Function saves only its inputs (fp32 stream + bf16 shadow), the backward
+re-computes the intermediates with the un-fused kernels and then runs
+
+  * dgrad GEMMs  -- the forward tcgen05 GEMM kernels on transposed bf16 weight copies, the residual-gradient add
+                    fused into their epilogue (`ops.linear_add`);
+  * wgrad GEMMs  -- `ops.linear_wgrad`: MN-major tcgen05 split over token ranges, no transposed copies;
+  * the window-attention backward kernel (`ops.window_attention_backward`), LayerNorm / GELU backward kernels.
+
+Parameter gradients are fp32 tensors shaped like the parameters, so DDP's bucketed NCCL all-reduce (or
+`pangu_b200.dist.allreduce_gradients`) sees exactly what it sees with the reference.  bf16 compute mode only.
+"""
+import torch
+
+from . import functional as PF
+from . import ops
+from .abi import PanguError
+
+F32 = torch.float32
+
+
+def _zeros(n, dev):
+    return torch.zeros((n,), dtype=F32, device=dev)
+
+
+def _wT(wc, key, p):
+    """bf16 copy of a weight TRANSPOSED to [in, out] -- the 'W' operand of a dgrad GEMM (dX = dY @ W)."""
+    def f(w):
+        if w.dim() == 3:
+            w = w[:, :, 0]
+        return w.t().contiguous().to(torch.bfloat16)
+    return wc.derived(key + ".T", (p,), f)
+
+
+def _like(p, g2d):
+    return g2d.reshape(p.shape)
+
+
+# ------------------------------------------------------------------------------------------ EarthSpecificBlock
+BLOCK_PARAMS = ("attention.linear1.weight", "attention.linear1.bias", "attention.earth_specific_bias",
+                "attention.linear2.weight", "attention.linear2.bias", "norm1.weight", "norm1.bias",
+                "linear.linear1.weight", "linear.linear1.bias", "linear.linear2.weight", "linear.linear2.bias",
+                "norm2.weight", "norm2.bias")
+
+
+def block_params(blk):
+    a, m = blk.attention, blk.linear
+    return (a.linear1.weight, a.linear1.bias, a.earth_specific_bias, a.linear2.weight, a.linear2.bias,
+            blk.norm1.weight, blk.norm1.bias, m.linear1.weight, m.linear1.bias, m.linear2.weight, m.linear2.bias,
+            blk.norm2.weight, blk.norm2.bias)
+
+
+def block_backward(blk, x0, x0b, Z, H, W, roll, s1, s2, g2):
+    """Backward of EarthSpecificBlock.forward (models/layers.py:218-299) for one sample.
+    x0 fp32 / x0b bf16 [N, C]: the block input; s1, s2: DropPath factors of the two branches (0 = branch dropped);
+    g2 fp32 [N, C]: gradient of the block output.  -> (dx0 fp32, 13 parameter gradients in BLOCK_PARAMS order)."""
+    att, mlp = blk.attention, blk.linear
+    wc = blk._wcache
+    dev = x0.device
+    N, C = x0.shape
+    heads = att.head_number
+    f = PF._f
+    g2 = g2.contiguous()
+    ps = block_params(blk)
+    grads = [None] * 13
+
+    # ---- re-compute the forward intermediates (un-fused kernels, so that they exist in HBM)
+    if s1 != 0.0:
+        w_qkv, b_qkv, eb = PF.attention_operands(att, wc)               # pre-scaled (scale*log2e folded into q)
+        qkv = ops.linear(x0b, w_qkv, b_qkv)
+        o, lse = ops.window_attention_train(qkv, b_qkv, eb, Z, H, W, heads, 1 if roll else 0)
+        y1 = ops.linear(o, wc.bf16("a2", att.linear2.weight), f(att.linear2.bias), out_dtype=F32)
+        gam1, bet1 = PF._affine(blk.norm1, s1)
+        x1, x1b = ops.ln_residual(y1, gam1, bet1, residual=x0, want_bf16=True, eps=blk.norm1.eps)
+    else:
+        x1, x1b = x0, x0b
+
+    # ---- x2 = x1 + s2 * LN2(Mlp(x1))
+    if s2 != 0.0:
+        h_pre = ops.linear(x1b, wc.bf16("m1", mlp.linear1.weight), f(mlp.linear1.bias))
+        h = ops.gelu_bf16(h_pre)
+        y2 = ops.linear(h, wc.bf16("m2", mlp.linear2.weight), f(mlp.linear2.bias), out_dtype=F32)
+        dg2, db2n, db2 = _zeros(C, dev), _zeros(C, dev), _zeros(C, dev)
+        dy2 = ops.ln_backward(g2, y2, f(blk.norm2.weight), scale=s2, dgamma=dg2, dbeta=db2n, dcolsum=db2, eps=blk.norm2.eps)
+        del y2
+        dw2 = ops.linear_wgrad(dy2, h)
+        del h
+        dh = ops.linear(dy2, _wT(wc, "m2", mlp.linear2.weight), None)   # [N, 4C] bf16
+        del dy2
+        db1 = _zeros(4 * C, dev)
+        ops.gelu_backward_bf16(dh, h_pre, db1)                          # dh <- dh * gelu'(h_pre)
+        del h_pre
+        dw1 = ops.linear_wgrad(dh, x1b)
+        g1 = ops.linear_add(dh, _wT(wc, "m1", mlp.linear1.weight), None, addend=g2)
+        del dh
+        grads[7], grads[8], grads[9], grads[10], grads[11], grads[12] = dw1, db1, dw2, db2, dg2, db2n
+    else:
+        g1 = g2
+        for i in range(7, 13):
+            grads[i] = torch.zeros_like(ps[i])
+
+    # ---- x1 = x0 + s1 * LN1(proj(attention(qkv(x0))))
+    if s1 != 0.0:
+        dg1, db1n, dba2 = _zeros(C, dev), _zeros(C, dev), _zeros(C, dev)
+        dy1 = ops.ln_backward(g1, y1, f(blk.norm1.weight), scale=s1, dgamma=dg1, dbeta=db1n, dcolsum=dba2, eps=blk.norm1.eps)
+        del y1
+        dwa2 = ops.linear_wgrad(dy1, o)
+        do = ops.linear(dy1, _wT(wc, "a2", att.linear2.weight), None)   # [N, C] bf16
+        del dy1
+        d_eb = torch.zeros(att.earth_specific_bias.shape[1:], dtype=F32, device=dev)
+        dba1 = _zeros(3 * C, dev)                                        # pad rows' share first, then the real rows
+        dqkv = ops.window_attention_backward(qkv, b_qkv, eb, o, do, lse, Z, H, W, heads, 1 if roll else 0, d_eb, dba1)
+        del qkv, o, do, lse
+        dwa1 = ops.linear_wgrad(dqkv, x0b)
+        ops.colsum(dqkv, out=dba1)
+        g0 = ops.linear_add(dqkv, _wT(wc, "a1", att.linear1.weight), None, addend=g1)
+        del dqkv
+        grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6] = \
+            dwa1, dba1, d_eb.unsqueeze(0), dwa2, dba2, dg1, db1n
+    else:
+        g0 = g1
+        for i in range(0, 7):
+            grads[i] = torch.zeros_like(ps[i])
+    return g0, [_like(p, g) for p, g in zip(ps, grads)]
+
+
+class BlockFn(torch.autograd.Function):
+    """(x fp32 [N,C], xb bf16 or None, 13 parameters) -> (x_out fp32, x_out bf16)."""
+
+    @staticmethod
+    def forward(ctx, x, xb, blk, Z, H, W, roll, s1, s2, *params):
+        x = x.contiguous()
+        if xb is None:
+            xb = ops.cast_bf16(x)
+        ctx.blk, ctx.geo, ctx.scales = blk, (Z, H, W, roll), (s1, s2)
+        ctx.save_for_backward(x, xb)
+        y, yb = PF.block_forward(blk, x, Z, H, W, roll, "bf16", xb, s1, s2)
+        if y is x:                                              # both branches dropped: outputs must not alias inputs
+            y, yb = x.clone(), xb.clone()
+        ctx.mark_non_differentiable(yb)
+        return y, yb
+
+    @staticmethod
+    def backward(ctx, g, _gb):
+        x, xb = ctx.saved_tensors
+        Z, H, W, roll = ctx.geo
+        s1, s2 = ctx.scales
+        with torch.no_grad():
+            dx, pg = block_backward(ctx.blk, x, xb, Z, H, W, roll, s1, s2, g)
+        need = ctx.needs_input_grad
+        return (dx if need[0] else None, None, None, None, None, None, None, None, None,
+                *[gp if need[9 + i] else None for i, gp in enumerate(pg)])
+
+
+# ------------------------------------------------------------------------------------------ PatchEmbedding
+class PatchEmbedFn(torch.autograd.Function):
+    """models/layers.py:53-120 for one sample; the input fields carry no gradient (they are data)."""
+
+    @staticmethod
+    def forward(ctx, inp, inp_s, pe, stats, maps, const_h, w, b, ws, bs):
+        ctx.pe, ctx.aux = pe, (stats, maps, const_h)
+        ctx.save_for_backward(inp, inp_s)
+        x, xb = PF.patch_embed_forward(pe, inp, inp_s, stats, maps, const_h, "bf16")
+        ctx.mark_non_differentiable(xb)
+        return x, xb
+
+    @staticmethod
+    def backward(ctx, g, _gb):
+        inp, inp_s = ctx.saved_tensors
+        stats, maps, const_h = ctx.aux
+        pe = ctx.pe
+        with torch.no_grad():
+            g = g.contiguous()
+            ps, pu = ops.patch_embed_gather(inp, inp_s, stats, maps, const_h, torch.bfloat16)
+            ns = ps.shape[0]
+            gb = ops.cast_bf16(g)
+            dws = ops.linear_wgrad(gb[:ns], ps)
+            dw = ops.linear_wgrad(gb[ns:], pu)
+            dbs, db = ops.colsum(g[:ns]), ops.colsum(g[ns:])
+        return (None, None, None, None, None, None, _like(pe.conv.weight, dw), db, _like(pe.conv_surface.weight, dws), dbs)
+
+
+# ------------------------------------------------------------------------------------------ DownSample
+class DownSampleFn(torch.autograd.Function):
+    """models/layers.py:497-524."""
+
+    @staticmethod
+    def forward(ctx, x, ds, Z, H, W, w, gamma, beta):
+        x = x.contiguous()
+        ctx.ds, ctx.geo = ds, (Z, H, W)
+        ctx.save_for_backward(x)
+        y, yb = PF.downsample_forward(ds, x, Z, H, W, "bf16")
+        ctx.mark_non_differentiable(yb)
+        return y, yb
+
+    @staticmethod
+    def backward(ctx, g, _gb):
+        (x,) = ctx.saved_tensors
+        ds = ctx.ds
+        Z, H, W = ctx.geo
+        with torch.no_grad():
+            f = PF._f
+            C4 = ds.norm.weight.shape[0]
+            m = ops.downsample_merge_ln(x, f(ds.norm.weight), f(ds.norm.bias), Z, H, W, torch.bfloat16, ds.norm.eps)
+            gb = ops.cast_bf16(g.contiguous())
+            dw = ops.linear_wgrad(gb, m)
+            del m
+            dm = ops.linear_add(gb, _wT(ds._wcache, "l", ds.linear.weight), None)
+            dgam, dbet = _zeros(C4, x.device), _zeros(C4, x.device)
+            dx = ops.downsample_merge_ln_backward(dm, x, f(ds.norm.weight), dgam, dbet, Z, H, W, ds.norm.eps)
+        return dx, None, None, None, None, dw, dgam, dbet
+
+
+# ------------------------------------------------------------------------------------------ UpSample
+class UpSampleFn(torch.autograd.Function):
+    """models/layers.py:540-567."""
+
+    @staticmethod
+    def forward(ctx, x, xb, us, geo, w1, w2, gamma, beta):
+        x = x.contiguous()
+        if xb is None:
+            xb = ops.cast_bf16(x)
+        ctx.us, ctx.geo = us, geo
+        ctx.save_for_backward(xb)
+        Z, H2, W2, H = geo
+        y, yb = PF.upsample_forward(us, x, "bf16", xb, Z, H2, W2, H)
+        ctx.mark_non_differentiable(yb)
+        return y, yb
+
+    @staticmethod
+    def backward(ctx, g, _gb):
+        (xb,) = ctx.saved_tensors
+        us = ctx.us
+        Z, H2, W2, H = ctx.geo
+        with torch.no_grad():
+            f, wc = PF._f, us._wcache
+            Co = us.norm.weight.shape[0]
+            y = ops.linear(xb, wc.bf16("l1", us.linear1.weight), None)
+            n = ops.upsample_shuffle_ln(y, f(us.norm.weight), f(us.norm.bias), Z, H2, W2, H, torch.bfloat16, us.norm.eps)
+            gb = ops.cast_bf16(g.contiguous())
+            dw2 = ops.linear_wgrad(gb, n)
+            del n
+            dn = ops.linear_add(gb, _wT(wc, "l2", us.linear2.weight), None)
+            dgam, dbet = _zeros(Co, xb.device), _zeros(Co, xb.device)
+            dy = ops.upsample_shuffle_ln_backward(dn, y, f(us.norm.weight), dgam, dbet, Z, H2, W2, H, us.norm.eps)
+            del dn, y
+            dw1 = ops.linear_wgrad(dy, xb)
+            dx = ops.linear_add(dy, _wT(wc, "l1", us.linear1.weight), None)
+        return dx, None, None, None, dw1, dw2, dgam, dbet
+
+
+# ------------------------------------------------------------------------------------------ PatchRecovery
+class PatchRecoverFn(torch.autograd.Function):
+    """models/layers.py:582-621 on the channel concat cat(skip, x) (models/pangu_model.py:98) for one sample.
+    `skip` may be None: then x already holds the concatenated channels."""
+
+    @staticmethod
+    def forward(ctx, skip, skip_b, x, xb, pr, geo, w, b, ws, bs):
+        Z, H, W = geo
+        x = x.contiguous()
+        if xb is None:
+            xb = ops.cast_bf16(x)
+        if skip is not None and skip_b is None:
+            skip_b = ops.cast_bf16(skip.contiguous())
+        ctx.pr, ctx.geo, ctx.has_skip = pr, geo, skip is not None
+        ctx.save_for_backward(skip_b, xb)
+        if skip is not None:
+            return PF.patch_recover_forward(pr, x, Z, H, W, "bf16", skip=skip, xb=xb, skip_b=skip_b)
+        return PF.patch_recover_forward(pr, x, Z, H, W, "bf16")
+
+    @staticmethod
+    def backward(ctx, g_out, g_out_s):
+        skip_b, xb = ctx.saved_tensors
+        pr = ctx.pr
+        Z, H, W = ctx.geo
+        with torch.no_grad():
+            dev = xb.device
+            ns = H * W
+            if g_out is None:
+                g_out = torch.zeros((1, 5, 13, 721, 1440), dtype=F32, device=dev)
+            if g_out_s is None:
+                g_out_s = torch.zeros((1, 4, 721, 1440), dtype=F32, device=dev)
+            dyu, dys = ops.patch_recover_gather_backward(g_out.contiguous().float(), g_out_s.contiguous().float(), 721)
+            wc = pr._wcache
+            wT, wsT = _wT(wc, "c", pr.conv.weight), _wT(wc, "cs", pr.conv_surface.weight)       # [Cin, 160] / [Cin, 64]
+            Cin = wT.shape[0]
+            dw = torch.zeros((160, Cin), dtype=F32, device=dev)
+            dws = torch.zeros((64, Cin), dtype=F32, device=dev)
+            db, dbs = ops.colsum(dyu), ops.colsum(dys)
+            if ctx.has_skip:
+                Cs = skip_b.shape[1]
+                parts = ((skip_b, 0, Cs), (xb, Cs, Cin))
+            else:
+                parts = ((xb, 0, Cin),)
+            dins = []
+            for src, c0, c1 in parts:
+                ops.linear_wgrad(dyu, src[ns:], dw[:, c0:c1])
+                ops.linear_wgrad(dys, src[:ns], dws[:, c0:c1])
+                d = torch.empty((src.shape[0], c1 - c0), dtype=F32, device=dev)
+                ops.linear_add(dyu, wT[c0:c1].contiguous(), None, out=d[ns:])
+                ops.linear_add(dys, wsT[c0:c1].contiguous(), None, out=d[:ns])
+                dins.append(d)
+        dskip, dx = (dins[0], dins[1]) if ctx.has_skip else (None, dins[0])
+        return (dskip, None, dx, None, None, None, _like(pr.conv.weight, dw), db, _like(pr.conv_surface.weight, dws), dbs)
+
+
+# ------------------------------------------------------------------------------------------ module-level helpers
+def wants_graph(mod, *tensors):
+    """True when a forward call must build an autograd graph: grad mode is on and either an input requires grad or
+    the module is in train() mode with trainable parameters.  (An eval() forward with grad mode left on -- the
+    reference's test loop, models/pangu_sample.py:443 -- stays a plain forward: nothing is saved for a backward.)"""
+    if not torch.is_grad_enabled():
+        return False
+    if any(t is not None and t.requires_grad for t in tensors):
+        return True
+    return mod.training and any(p.requires_grad for p in mod.parameters())
+
+
+def require_bf16(mod):
+    if mod._mode() != "bf16":
+        raise PanguError(f"{type(mod).__name__}: the backward kernels exist for compute_dtype='bf16' only "
+                         "(fp32 is the inference parity path)")
+
+
+def block_apply(blk, x, xb, Z, H, W, roll):
+    s1, s2 = blk.branch_scales()
+    return BlockFn.apply(x, xb, blk, Z, H, W, roll, s1, s2, *block_params(blk))
+
+
+def embed_apply(pe, inp, inp_s, stats, maps, const_h):
+    return PatchEmbedFn.apply(inp, inp_s, pe, stats, maps, const_h, pe.conv.weight, pe.conv.bias,
+                              pe.conv_surface.weight, pe.conv_surface.bias)
+
+
+def downsample_apply(ds, x, Z, H, W):
+    return DownSampleFn.apply(x, ds, Z, H, W, ds.linear.weight, ds.norm.weight, ds.norm.bias)
+
+
+def upsample_apply(us, x, xb, Z=8, H2=91, W2=180, H=181):
+    return UpSampleFn.apply(x, xb, us, (Z, H2, W2, H), us.linear1.weight, us.linear2.weight, us.norm.weight, us.norm.bias)
+
+
+def recover_apply(pr, x, xb, Z, H, W, skip=None, skip_b=None):
+    return PatchRecoverFn.apply(skip, skip_b, x, xb, pr, (Z, H, W), pr.conv.weight, pr.conv.bias,
+                                pr.conv_surface.weight, pr.conv_surface.bias)

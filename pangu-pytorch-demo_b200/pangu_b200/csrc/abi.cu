@@ -36,7 +36,8 @@ int launch_window_attention_f32(const float* qkv, const float* qkv_bias, const f
 // tc_gemm.cu
 int launch_tc_linear(const void* A, long long lda, const void* W, const float* bias, void* out,
                      long long ldo, long long M, int K, int N, int act, int out_dtype, cudaStream_t st,
-                     void* shadow = nullptr, const void* A2 = nullptr, long long lda2 = 0, int K1 = 0);
+                     void* shadow = nullptr, const void* A2 = nullptr, long long lda2 = 0, int K1 = 0,
+                     const float* addend = nullptr);
 int launch_tc_linear_ln(const void* A, long long lda, const void* W, const float* bias,
                         const float* gamma, const float* beta, const float* residual, float* x_out,
                         void* x_out_bf16, long long M, int K, int C, float eps, cudaStream_t st);
@@ -48,7 +49,12 @@ int debug_read_mlp_trace(long long* out, int n);
 // tc_attention.cu
 int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias, const void* earth_bias,
                                  int bias_dtype, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
-                                 int roll, int prescaled, cudaStream_t st);
+                                 int roll, int prescaled, cudaStream_t st, float* lse = nullptr);
+
+// attention_bwd.cu
+int launch_window_attention_bwd(const void* qkv, const float* qkv_bias, const void* earth_bias, const void* o,
+                                const void* dout, const float* lse, void* dqkv, float* dbias, float* dpad,
+                                const WinGeom& g, int roll, cudaStream_t st);
 
 }  // namespace pangu
 
@@ -155,4 +161,34 @@ extern "C" int pangu_window_attention_band(const void* qkv, const void* halo_qkv
     }
   }
   return launch_window_attention_bf16(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, bias_dtype, out, halo_out, g, bd, roll, prescaled != 0, as_stream(stream));
+}
+
+extern "C" int pangu_linear_bf16_add(const void* A, int64_t lda, const void* W, const float* bias, const float* addend,
+                                     float* out, int64_t ldo, int64_t M, int32_t K, int32_t N, void* stream) {
+  if (!A || !W || !out || M < 0 || K <= 0 || N <= 0) { set_error("linear_add: bad argument"); return PANGU_ERR_BAD_ARG; }
+  return launch_tc_linear(A, lda, W, bias, out, ldo, M, K, N, PANGU_ACT_NONE, PANGU_F32, as_stream(stream), nullptr, nullptr, 0, 0, addend);
+}
+
+extern "C" int pangu_window_attention_train(const void* qkv, const float* qkv_bias, const void* earth_bias, void* out,
+                                            float* lse, const pangu_geom* gg, int roll, void* stream) {
+  WinGeom g;
+  if (!make_geom(gg, g) || !qkv || !qkv_bias || !earth_bias || !out || !lse) { set_error("window_attention_train: bad argument"); return PANGU_ERR_BAD_ARG; }
+  if (g.C != g.heads * kHeadDim) { set_error("window_attention_train: C=%d must equal heads*32", g.C); return PANGU_ERR_BAD_ARG; }
+  if (roll < 0 || roll > 2) { set_error("window_attention_train: roll must be 0, 1 or 2"); return PANGU_ERR_BAD_ARG; }
+  const BandGeom full{0, g.H, 0, g.nH, 0, 0, 0};
+  return launch_window_attention_bf16(qkv, nullptr, nullptr, qkv_bias, earth_bias, PANGU_BF16, out, nullptr, g, full, roll, 1, as_stream(stream), lse);
+}
+
+extern "C" int pangu_window_attention_backward(const void* qkv, const float* qkv_bias, const void* earth_bias,
+                                               const void* out, const void* d_out, const float* lse, void* d_qkv,
+                                               float* d_earth_bias, float* d_qkv_bias_pad, const pangu_geom* gg,
+                                               int roll, void* stream) {
+  WinGeom g;
+  if (!make_geom(gg, g) || !qkv || !qkv_bias || !earth_bias || !out || !d_out || !lse || !d_qkv || !d_earth_bias || !d_qkv_bias_pad) {
+    set_error("window_attention_backward: bad argument");
+    return PANGU_ERR_BAD_ARG;
+  }
+  if (g.C != g.heads * kHeadDim) { set_error("window_attention_backward: C=%d must equal heads*32", g.C); return PANGU_ERR_BAD_ARG; }
+  if (roll < 0 || roll > 2) { set_error("window_attention_backward: roll must be 0, 1 or 2"); return PANGU_ERR_BAD_ARG; }
+  return launch_window_attention_bwd(qkv, qkv_bias, earth_bias, out, d_out, lse, d_qkv, d_earth_bias, d_qkv_bias_pad, g, roll, as_stream(stream));
 }

@@ -9,7 +9,7 @@
 //
 // Round-1 note: the two small GEMMs (7 % of the model's FLOPs) use warp-level mma.sync fragments so that
 // softmax stays register-resident; the tcgen05/TMEM formulation is the planned upgrade.
-#include "common.cuh"
+#include "attn_common.cuh"
 
 namespace pangu {
 namespace tc { int num_sms(); }
@@ -19,44 +19,9 @@ namespace attn {
 constexpr int kWarps = 9;                         // 9 x 16 query rows = 144
 constexpr int kThreads = kWarps * 32;
 constexpr int kKvBlock = 48;                      // keys per online-softmax block (3 blocks)
-constexpr int kBiasPitch = 152;                   // bf16 elements per bias row in smem (304 B: conflict-free)
-constexpr int kTileBytes = kWinTokens * 64;       // one [144][32] bf16 operand tile, 64-byte rows, XOR-swizzled
 constexpr int kBufBytes = 3 * kTileBytes;         // q, k, v
 constexpr int kSmemBytes = kWinTokens * kBiasPitch * 2 + 2 * kBufBytes + kWinTokens * 4 /*rowbase*/ +
                            kWinTokens * 4 /*dw*/ + kWinTokens /*gid*/ + 16;
-constexpr float kLog2e = 1.4426950408889634f;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-// D(16x8,f32) += A(16x16,bf16,row) * B(16x8,bf16,col)
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&p);
-}
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// byte offset of 16-byte chunk c (0..3) of row r in a 64-byte-row tile; XOR swizzle keeps both the
-// cp.async fills and the ldmatrix reads (8 consecutive rows, same chunk) bank-conflict free.
-__device__ __forceinline__ int tile_off(int r, int c) { return r * 64 + ((c ^ ((r >> 1) & 3)) << 4); }
 
 // PRE: the caller folded scale*log2(e) into the q projection (weights and bias) and log2(e) into the bias table,
 // so q k^T + bias is already the softmax exponent in log2 units: the bias tile initialises the MMA accumulator
@@ -67,7 +32,7 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
                              const __nv_bfloat16* __restrict__ halo_lo_qkv,
                              const float* __restrict__ qkv_bias, const TB* __restrict__ earth_bias,
                              __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ halo_out, WinGeom g,
-                             BandGeom bd, int roll, int lon_chunk) {
+                             BandGeom bd, int roll, int lon_chunk, float* __restrict__ lse) {
   extern __shared__ __align__(128) uint8_t smem[];
   __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(smem);                       // [144][152]
   uint8_t* s_buf = smem + kWinTokens * kBiasPitch * 2;                                  // 2 x {q,k,v}
@@ -271,6 +236,11 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
       }
     }
     const float inv_lo = 1.0f / l_acc[0], inv_hi = 1.0f / l_acc[2];   // every column of the ones tile holds the row sum
+    if (lse != nullptr && tq == 0) {                        // log2-sum-exp of every score row, kept for the backward kernel
+      float* L = lse + (((long long)l * g.T + t) * g.heads + head) * kWinTokens + row0 + gq;
+      L[0] = m_lo + log2f(l_acc[0]);
+      L[8] = m_hi + log2f(l_acc[2]);
+    }
 
     // stage O (bf16) into this warp's own, now dead, Q rows; then 64-byte coalesced row stores
     __syncwarp();
@@ -304,20 +274,20 @@ window_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
 template <typename TB, bool PRE>
 static int launch_attn_t(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias,
                          const void* earth_bias, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
-                         int roll, int lon_chunk, dim3 grid, cudaStream_t st) {
+                         int roll, int lon_chunk, dim3 grid, cudaStream_t st, float* lse) {
   using namespace attn;
   auto kern = window_attention_bf16_kernel<TB, PRE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) { set_error("attention_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
   kern<<<grid, kThreads, kSmemBytes, st>>>((const __nv_bfloat16*)qkv, (const __nv_bfloat16*)halo_qkv,
                                            (const __nv_bfloat16*)halo_lo_qkv, qkv_bias, (const TB*)earth_bias,
-                                           (__nv_bfloat16*)out, (__nv_bfloat16*)halo_out, g, bd, roll, lon_chunk);
+                                           (__nv_bfloat16*)out, (__nv_bfloat16*)halo_out, g, bd, roll, lon_chunk, lse);
   return check_launch("window_attention_bf16");
 }
 
 int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias, const void* earth_bias,
                                  int bias_dtype, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
-                                 int roll, int prescaled, cudaStream_t st) {
+                                 int roll, int prescaled, cudaStream_t st, float* lse) {
   using namespace attn;
   if (bd.nhw <= 0) return PANGU_OK;
   // longitude windows per CTA (they share the staged bias tile): as many as possible (<= 5) while the grid
@@ -332,11 +302,11 @@ int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const vo
   }
   dim3 grid((unsigned)g.heads, (unsigned)((g.nLon + lon_chunk - 1) / lon_chunk), (unsigned)(g.nZ * bd.nhw));
   if (bias_dtype == PANGU_BF16)
-    return prescaled ? launch_attn_t<__nv_bfloat16, true>(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, lon_chunk, grid, st)
-                     : launch_attn_t<__nv_bfloat16, false>(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, lon_chunk, grid, st);
+    return prescaled ? launch_attn_t<__nv_bfloat16, true>(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, lon_chunk, grid, st, lse)
+                     : launch_attn_t<__nv_bfloat16, false>(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, lon_chunk, grid, st, lse);
   if (bias_dtype == PANGU_F32)
-    return prescaled ? launch_attn_t<float, true>(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, lon_chunk, grid, st)
-                     : launch_attn_t<float, false>(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, lon_chunk, grid, st);
+    return prescaled ? launch_attn_t<float, true>(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, lon_chunk, grid, st, lse)
+                     : launch_attn_t<float, false>(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, lon_chunk, grid, st, lse);
   set_error("attention_bf16: unknown bias dtype %d", bias_dtype);
   return PANGU_ERR_BAD_ARG;
 }

@@ -32,6 +32,7 @@ struct GemmArgs {
   int act;
   __nv_bfloat16* shadow;        // optional bf16 copy of an fp32 output (operand of the next GEMM), row pitch ldo
   int k_blocks_a1;              // k-blocks taken from the first A tensor; the rest come from the second (channel concat)
+  const float* addend;          // optional fp32 tensor added to an fp32 output (same row pitch ldo): out = A.W^T + bias + addend
   // LayerNorm + residual epilogue
   const float* gamma;
   const float* beta;
@@ -248,9 +249,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = (lane >> 3) + 4 * i, cc = lane & 7;
-              const float4 val = *reinterpret_cast<const float4*>(stg + stg_f32(rr, cc));
+              float4 val = *reinterpret_cast<const float4*>(stg + stg_f32(rr, cc));
               const long long m = m_base + rr;
               if (m < a.M) {
+                if (a.addend != nullptr) {
+                  const float4 ad = __ldg(reinterpret_cast<const float4*>(a.addend + m * a.ldo + n + cc * 4));
+                  val.x += ad.x; val.y += ad.y; val.z += ad.z; val.w += ad.w;
+                }
                 *reinterpret_cast<float4*>(out + m * a.ldo + n + cc * 4) = val;
                 if (a.shadow != nullptr)
                   *reinterpret_cast<uint2*>(a.shadow + m * a.ldo + n + cc * 4) = make_uint2(pack_bf16(val.x, val.y), pack_bf16(val.z, val.w));
@@ -394,7 +399,7 @@ int launch_tc_linear_pair(const void* A, long long lda, const void* W, const flo
 // from the two tensors directly.  shadow != nullptr (fp32 output only): also write a bf16 copy of the output.
 int launch_tc_linear(const void* A, long long lda, const void* W, const float* bias, void* out,
                      long long ldo, long long M, int K, int N, int act, int out_dtype, cudaStream_t st,
-                     void* shadow, const void* A2, long long lda2, int K1) {
+                     void* shadow, const void* A2, long long lda2, int K1, const float* addend) {
   if (M == 0) return PANGU_OK;
   if (shadow && out_dtype != PANGU_F32) { set_error("linear(bf16): a bf16 shadow needs an fp32 output"); return PANGU_ERR_BAD_ARG; }
   if (A2 && (K1 <= 0 || K1 >= K || K1 % tc::BK || (K - K1) % tc::BK || lda2 % 8)) { set_error("linear(bf16): concat split K1=%d of K=%d must be a multiple of 64", K1, K); return PANGU_ERR_BAD_ARG; }
@@ -402,7 +407,7 @@ int launch_tc_linear(const void* A, long long lda, const void* W, const float* b
   if (out_dtype != PANGU_BF16 && out_dtype != PANGU_F32) { set_error("linear(bf16): bad out_dtype"); return PANGU_ERR_BAD_ARG; }
   {   // skinny-K shapes: A-resident CTA-pair kernel (tc_gemm2.cu); $PANGU_B200_GEMM2=0 keeps the tiled kernel
     static const bool use_pair = []() { const char* e = getenv("PANGU_B200_GEMM2"); return e == nullptr || atoi(e) != 0; }();
-    if (use_pair && !A2) {
+    if (use_pair && !A2 && !addend) {
       const int rc = launch_tc_linear_pair(A, lda, W, bias, out, ldo, M, K, N, act, out_dtype, shadow, st);
       if (rc != PANGU_ERR_UNSUPPORTED) return rc;
     }
@@ -410,6 +415,8 @@ int launch_tc_linear(const void* A, long long lda, const void* W, const float* b
   tc::GemmArgs a{};
   a.M = M; a.K = K; a.N = N; a.bias = bias; a.out = out; a.ldo = ldo; a.out_dtype = out_dtype; a.act = act;
   a.shadow = reinterpret_cast<__nv_bfloat16*>(shadow);
+  a.addend = addend;
+  if (addend && out_dtype != PANGU_F32) { set_error("linear(bf16): an addend needs an fp32 output"); return PANGU_ERR_BAD_ARG; }
   if (N % 256 == 0) return tc::launch_gemm_t<256, false>(A, lda, W, a, st, A2, lda2, K1);
   if (N % 192 == 0) return tc::launch_gemm_t<192, false>(A, lda, W, a, st, A2, lda2, K1);
   if (N % 160 == 0) return tc::launch_gemm_t<160, false>(A, lda, W, a, st, A2, lda2, K1);

@@ -99,12 +99,21 @@ def _f(p):
 
 
 # ------------------------------------------------------------------------------------------
-def block_forward(blk, x, Z, H, W, roll, mode, xb=None):
-    """EarthSpecificBlock.forward (models/layers.py:218-299), eval semantics.
+def _affine(norm, s):
+    """LayerNorm affine parameters with a DropPath factor folded in: s * (LN(y) g + b) = LN(y) (s g) + (s b)."""
+    g, b = _f(norm.weight), _f(norm.bias)
+    return (g, b) if s == 1.0 else (g * s, b * s)
+
+
+def block_forward(blk, x, Z, H, W, roll, mode, xb=None, s1=1.0, s2=1.0):
+    """EarthSpecificBlock.forward (models/layers.py:218-299).  s1 / s2 are the DropPath factors of the attention and
+    Mlp branches for this sample (1 in eval; in training 0 = branch dropped, else 1/keep -- timm DropPath with batch 1).
     x fp32 [N, C]; returns (x_out fp32, x_out_bf16 or None)."""
     att, mlp = blk.attention, blk.linear
     heads = att.head_number
     rmode = ROLL_SHIFT if roll else ROLL_NONE
+    if (s1 != 1.0 or s2 != 1.0) and mode != "bf16":
+        raise PanguError("stochastic depth (training) runs in compute_dtype='bf16' only")
     if mode == "fp32":
         qkv = ops.linear(x, _w2d(att.linear1.weight), _f(att.linear1.bias))
         o = ops.window_attention(qkv, _f(att.linear1.bias), _f(att.earth_specific_bias), Z, H, W, heads, rmode)
@@ -119,22 +128,29 @@ def block_forward(blk, x, Z, H, W, roll, mode, xb=None):
     wc = blk._wcache
     if xb is None:
         xb = ops.cast_bf16(x)
-    w_qkv, b_qkv, eb = attention_operands(att, wc)
-    qkv = ops.linear(xb, w_qkv, b_qkv)
-    o, _ = ops.window_attention_band(qkv, None, b_qkv, eb, Z, H, W, heads, ops.full_band(H), 1 if roll else 0,
-                                     prescaled=True)
-    del qkv
-    x1, x1b = ops.linear_ln_residual_bf16(o, wc.bf16("a2", att.linear2.weight), _f(att.linear2.bias),
-                                          _f(blk.norm1.weight), _f(blk.norm1.bias), x, eps=blk.norm1.eps)
-    del o
+    if s1 != 0.0:
+        w_qkv, b_qkv, eb = attention_operands(att, wc)
+        qkv = ops.linear(xb, w_qkv, b_qkv)
+        o, _ = ops.window_attention_band(qkv, None, b_qkv, eb, Z, H, W, heads, ops.full_band(H), 1 if roll else 0,
+                                         prescaled=True)
+        del qkv
+        g1, b1 = _affine(blk.norm1, s1)
+        x1, x1b = ops.linear_ln_residual_bf16(o, wc.bf16("a2", att.linear2.weight), _f(att.linear2.bias), g1, b1, x,
+                                              eps=blk.norm1.eps)
+        del o
+    else:
+        x1, x1b = x, xb
+    if s2 == 0.0:
+        return x1, x1b
+    g2, b2 = _affine(blk.norm2, s2)
     if FUSED_MLP:
         x2, x2b = ops.mlp_ln_residual_bf16(x1b, wc.bf16("m1", mlp.linear1.weight), _f(mlp.linear1.bias),
-                                           wc.f16("m2h", mlp.linear2.weight), _f(mlp.linear2.bias),
-                                           _f(blk.norm2.weight), _f(blk.norm2.bias), x1, eps=blk.norm2.eps)
+                                           wc.f16("m2h", mlp.linear2.weight), _f(mlp.linear2.bias), g2, b2, x1,
+                                           eps=blk.norm2.eps)
         return x2, x2b
     h = ops.linear(x1b, wc.bf16("m1", mlp.linear1.weight), _f(mlp.linear1.bias), act=ACT_GELU)
-    x2, x2b = ops.linear_ln_residual_bf16(h, wc.bf16("m2", mlp.linear2.weight), _f(mlp.linear2.bias),
-                                          _f(blk.norm2.weight), _f(blk.norm2.bias), x1, eps=blk.norm2.eps)
+    x2, x2b = ops.linear_ln_residual_bf16(h, wc.bf16("m2", mlp.linear2.weight), _f(mlp.linear2.bias), g2, b2, x1,
+                                          eps=blk.norm2.eps)
     return x2, x2b
 
 

@@ -347,3 +347,158 @@ def concat_cast_bf16(a, b):
     _call("concat_cast_bf16", "pangu_concat_cast_bf16", (_ptr(a), _ptr(b), _ptr(out), n, C1, C2, _stream(),),
           nbytes=float(n * (C1 + C2) * 6))
     return out
+
+
+# ------------------------------------------------------------------ fine-tune backward (bf16 operands, fp32 accumulation)
+def linear_add(a, w, bias=None, addend=None, out=None):
+    """out (fp32) = a @ w.T + bias + addend -- dgrad GEMM fused with the residual-gradient add."""
+    _chk(a, torch.bfloat16, "a")
+    _chk(w, torch.bfloat16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise abi.PanguError("linear_add: a and w disagree on K")
+    if addend is not None:
+        _chk(addend, torch.float32, "addend")
+        if addend.shape != (M, N):
+            raise abi.PanguError("linear_add: addend must be [M, N]")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    _call("gemm_bf16_dgrad[K=%d,N=%d]" % (K, N), "pangu_linear_bf16_add",
+          (_ptr(a), K, _ptr(w), _ptr(bias), _ptr(addend), _ptr(out), N, M, K, N, _stream(),), flops=2.0 * M * K * N,
+          nbytes=float(M * K * 2 + N * K * 2 + M * N * (4 + 4 * (addend is not None))))
+    return out
+
+
+def linear_wgrad(dy, x, dw=None):
+    """dw [n_out, k_in] (fp32) += dy[M, n_out].T @ x[M, k_in]; dy / x bf16 row-major (row slices allowed)."""
+    for t, n in ((dy, "dy"), (x, "x")):
+        if not t.is_cuda or t.dtype != torch.bfloat16 or t.stride(-1) != 1:
+            raise abi.PanguError(f"linear_wgrad: {n} must be a CUDA bf16 tensor with unit inner stride")
+    M, n_out = dy.shape
+    k_in = x.shape[1]
+    if x.shape[0] != M:
+        raise abi.PanguError("linear_wgrad: dy and x disagree on the token count")
+    if dw is None:
+        dw = torch.zeros((n_out, k_in), dtype=torch.float32, device=dy.device)
+    if dw.dtype != torch.float32 or dw.stride(-1) != 1 or dw.shape != (n_out, k_in):
+        raise abi.PanguError("linear_wgrad: dw must be fp32 [n_out, k_in] with unit inner stride")
+    _call("wgrad_bf16[N=%d,K=%d]" % (n_out, k_in), "pangu_linear_wgrad_bf16",
+          (_ptr(dy), dy.stride(0), _ptr(x), x.stride(0), _ptr(dw), dw.stride(0), M, n_out, k_in, _stream(),),
+          flops=2.0 * M * n_out * k_in, nbytes=float(M * (n_out + k_in) * 2))
+    return dw
+
+
+def colsum(x, out=None):
+    """out [C] (fp32) += x.sum(0); x bf16 or fp32 [M, C]."""
+    if not x.is_cuda or x.stride(-1) != 1:
+        raise abi.PanguError("colsum: x must be a CUDA tensor with unit inner stride")
+    M, C = x.shape
+    if out is None:
+        out = torch.zeros((C,), dtype=torch.float32, device=x.device)
+    _call("colsum", "pangu_colsum", (_ptr(x), _DT[x.dtype], x.stride(0), M, C, _ptr(out), _stream(),),
+          nbytes=float(M * C * x.element_size()))
+    return out
+
+
+def ln_backward(dout, y, gamma, scale=1.0, dout2=None, dgamma=None, dbeta=None, dcolsum=None, eps=1e-5):
+    """Backward of scale * (LN(y) * gamma + beta) -> dy bf16; dgamma / dbeta / dcolsum (fp32 [C]) are accumulated."""
+    _chk(dout, torch.float32, "dout")
+    _chk(y, name="y")
+    if dout2 is not None:
+        _chk(dout2, torch.float32, "dout2")
+    M, C = y.shape
+    dy = torch.empty((M, C), dtype=torch.bfloat16, device=y.device)
+    _call("ln_backward[C=%d]" % C, "pangu_ln_backward",
+          (_ptr(dout), _ptr(dout2), _ptr(y), _DT[y.dtype], _ptr(gamma), float(scale), _ptr(dy), _ptr(dgamma), _ptr(dbeta),
+           _ptr(dcolsum), M, C, eps, _stream(),),
+          nbytes=float(M * C * (4 + 4 * (dout2 is not None) + y.element_size() + 2)))
+    return dy
+
+
+def upsample_shuffle_ln_backward(dout, y, gamma, dgamma, dbeta, Z, H2, W2, H, eps=1e-5):
+    _chk(dout, torch.float32, "dout")
+    _chk(y, torch.bfloat16, "y")
+    Co = y.shape[-1] // 4
+    dy = torch.zeros_like(y)                              # the cropped row gets no gradient
+    _call("upsample_shuffle_ln_backward", "pangu_upsample_shuffle_ln_backward",
+          (_ptr(dout), _ptr(y), _ptr(gamma), _ptr(dy), _ptr(dgamma), _ptr(dbeta), Z, H2, W2, H, Co, eps, _stream(),),
+          nbytes=float(dout.numel() * 4 + y.numel() * 4))
+    return dy
+
+
+def downsample_merge_ln_backward(dout, x, gamma, dgamma, dbeta, Z, H, W, eps=1e-5):
+    _chk(dout, torch.float32, "dout")
+    _chk(x, torch.float32, "x")
+    C = x.shape[-1]
+    dx = torch.empty_like(x)
+    _call("downsample_merge_ln_backward", "pangu_downsample_merge_ln_backward",
+          (_ptr(dout), _ptr(x), _ptr(gamma), _ptr(dx), _ptr(dgamma), _ptr(dbeta), Z, H, W, C, eps, _stream(),),
+          nbytes=float(dout.numel() * 4 + x.numel() * 8))
+    return dx
+
+
+def gelu_bf16(h_pre):
+    _chk(h_pre, torch.bfloat16, "h_pre")
+    h = torch.empty_like(h_pre)
+    _call("gelu_bf16", "pangu_gelu_bf16", (_ptr(h_pre), _ptr(h), h_pre.numel(), _stream(),), nbytes=float(h_pre.numel() * 4))
+    return h
+
+
+def gelu_backward_bf16(dh, h_pre, dcolsum=None):
+    """dh <- dh * GELU'(h_pre) in place; dcolsum [F] += column sums of the result."""
+    _chk(dh, torch.bfloat16, "dh")
+    _chk(h_pre, torch.bfloat16, "h_pre")
+    M, F = dh.shape
+    _call("gelu_backward_bf16", "pangu_gelu_backward_bf16", (_ptr(dh), _ptr(h_pre), _ptr(dh), _ptr(dcolsum), M, F, _stream(),),
+          nbytes=float(dh.numel() * 6))
+    return dh
+
+
+def window_attention_train(qkv, qkv_bias, earth_bias, Z, H, W, heads, roll):
+    """Pre-scaled bf16 window attention that also returns the log2-sum-exp rows for the backward kernel."""
+    _chk(qkv, torch.bfloat16, "qkv")
+    _chk(qkv_bias, torch.float32, "qkv_bias")
+    _chk(earth_bias, torch.bfloat16, "earth_bias")
+    N, C3 = qkv.shape
+    C = C3 // 3
+    nLon, T = window_counts(Z, H, W)
+    out = torch.empty((N, C), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((nLon, T, heads, 144), dtype=torch.float32, device=qkv.device)
+    g = geom(Z, H, W, C, heads)
+    _call("attention_bf16[C=%d]" % C, "pangu_window_attention_train",
+          (_ptr(qkv), _ptr(qkv_bias), _ptr(earth_bias), _ptr(out), _ptr(lse), g, int(roll), _stream(),),
+          flops=nLon * T * heads * 4.0 * 144 * 144 * 32, nbytes=float(qkv.numel() * 2 + out.numel() * 2 + earth_bias.numel() * 2))
+    return out, lse
+
+
+def window_attention_backward(qkv, qkv_bias, earth_bias, out, d_out, lse, Z, H, W, heads, roll, d_earth_bias, d_pad):
+    """-> d_qkv bf16 [N, 3C]; d_earth_bias fp32 [T, heads, 144, 144] and d_pad fp32 [3C] are accumulated."""
+    for t, n in ((qkv, "qkv"), (earth_bias, "earth_bias"), (out, "out"), (d_out, "d_out")):
+        _chk(t, torch.bfloat16, n)
+    _chk(lse, torch.float32, "lse")
+    _chk(d_earth_bias, torch.float32, "d_earth_bias")
+    _chk(d_pad, torch.float32, "d_pad")
+    N, C3 = qkv.shape
+    C = C3 // 3
+    nLon, T = window_counts(Z, H, W)
+    d_qkv = torch.empty_like(qkv)
+    g = geom(Z, H, W, C, heads)
+    _call("attention_bwd_bf16[C=%d]" % C, "pangu_window_attention_backward",
+          (_ptr(qkv), _ptr(qkv_bias), _ptr(earth_bias), _ptr(out), _ptr(d_out), _ptr(lse), _ptr(d_qkv), _ptr(d_earth_bias),
+           _ptr(d_pad), g, int(roll), _stream(),),
+          flops=nLon * T * heads * 14.0 * 144 * 144 * 32, nbytes=float(qkv.numel() * 4 + out.numel() * 4 + earth_bias.numel() * 6))
+    return d_qkv
+
+
+def patch_recover_gather_backward(d_output, d_output_surface, lat=721):
+    _chk(d_output, torch.float32, "d_output")
+    _chk(d_output_surface, torch.float32, "d_output_surface")
+    tok_rows = (lat + 3) // 4
+    dev = d_output.device
+    dyu = torch.empty((7 * tok_rows * 360, 160), dtype=torch.bfloat16, device=dev)
+    dys = torch.empty((tok_rows * 360, 64), dtype=torch.bfloat16, device=dev)
+    _call("patch_recover_gather_backward", "pangu_patch_recover_gather_backward",
+          (_ptr(d_output), _ptr(d_output_surface), _ptr(dyu), _ptr(dys), lat, tok_rows, _stream(),), kernels=2,
+          nbytes=float((d_output.numel() + d_output_surface.numel()) * 4 + (dyu.numel() + dys.numel()) * 2))
+    return dyu, dys
