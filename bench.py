@@ -171,6 +171,123 @@ def run_cpu_reference(args, as_impl):
             "seconds_per_forward": sec, "detail": detail, "steps": steps, "warmup": warm, "times": times}
 
 
+
+# --------------------------------------------------------------------------------------------
+# fine-tune step (BASELINE configs[4]): fwd + loss + bwd + gradient all-reduce + Adam, one sample per GPU
+# --------------------------------------------------------------------------------------------
+def run_finetune(args, rank, world, dev, torch, dist, orc, PanguModel, ops):
+    from pangu_b200.loss import weighted_l1_loss
+    torch.manual_seed(1234 + rank)                          # DropPath draws differ per rank, like under DDP
+    model = PanguModel(device="cpu")
+    model.load_state_dict(orc.synth_params(seed=0), strict=True)
+    model = model.to(dev).train().set_compute_dtype("bf16")
+    inp, inp_s, stats, maps, const_h = orc.synth_inputs(seed=1 + rank)
+    g = torch.Generator().manual_seed(100 + rank)
+    tgt, tgt_s = torch.randn(inp.shape, generator=g), torch.randn(inp_s.shape, generator=g)
+    h_bufs = [t.pin_memory() for t in (inp, inp_s, tgt, tgt_s)]
+    d_bufs = [t.to(dev) for t in (inp, inp_s, tgt, tgt_s)]
+    stats = tuple(s.to(dev) for s in stats)
+    maps, const_h = maps.to(dev), const_h.to(dev)
+    # era5_data/config.py:45-46 (Adam, lr 2e-5, weight decay 3e-6), finetune/finetune_fully.py:202
+    opt = torch.optim.Adam(model.parameters(), lr=2e-5, weight_decay=3e-6, fused=True)
+    reducer, fwd = None, model
+    if world > 1:
+        if args.dp == "ddp":
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            fwd = DDP(model, device_ids=[dev.index], bucket_cap_mb=64, gradient_as_bucket_view=True)
+        else:
+            from pangu_b200.dist import GradientAllReducer
+            reducer = GradientAllReducer(model)
+    h_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def train_step(bufs):
+        a, b, t, ts = bufs
+        opt.zero_grad(set_to_none=True)
+        o, os_ = fwd(a, b, stats, maps, const_h)
+        loss = weighted_l1_loss(o, os_, t, ts)              # targets are already normalised (synthetic)
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        opt.step()
+        return loss
+
+    def step_resident():
+        return train_step(d_bufs)
+
+    def step_e2e():
+        loss = train_step([h.to(dev, non_blocking=True) for h in h_bufs])
+        h_loss.copy_(loss.detach(), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    ops.LAUNCHES = 0
+    total_ms = timed(step_resident, args.steps)
+    launches = ops.LAUNCHES
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * args.steps / (total_ms / 1000.0)
+    step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+    peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    kernels = None
+    if not args.no_kernel_times:
+        ops.start_kernel_timing()
+        step_resident()
+        table = ops.stop_kernel_timing()
+        kernels = {k: {"calls_per_step": v[0], "ms_per_step": v[1],
+                       "tflops": (v[2] / (v[1] / 1000.0) / 1e12) if v[1] > 0 and v[2] > 0 else None,
+                       "gbs": (v[3] / (v[1] / 1000.0) / 1e9) if v[1] > 0 and v[3] > 0 else None}
+                   for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])}
+    peaks = load_peaks()
+    if rank == 0:
+        ms = total_ms / args.steps
+        line = {"metric": "fine-tune steps/s at 721x1440 bf16 (fwd + L1 loss + bwd + gradient all-reduce + Adam), batch 1 per GPU",
+                "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic (seeded random-init weights, ERA5-shaped inputs and targets)",
+                "config": {"workload": "finetune_fully.py fwd+bwd bf16, batch 1 per GPU, data-parallel NCCL all-reduce (BASELINE.json configs[4])",
+                           "parallelism": f"dp{world} ({'torch DDP' if args.dp == 'ddp' else 'GradientAllReducer: flat fp32 buckets, NCCL all-reduce overlapped with the backward'})",
+                           "params": 276659936, "grad_bytes": 276659936 * 4, "optimizer": "Adam lr 2e-5 wd 3e-6 (torch fused)",
+                           "activations": "saved (no re-computation)" if os.environ.get("PANGU_B200_TRAIN_RECOMPUTE", "0") == "0" else "re-computed per block",
+                           "peak_mem_gb": peak_gb, "cache": "activations per step (>= 35 GB) exceed the 126 MB L2; no flush needed"},
+                "e2e": {"value": world * args.steps / (e2e_ms / 1000.0), "unit": "steps/s", "ms_per_step": e2e_ms / args.steps,
+                        "h2d_bytes_per_step": sum(h.numel() for h in h_bufs) * 4, "d2h_bytes_per_step": 4,
+                        "api": "PanguModel(...).train() forward, pangu_b200.loss.weighted_l1_loss, loss.backward(), optimizer.step() from pinned host samples"},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"bound": "tensor", "achieved": 3 * FLOPS_TOTAL / (ms / 1000.0) / 1e12, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                             "frac": 3 * FLOPS_TOTAL / (ms / 1000.0) / 1e12 / peaks["tf_sust"], "traffic": None,
+                             "note": "whole step: 3 x 8.421 TFLOP (fwd + dgrad + wgrad, SURVEY 8d) per sample / step time"},
+                "cpu_baseline": None, "kernels": kernels}
+        print(json.dumps(line))
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        threading.Timer(15.0, lambda: os._exit(0)).start()
+        dist.destroy_process_group()
+        os._exit(0)
+
+
 # --------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -178,10 +295,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "bands"],
+    ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "bands", "finetune"],
                     help="multi-GPU partition: replicas = one forecast per GPU (weak scaling); bands = ONE forecast "
                          "sharded over latitude bands with NCCL halo exchange (strong scaling, BASELINE configs[3]); "
-                         "auto = bands when N > 1")
+                         "finetune = BASELINE configs[4]: fwd + loss + bwd + NCCL gradient all-reduce + Adam, one sample per "
+                         "GPU (data parallel, weak scaling); auto = bands when N > 1")
+    ap.add_argument("--dp", default="buckets", choices=["buckets", "ddp"],
+                    help="--mode finetune gradient all-reduce: pangu_b200.dist.GradientAllReducer or torch DDP (what the "
+                         "reference uses, finetune/finetune_fully.py:220)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the step from a CUDA graph (pangu_b200.graph.GraphedForward) instead of ~100 "
@@ -198,6 +319,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     mode = args.mode if args.mode != "auto" else ("bands" if world > 1 else "replicas")
+    if mode == "finetune" and args.impl == "reference":
+        raise SystemExit("--impl reference times the forward (the headline metric); --mode finetune has no CPU arm")
     if mode == "bands" and world not in (1, 2, 4, 8):
         mode = "replicas"
     par = (f"replicas x{world} (one forecast per GPU, no data-path collective)" if mode == "replicas" else
@@ -235,6 +358,9 @@ def main():
     import pangu_oracle as orc
     from models.pangu_model import PanguModel
     from pangu_b200 import ops
+
+    if mode == "finetune":
+        return run_finetune(args, rank, world, dev, torch, dist, orc, PanguModel, ops)
 
     model = PanguModel(device="cpu")
     model.load_state_dict(orc.synth_params(seed=0), strict=True)

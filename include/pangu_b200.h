@@ -283,16 +283,26 @@ int pangu_window_attention_train(const void* qkv, const float* qkv_bias, const v
  * pre-scaled exactly as given to pangu_window_attention_train, out its output, d_out bf16 [N, C] the incoming
  * gradient, lse from the forward.  Writes d_qkv bf16 [N, 3C] (w.r.t. the UN-scaled linear1 output, token order);
  * accumulates d_earth_bias fp32 [T, heads, 144, 144] (sum over longitude windows of dS; gradient of the fp32
- * earth_specific_bias parameter) and d_qkv_bias_pad fp32 [3C] (the zero-pad rows' share of linear1's bias gradient:
- * those rows equal the bias in the forward, models/layers.py:228,419).  roll as in pangu_window_attention. */
+ * earth_specific_bias parameter) and d_qkv_bias fp32 [3C] = linear1's bias gradient: the column sums of dq/dk/dv over
+ * ALL window rows, including the zero-pad rows, which equal the bias in the forward (models/layers.py:228,419).
+ * roll as in pangu_window_attention. */
 int pangu_window_attention_backward(const void* qkv, const float* qkv_bias, const void* earth_bias, const void* out,
                                     const void* d_out, const float* lse, void* d_qkv, float* d_earth_bias,
-                                    float* d_qkv_bias_pad, const pangu_geom* g, int roll, void* stream);
+                                    float* d_qkv_bias, const pangu_geom* g, int roll, void* stream);
 
 /* Inverse of pangu_patch_recover_scatter_rows (models/layers.py:593-619): gradients of the output fields ->
  * gradients of the two conv outputs as bf16 [7*tok_rows*360, 160] / [tok_rows*360, 64]; cropped positions get 0. */
 int pangu_patch_recover_gather_backward(const float* d_output, const float* d_output_surface, void* dy_upper,
                                         void* dy_surface, int32_t lat_rows, int32_t tok_rows, void* stream);
+
+/* The reference's training loss and its gradient in ONE pass (models/pangu_sample.py:163-218, default branch; SURVEY 8f
+ * rank 2): target normalised per plane ((x - mean[plane]) / std[plane], era5_data/utils_data.py normData; mean = std =
+ * NULL: already normalised), loss_sum += scale * sum w[plane / planes_per_var] * |out - target|, and, when d_out is
+ * not NULL, d_out = scale * w * sign(out - target).  out / target / d_out fp32 [planes, plane_elems]; the caller
+ * passes scale = loss_weight / numel so that loss_sum is loss_weight * mean(L1 * w). */
+int pangu_weighted_l1_loss(const float* out, const float* target, const float* mean, const float* stdv,
+                           const float* weight, int32_t planes, int32_t planes_per_var, int64_t plane_elems,
+                           float scale, float* loss_sum, float* d_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -3,8 +3,9 @@
 The reference trains `PanguModel` with plain autograd (`loss.backward()`, models/pangu_sample.py:226) under DDP
 (finetune/finetune_fully.py:220) and re-computes every block in the backward pass (checkpoint.checkpoint,
 models/layers.py:143-149).  This module keeps that shape: one Function per EarthSpecificBlock / PatchEmbedding /
-DownSample / UpSample / PatchRecovery; a Function saves only its inputs (fp32 stream + bf16 shadow), the backward
-re-computes the intermediates with the un-fused kernels and then runs
+DownSample / UpSample / PatchRecovery.  With 180 GB of HBM3e per GPU the block Function SAVES its intermediates
+(35 GB per sample) instead of re-computing them; $PANGU_B200_TRAIN_RECOMPUTE=1 gives the reference's behaviour
+(only the block inputs are kept; the backward re-runs the un-fused forward first).  The backward runs
 
   * dgrad GEMMs  -- the forward tcgen05 GEMM kernels on transposed bf16 weight copies, the residual-gradient add
                     fused into their epilogue (`ops.linear_add`);
@@ -14,6 +15,8 @@ re-computes the intermediates with the un-fused kernels and then runs
 Parameter gradients are fp32 tensors shaped like the parameters, so DDP's bucketed NCCL all-reduce (or
 `pangu_b200.dist.allreduce_gradients`) sees exactly what it sees with the reference.  bf16 compute mode only.
 """
+import os
+
 import torch
 
 from . import functional as PF
@@ -21,6 +24,8 @@ from . import ops
 from .abi import PanguError
 
 F32 = torch.float32
+# 1 = keep only block inputs and re-compute the block in its backward (the reference's checkpointing)
+RECOMPUTE = os.environ.get("PANGU_B200_TRAIN_RECOMPUTE", "0") != "0"
 
 
 def _zeros(n, dev):
@@ -54,46 +59,65 @@ def block_params(blk):
             blk.norm2.weight, blk.norm2.bias)
 
 
-def block_backward(blk, x0, x0b, Z, H, W, roll, s1, s2, g2):
-    """Backward of EarthSpecificBlock.forward (models/layers.py:218-299) for one sample.
-    x0 fp32 / x0b bf16 [N, C]: the block input; s1, s2: DropPath factors of the two branches (0 = branch dropped);
-    g2 fp32 [N, C]: gradient of the block output.  -> (dx0 fp32, 13 parameter gradients in BLOCK_PARAMS order)."""
+SAVED_KEYS = ("x0b", "qkv", "o", "lse", "y1", "x1b", "h_pre", "h", "y2")
+
+
+def block_forward_train(blk, x0, x0b, Z, H, W, roll, s1, s2):
+    """EarthSpecificBlock.forward (models/layers.py:218-299) with the UN-fused kernels, so that every intermediate the
+    backward needs is left in HBM: qkv, the attention output and its log2-sum-exp rows, the two pre-LayerNorm
+    tensors, the Mlp hidden activation before and after the GELU.  -> (x2 fp32, x2 bf16, saved dict)."""
     att, mlp = blk.attention, blk.linear
     wc = blk._wcache
-    dev = x0.device
-    N, C = x0.shape
+    f = PF._f
+    sv = {"x0b": x0b}
+    if s1 != 0.0:
+        w_qkv, b_qkv, eb = PF.attention_operands(att, wc)               # pre-scaled (scale*log2e folded into q)
+        qkv = ops.linear(x0b, w_qkv, b_qkv)
+        o, lse = ops.window_attention_train(qkv, b_qkv, eb, Z, H, W, att.head_number, 1 if roll else 0)
+        y1 = ops.linear(o, wc.bf16("a2", att.linear2.weight), f(att.linear2.bias), out_dtype=F32)
+        gam1, bet1 = PF._affine(blk.norm1, s1)
+        x1, x1b = ops.ln_residual(y1, gam1, bet1, residual=x0, want_bf16=True, eps=blk.norm1.eps)
+        sv.update(qkv=qkv, o=o, lse=lse, y1=y1)
+    else:
+        x1, x1b = x0, x0b
+    sv["x1b"] = x1b
+    if s2 != 0.0:
+        w1, b1 = wc.bf16("m1", mlp.linear1.weight), f(mlp.linear1.bias)
+        h_pre = ops.linear(x1b, w1, b1)
+        h = ops.linear(x1b, w1, b1, act=PF.ACT_GELU)                    # second pass of the GEMM beats an elementwise pass
+        y2 = ops.linear(h, wc.bf16("m2", mlp.linear2.weight), f(mlp.linear2.bias), out_dtype=F32)
+        gam2, bet2 = PF._affine(blk.norm2, s2)
+        x2, x2b = ops.ln_residual(y2, gam2, bet2, residual=x1, want_bf16=True, eps=blk.norm2.eps)
+        sv.update(h_pre=h_pre, h=h, y2=y2)
+    else:
+        x2, x2b = x1, x1b
+    return x2, x2b, sv
+
+
+def block_backward(blk, sv, Z, H, W, roll, s1, s2, g2):
+    """Backward of EarthSpecificBlock.forward for one sample.  sv: the intermediates of block_forward_train;
+    s1, s2: DropPath factors of the two branches (0 = branch dropped); g2 fp32 [N, C]: gradient of the block output.
+    -> (dx0 fp32, 13 parameter gradients in BLOCK_PARAMS order)."""
+    att, mlp = blk.attention, blk.linear
+    wc = blk._wcache
+    x0b, x1b = sv["x0b"], sv["x1b"]
+    dev = x0b.device
+    N, C = x0b.shape
     heads = att.head_number
     f = PF._f
     g2 = g2.contiguous()
     ps = block_params(blk)
     grads = [None] * 13
 
-    # ---- re-compute the forward intermediates (un-fused kernels, so that they exist in HBM)
-    if s1 != 0.0:
-        w_qkv, b_qkv, eb = PF.attention_operands(att, wc)               # pre-scaled (scale*log2e folded into q)
-        qkv = ops.linear(x0b, w_qkv, b_qkv)
-        o, lse = ops.window_attention_train(qkv, b_qkv, eb, Z, H, W, heads, 1 if roll else 0)
-        y1 = ops.linear(o, wc.bf16("a2", att.linear2.weight), f(att.linear2.bias), out_dtype=F32)
-        gam1, bet1 = PF._affine(blk.norm1, s1)
-        x1, x1b = ops.ln_residual(y1, gam1, bet1, residual=x0, want_bf16=True, eps=blk.norm1.eps)
-    else:
-        x1, x1b = x0, x0b
-
     # ---- x2 = x1 + s2 * LN2(Mlp(x1))
     if s2 != 0.0:
-        h_pre = ops.linear(x1b, wc.bf16("m1", mlp.linear1.weight), f(mlp.linear1.bias))
-        h = ops.gelu_bf16(h_pre)
-        y2 = ops.linear(h, wc.bf16("m2", mlp.linear2.weight), f(mlp.linear2.bias), out_dtype=F32)
         dg2, db2n, db2 = _zeros(C, dev), _zeros(C, dev), _zeros(C, dev)
-        dy2 = ops.ln_backward(g2, y2, f(blk.norm2.weight), scale=s2, dgamma=dg2, dbeta=db2n, dcolsum=db2, eps=blk.norm2.eps)
-        del y2
-        dw2 = ops.linear_wgrad(dy2, h)
-        del h
+        dy2 = ops.ln_backward(g2, sv["y2"], f(blk.norm2.weight), scale=s2, dgamma=dg2, dbeta=db2n, dcolsum=db2, eps=blk.norm2.eps)
+        dw2 = ops.linear_wgrad(dy2, sv["h"])
         dh = ops.linear(dy2, _wT(wc, "m2", mlp.linear2.weight), None)   # [N, 4C] bf16
         del dy2
         db1 = _zeros(4 * C, dev)
-        ops.gelu_backward_bf16(dh, h_pre, db1)                          # dh <- dh * gelu'(h_pre)
-        del h_pre
+        ops.gelu_backward_bf16(dh, sv["h_pre"], db1)                    # dh <- dh * gelu'(h_pre)
         dw1 = ops.linear_wgrad(dh, x1b)
         g1 = ops.linear_add(dh, _wT(wc, "m1", mlp.linear1.weight), None, addend=g2)
         del dh
@@ -105,18 +129,18 @@ def block_backward(blk, x0, x0b, Z, H, W, roll, s1, s2, g2):
 
     # ---- x1 = x0 + s1 * LN1(proj(attention(qkv(x0))))
     if s1 != 0.0:
+        _w_qkv, b_qkv, eb = PF.attention_operands(att, wc)
         dg1, db1n, dba2 = _zeros(C, dev), _zeros(C, dev), _zeros(C, dev)
-        dy1 = ops.ln_backward(g1, y1, f(blk.norm1.weight), scale=s1, dgamma=dg1, dbeta=db1n, dcolsum=dba2, eps=blk.norm1.eps)
-        del y1
-        dwa2 = ops.linear_wgrad(dy1, o)
+        dy1 = ops.ln_backward(g1, sv["y1"], f(blk.norm1.weight), scale=s1, dgamma=dg1, dbeta=db1n, dcolsum=dba2, eps=blk.norm1.eps)
+        dwa2 = ops.linear_wgrad(dy1, sv["o"])
         do = ops.linear(dy1, _wT(wc, "a2", att.linear2.weight), None)   # [N, C] bf16
         del dy1
         d_eb = torch.zeros(att.earth_specific_bias.shape[1:], dtype=F32, device=dev)
-        dba1 = _zeros(3 * C, dev)                                        # pad rows' share first, then the real rows
-        dqkv = ops.window_attention_backward(qkv, b_qkv, eb, o, do, lse, Z, H, W, heads, 1 if roll else 0, d_eb, dba1)
-        del qkv, o, do, lse
+        dba1 = _zeros(3 * C, dev)
+        dqkv = ops.window_attention_backward(sv["qkv"], b_qkv, eb, sv["o"], do, sv["lse"], Z, H, W, heads, 1 if roll else 0,
+                                             d_eb, dba1)
+        del do
         dwa1 = ops.linear_wgrad(dqkv, x0b)
-        ops.colsum(dqkv, out=dba1)
         g0 = ops.linear_add(dqkv, _wT(wc, "a1", att.linear1.weight), None, addend=g1)
         del dqkv
         grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6] = \
@@ -129,7 +153,12 @@ def block_backward(blk, x0, x0b, Z, H, W, roll, s1, s2, g2):
 
 
 class BlockFn(torch.autograd.Function):
-    """(x fp32 [N,C], xb bf16 or None, 13 parameters) -> (x_out fp32, x_out bf16)."""
+    """(x fp32 [N,C], xb bf16 or None, 13 parameters) -> (x_out fp32, x_out bf16).
+
+    Default: the forward runs the un-fused kernels and SAVES the intermediates (about 3.4 GB per stage-A block,
+    1.7 GB per stage-B block, 35 GB per sample in total -- a B200 has 180 GB), so the backward re-computes nothing.
+    $PANGU_B200_TRAIN_RECOMPUTE=1 restores the reference's checkpoint behaviour (models/layers.py:143-149): fused
+    forward kernels, only the block input is kept, the backward re-runs the un-fused forward first."""
 
     @staticmethod
     def forward(ctx, x, xb, blk, Z, H, W, roll, s1, s2, *params):
@@ -137,8 +166,14 @@ class BlockFn(torch.autograd.Function):
         if xb is None:
             xb = ops.cast_bf16(x)
         ctx.blk, ctx.geo, ctx.scales = blk, (Z, H, W, roll), (s1, s2)
-        ctx.save_for_backward(x, xb)
-        y, yb = PF.block_forward(blk, x, Z, H, W, roll, "bf16", xb, s1, s2)
+        ctx.recompute = RECOMPUTE
+        if RECOMPUTE:
+            ctx.save_for_backward(x, xb)
+            y, yb = PF.block_forward(blk, x, Z, H, W, roll, "bf16", xb, s1, s2)
+        else:
+            y, yb, sv = block_forward_train(blk, x, xb, Z, H, W, roll, s1, s2)
+            ctx.keys = [k for k in SAVED_KEYS if k in sv]
+            ctx.save_for_backward(*[sv[k] for k in ctx.keys])
         if y is x:                                              # both branches dropped: outputs must not alias inputs
             y, yb = x.clone(), xb.clone()
         ctx.mark_non_differentiable(yb)
@@ -146,11 +181,15 @@ class BlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, _gb):
-        x, xb = ctx.saved_tensors
         Z, H, W, roll = ctx.geo
         s1, s2 = ctx.scales
         with torch.no_grad():
-            dx, pg = block_backward(ctx.blk, x, xb, Z, H, W, roll, s1, s2, g)
+            if ctx.recompute:
+                x, xb = ctx.saved_tensors
+                _y, _yb, sv = block_forward_train(ctx.blk, x, xb, Z, H, W, roll, s1, s2)
+            else:
+                sv = dict(zip(ctx.keys, ctx.saved_tensors))
+            dx, pg = block_backward(ctx.blk, sv, Z, H, W, roll, s1, s2, g)
         need = ctx.needs_input_grad
         return (dx if need[0] else None, None, None, None, None, None, None, None, None,
                 *[gp if need[9 + i] else None for i, gp in enumerate(pg)])

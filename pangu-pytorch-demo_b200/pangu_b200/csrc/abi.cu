@@ -181,14 +181,14 @@ extern "C" int pangu_window_attention_train(const void* qkv, const float* qkv_bi
 
 extern "C" int pangu_window_attention_backward(const void* qkv, const float* qkv_bias, const void* earth_bias,
                                                const void* out, const void* d_out, const float* lse, void* d_qkv,
-                                               float* d_earth_bias, float* d_qkv_bias_pad, const pangu_geom* gg,
+                                               float* d_earth_bias, float* d_qkv_bias, const pangu_geom* gg,
                                                int roll, void* stream) {
   WinGeom g;
-  if (!make_geom(gg, g) || !qkv || !qkv_bias || !earth_bias || !out || !d_out || !lse || !d_qkv || !d_earth_bias || !d_qkv_bias_pad) {
+  if (!make_geom(gg, g) || !qkv || !qkv_bias || !earth_bias || !out || !d_out || !lse || !d_qkv || !d_earth_bias || !d_qkv_bias) {
     set_error("window_attention_backward: bad argument");
     return PANGU_ERR_BAD_ARG;
   }
   if (g.C != g.heads * kHeadDim) { set_error("window_attention_backward: C=%d must equal heads*32", g.C); return PANGU_ERR_BAD_ARG; }
   if (roll < 0 || roll > 2) { set_error("window_attention_backward: roll must be 0, 1 or 2"); return PANGU_ERR_BAD_ARG; }
-  return launch_window_attention_bwd(qkv, qkv_bias, earth_bias, out, d_out, lse, d_qkv, d_earth_bias, d_qkv_bias_pad, g, roll, as_stream(stream));
+  return launch_window_attention_bwd(qkv, qkv_bias, earth_bias, out, d_out, lse, d_qkv, d_earth_bias, d_qkv_bias, g, roll, as_stream(stream));
 }

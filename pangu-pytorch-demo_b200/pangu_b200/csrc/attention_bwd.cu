@@ -10,8 +10,8 @@
 //                                       dV = P^T dO and dK = dS^T q stay warp-local (no smem round trip of the
 //                                       144 x 144 matrices, no atomics on the activations)
 // Gradients of real tokens are written at their un-rolled token position of dqkv [N, 3C]; zero-pad rows were
-// linear1(0) = bias in the forward (layers.py:228,419), so their dq/dk/dv are summed into dpad [3C] (a part of the
-// bias gradient of linear1).  q, k, bias arrive pre-scaled like in the forward (scale*log2e folded into q, log2e
+// linear1(0) = bias in the forward (layers.py:228,419), so they only feed linear1's bias gradient: the kernel sums
+// dq/dk/dv over ALL window rows (real and pad) into dqkv_bias [3C], which IS that bias gradient.  q, k, bias arrive pre-scaled like in the forward (scale*log2e folded into q, log2e
 // into the bias table): dq is returned w.r.t. the UN-scaled linear1 output, dk gets the matching ln2 factor.
 #include <type_traits>
 
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ qkv_bias,
                             const __nv_bfloat16* __restrict__ earth_bias, const __nv_bfloat16* __restrict__ o,
                             const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
-                            __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, float* __restrict__ dpad,
+                            __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, float* __restrict__ dqkv_bias,
                             WinGeom g, int roll, int lon_chunk) {
   extern __shared__ __align__(128) uint8_t smem[];
   __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(smem);                       // [144][152]
@@ -51,7 +51,6 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
   const int l_begin = lchunk * lon_chunk;
   const int l_end = min(g.nLon, l_begin + lon_chunk);
 
-  int my_pad = 0;
   for (int k = tid; k < kWinTokens; k += kThreads) {
     const int zw = t / g.nH, hw = t - zw * g.nH;
     const int dz = k / 72, r = k - dz * 72, dh = r / 12, dw = r - dh * 12;
@@ -64,7 +63,6 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
       const bool real = h < g.H;
       s_rowbase[k] = real ? (z * g.H + h) * g.W : -1;
       s_dw[k] = dw | ((real ? 1 : 0) << 8);
-      my_pad |= real ? 0 : 1;
     }
     s_gid[k] = (uint8_t)shift_group(g, t, k);
   }
@@ -75,7 +73,7 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
       cp_async16(smem_u32(s_bias + r * kBiasPitch + c * 8), src + r * kWinTokens + c * 8);
     }
   }
-  const bool has_pad = __syncthreads_or(my_pad) != 0;
+  __syncthreads();
 
   auto token_of = [&](int l, int dwc, int rb) -> long long {
     if (roll == 2) return (long long)l * g.T * kWinTokens + rb;
@@ -119,7 +117,6 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
   const int mi = lane >> 3, mr = lane & 7;
   const bool masked_type = roll == 1 && ((t / g.nH == g.nZ - 1) || (t % g.nH == g.nH - 1));
   const int gid_lo = s_gid[row0 + gq], gid_hi = s_gid[row0 + gq + 8];       // valid after the barrier above
-  const bool pad_lo = (s_dw[row0 + gq] >> 8) == 0, pad_hi = (s_dw[row0 + gq + 8] >> 8) == 0;
 
   float dbias_acc[3][6][4];
 #pragma unroll
@@ -128,11 +125,11 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
     for (int b = 0; b < 6; ++b)
 #pragma unroll
       for (int c = 0; c < 4; ++c) dbias_acc[a][b][c] = 0.f;
-  float padsum[3][4][2];
+  float colsum[3][4][2];
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) padsum[a][b][0] = padsum[a][b][1] = 0.f;
+    for (int b = 0; b < 4; ++b) colsum[a][b][0] = colsum[a][b][1] = 0.f;
 
   for (int l = l_begin; l < l_end; ++l) {
     const int b = (l - l_begin) & 1;
@@ -175,10 +172,8 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
         const float v0 = acc[nt][0] * mult, v1 = acc[nt][1] * mult, v2 = acc[nt][2] * mult, v3 = acc[nt][3] * mult;
         *reinterpret_cast<uint32_t*>(so + tile_off(row0 + gq, nt) + 4 * tq) = pack_bf16(v0, v1);
         *reinterpret_cast<uint32_t*>(so + tile_off(row0 + gq + 8, nt) + 4 * tq) = pack_bf16(v2, v3);
-        if (has_pad) {
-          if (pad_lo) { padsum[s][nt][0] += v0; padsum[s][nt][1] += v1; }
-          if (pad_hi) { padsum[s][nt][0] += v2; padsum[s][nt][1] += v3; }
-        }
+        colsum[s][nt][0] += v0 + v2;                        // every window row, pad rows included, is a row of linear1's output
+        colsum[s][nt][1] += v1 + v3;
       }
       __syncwarp();
 #pragma unroll
@@ -343,19 +338,19 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
         atomicAdd(dst + (row0 + gq + 8) * kWinTokens + j + 1, dbias_acc[kvb][nt][3]);
       }
   }
-  // ---- ... and the pad rows' share of linear1's bias gradient
-  if (has_pad) {
+  // ---- ... and linear1's bias gradient: column sums of dq / dk / dv over all rows this CTA produced
+  {
 #pragma unroll
     for (int s = 0; s < 3; ++s)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          float v = padsum[s][nt][e];
+          float v = colsum[s][nt][e];
           v += __shfl_xor_sync(0xffffffffu, v, 4);
           v += __shfl_xor_sync(0xffffffffu, v, 8);
           v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (gq == 0) atomicAdd(dpad + s * C + head * kHeadDim + nt * 8 + 2 * tq + e, v);
+          if (gq == 0) atomicAdd(dqkv_bias + s * C + head * kHeadDim + nt * 8 + 2 * tq + e, v);
         }
   }
 }

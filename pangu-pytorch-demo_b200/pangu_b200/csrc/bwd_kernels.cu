@@ -215,6 +215,40 @@ patch_recover_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* __restri
   }
 }
 
+
+// Training loss of the reference in one pass (models/pangu_sample.py:163-218, default branch): the target is normalised
+// (era5_data/utils_data.py normData: (x - mean) / std per variable and level), then
+//   loss += scale * sum_i w[var(i)] * |out_i - target_i|     and     d_out_i = scale * w[var(i)] * sign(out_i - target_i)
+// with scale = loss_weight / numel, i.e. loss_weight * mean(L1(out, target) * w) and its gradient for d loss = 1.
+__global__ void __launch_bounds__(256)
+weighted_l1_loss_kernel(const float4* __restrict__ out, const float4* __restrict__ target, const float* __restrict__ mean,
+                        const float* __restrict__ stdv, const float* __restrict__ weight, int planes_per_var,
+                        long long plane_elems4, long long total4, float scale, float* __restrict__ loss_sum,
+                        float4* __restrict__ d_out) {
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int plane = (int)(i / plane_elems4);
+    const float w = __ldg(weight + plane / planes_per_var) * scale;
+    float m = 0.f, rs = 1.f;
+    if (mean != nullptr) { m = __ldg(mean + plane); rs = 1.0f / __ldg(stdv + plane); }
+    const float4 o = __ldg(out + i), t = __ldg(target + i);
+    const float d0 = o.x - (t.x - m) * rs, d1 = o.y - (t.y - m) * rs, d2 = o.z - (t.z - m) * rs, d3 = o.w - (t.w - m) * rs;
+    acc += w * (fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3));
+    if (d_out != nullptr)
+      d_out[i] = make_float4(d0 > 0.f ? w : (d0 < 0.f ? -w : 0.f), d1 > 0.f ? w : (d1 < 0.f ? -w : 0.f),
+                             d2 > 0.f ? w : (d2 < 0.f ? -w : 0.f), d3 > 0.f ? w : (d3 < 0.f ? -w : 0.f));
+  }
+  acc = warp_sum(acc);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = part[threadIdx.x];
+    v += __shfl_xor_sync(0xffu, v, 4); v += __shfl_xor_sync(0xffu, v, 2); v += __shfl_xor_sync(0xffu, v, 1);
+    if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+  }
+}
+
 static unsigned row_grid(long long M, int warps_per_cta) {
   long long want = (M + warps_per_cta - 1) / warps_per_cta;
   const long long cap = 148LL * 8;
@@ -309,4 +343,17 @@ extern "C" int pangu_patch_recover_gather_backward(const float* d_output, const 
   patch_recover_bwd_kernel<160, 40, true><<<gu, 256, 0, st>>>(d_output, (__nv_bfloat16*)dy_upper, lat_rows, tok_rows);
   patch_recover_bwd_kernel<64, 16, false><<<gs, 256, 0, st>>>(d_output_surface, (__nv_bfloat16*)dy_surface, lat_rows, tok_rows);
   return check_launch("patch_recover_gather_backward");
+}
+
+extern "C" int pangu_weighted_l1_loss(const float* out, const float* target, const float* mean, const float* stdv,
+                                      const float* weight, int32_t planes, int32_t planes_per_var, int64_t plane_elems,
+                                      float scale, float* loss_sum, float* d_out, void* stream) {
+  if (!out || !target || !weight || !loss_sum || planes <= 0 || planes_per_var <= 0 || plane_elems <= 0 || (plane_elems & 3) ||
+      ((mean == nullptr) != (stdv == nullptr))) { set_error("weighted_l1_loss: bad argument"); return PANGU_ERR_BAD_ARG; }
+  const long long total4 = (long long)planes * (plane_elems / 4);
+  long long want = (total4 + 255) / 256;
+  const unsigned grid = (unsigned)(want < 148LL * 16 ? want : 148LL * 16);
+  weighted_l1_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>((const float4*)out, (const float4*)target, mean, stdv, weight,
+                                                              planes_per_var, plane_elems / 4, total4, scale, loss_sum, (float4*)d_out);
+  return check_launch("weighted_l1_loss");
 }

@@ -144,3 +144,47 @@ def test_dist_comm_neighbour_exchange_gloo_world2():
     assert torch.equal(got[1][1], got[0][2] * 2), "rank 1 receives what rank 0 computed for it"
     assert torch.equal(got[0][3], got[1][2]) and got[0][4] is None      # swap_edges: south halo of rank 0
     assert torch.equal(got[1][4], got[0][2] + 7) and got[1][3] is None  # north halo of rank 1
+
+
+# ------------------------------------------------------------------------------------------ fine-tune DP (configs[4])
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pangu_b200.dist import GradientAllReducer
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.LayerNorm(16), torch.nn.Linear(16, 4))
+        red = GradientAllReducer(net, bucket_mb=16 * 4 / (1 << 20) * 4)      # several tiny buckets
+        outs = []
+        for it in range(2):                                                   # buckets are reusable step after step
+            net.zero_grad(set_to_none=True)
+            x = torch.full((3, 8), float(rank + 1 + it))
+            net(x).square().sum().backward()
+            local = [p.grad.numpy().copy() for p in net.parameters()]           # numpy: pickled by value
+            red.finish()
+            outs.append((local, [p.grad.numpy().copy() for p in net.parameters()]))
+        q.put((rank, len(red.buckets), outs))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreducer_gloo_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        rank, nb, outs = q.get(timeout=120)
+        got[rank] = outs
+        assert nb > 1
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for it in range(2):
+        mean = [(a + b) / 2 for a, b in zip(got[0][it][0], got[1][it][0])]
+        for r in range(world):
+            for m, g in zip(mean, got[r][it][1]):
+                assert np.allclose(m, g, rtol=1e-6, atol=1e-7)
