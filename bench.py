@@ -300,7 +300,7 @@ def main():
                          "sharded over latitude bands with NCCL halo exchange (strong scaling, BASELINE configs[3]); "
                          "finetune = BASELINE configs[4]: fwd + loss + bwd + NCCL gradient all-reduce + Adam, one sample per "
                          "GPU (data parallel, weak scaling); auto = bands when N > 1")
-    ap.add_argument("--dp", default="buckets", choices=["buckets", "ddp"],
+    ap.add_argument("--dp", default="ddp", choices=["buckets", "ddp"],
                     help="--mode finetune gradient all-reduce: pangu_b200.dist.GradientAllReducer or torch DDP (what the "
                          "reference uses, finetune/finetune_fully.py:220)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
