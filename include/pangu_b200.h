@@ -132,6 +132,8 @@ int pangu_mlp_ln_residual_bf16(const void* x, const void* w1, const float* b1, c
 /* Bring-up aid: copies the fused-Mlp kernel's pipeline timeline (clock64 stamps recorded by CTA 0 when
  * $PANGU_MLP_DBG has bit 16 set) to HOST memory `out` (n <= 512 int64).  Synchronises the device. */
 int pangu_debug_mlp_trace(int64_t* out, int32_t n);
+/* Same for the tcgen05 window-attention kernel (CTA (0,0,0), $PANGU_ATTN_DBG != 0): [8 windows][16 stamps]. */
+int pangu_debug_attn_trace(int64_t* out, int32_t n);
 
 /* ------------------------------------------------------------------ 3-D window attention */
 

@@ -49,6 +49,7 @@ _PROTOS = {
                                               c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p]),
     "pangu_mlp_ln_residual_bf16": (c_int, [c_void_p] * 10 + [c_int64, c_int32, c_float, c_void_p]),
     "pangu_debug_mlp_trace": (c_int, [c_void_p, c_int32]),
+    "pangu_debug_attn_trace": (c_int, [c_void_p, c_int32]),
     "pangu_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(Geom), c_int, c_int,
                                        c_void_p]),
     "pangu_window_attention_band": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpangu_b200.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
 SOURCES = ["abi.cu", "index_kernels.cu", "simt_fp32.cu", "layout_kernels.cu", "tc_gemm.cu", "tc_attention.cu",
-           "tc_mlp.cu", "tc_gemm2.cu", "bwd_kernels.cu", "tc_wgrad.cu", "attention_bwd.cu"]
+           "tc_mlp.cu", "tc_gemm2.cu", "bwd_kernels.cu", "tc_wgrad.cu", "attention_bwd.cu", "tc_attention2.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

@@ -51,6 +51,8 @@ int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const vo
                                  int bias_dtype, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
                                  int roll, int prescaled, cudaStream_t st, float* lse = nullptr);
 
+// tc_attention2.cu
+int debug_read_attn_trace(long long* out, int n);
 // attention_bwd.cu
 int launch_window_attention_bwd(const void* qkv, const float* qkv_bias, const void* earth_bias, const void* o,
                                 const void* dout, const float* lse, void* dqkv, float* dbias, float* dpad,
@@ -192,3 +194,5 @@ extern "C" int pangu_window_attention_backward(const void* qkv, const float* qkv
   if (roll < 0 || roll > 2) { set_error("window_attention_backward: roll must be 0, 1 or 2"); return PANGU_ERR_BAD_ARG; }
   return launch_window_attention_bwd(qkv, qkv_bias, earth_bias, out, d_out, lse, d_qkv, d_earth_bias, d_qkv_bias, g, roll, as_stream(stream));
 }
+
+extern "C" int pangu_debug_attn_trace(int64_t* out, int32_t n) { return debug_read_attn_trace(reinterpret_cast<long long*>(out), n); }

@@ -9,6 +9,8 @@
 //
 // Round-1 note: the two small GEMMs (7 % of the model's FLOPs) use warp-level mma.sync fragments so that
 // softmax stays register-resident; the tcgen05/TMEM formulation is the planned upgrade.
+#include <cstdlib>
+
 #include "attn_common.cuh"
 
 namespace pangu {
@@ -285,11 +287,21 @@ static int launch_attn_t(const void* qkv, const void* halo_qkv, const void* halo
   return check_launch("window_attention_bf16");
 }
 
+// tc_attention2.cu: tcgen05 / TMEM formulation (bf16 pre-scaled operands)
+int launch_window_attention_tc(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias,
+                               const void* earth_bias, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
+                               int roll, cudaStream_t st, float* lse);
+
 int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias, const void* earth_bias,
                                  int bias_dtype, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
                                  int roll, int prescaled, cudaStream_t st, float* lse) {
   using namespace attn;
   if (bd.nhw <= 0) return PANGU_OK;
+  {   // pre-scaled bf16 operands: the tcgen05 kernel; $PANGU_B200_ATTN_TC=0 keeps the mma.sync kernel below
+    static const bool use_tc = []() { const char* e = getenv("PANGU_B200_ATTN_TC"); return e == nullptr || atoi(e) != 0; }();
+    if (use_tc && prescaled && bias_dtype == PANGU_BF16)
+      return launch_window_attention_tc(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, st, lse);
+  }
   // longitude windows per CTA (they share the staged bias tile): as many as possible (<= 5) while the grid
   // still fills the GPU for at least ~4 waves of 2 CTAs/SM -- small latitude bands get finer CTAs
   int lon_chunk = 1;

@@ -1,0 +1,717 @@
+// bf16 3-D window attention on the 5th-gen tensor cores (tcgen05 / TMEM / TMA) -- the upgrade of tc_attention.cu
+// (same contract: models/layers.py:422-478 with the block's pad / roll / partition / shift-mask / reverse / crop,
+// :224-293, folded into the addressing; pre-scaled operands).
+//
+// Persistent kernel, one CTA per SM.  The SMs are split into TEAMS of `heads` CTAs: the CTAs of a team walk the same
+// contiguous range of (window type, longitude window) pairs at the same time, one head each, so the 64-byte head slices
+// of a qkv row are fetched together (one 128/256-byte DRAM burst serves the team) and every team gets the same number
+// of windows.  Within a CTA the windows flow through a pipeline:
+//   gather     TMA: a window is 12 runs of 12 longitude-consecutive tokens; one box (32 channels x 12 tokens, or a 3-D
+//              box of 6 latitude rows) per q / k / v lands directly in the UMMA canonical SWIZZLE_64B layout; 6-stage
+//              smem ring; zero-pad rows equal linear1's bias (layers.py:228,419) and are written by the producer warp
+//              only when a stage changes window type
+//   S = Q K^T  tcgen05.mma M=128 N=144 K=32 (K-major operands), fp32 accumulator in TMEM, two S buffers
+//   softmax    TWO groups of 8 warps, group g takes windows i = g (mod 2) so that the MUFU-bound exp phase of one window
+//              overlaps the FMA/ALU-bound max phase of the next.  A thread owns (score row, 80 or 64 keys) and makes
+//              two passes over its TMEM columns in 16-column chunks: max of S + bias (+ mask), then exp2 -> bf16 P
+//              written back over its OWN first columns (tcgen05.st), so no registers hold a whole row.  The bf16 bias
+//              is added with the mixed-precision add (one FHADD.BF16 per score, no unpacking).
+//   O = P V    tcgen05.mma, A = P from TMEM (TS form), B = V from smem (MN-major), N=32 K=144, four O buffers
+//   epilogue   of window i-2 after the softmax of window i: 16 columns per thread -> one 32-byte sector at the
+//              un-rolled token position
+//   rows 128..143  (they do not fit M=128) run on four "tail" warps with mma.sync fragments on the same smem tiles,
+//              one whole window per warp (online softmax over three 48-key blocks, as tc_attention.cu)
+// When the window type changes, the 20 consumer warps swap the bias tile (the producer warp has already pulled it into
+// L2); TMA and MMA keep running ahead meanwhile.
+// Warps (768 threads, 512 TMEM columns): 0-15 softmax, 16 TMA producer, 17 MMA issuer + TMEM allocator, 20-23 tails.
+#include <cstdlib>
+
+#include "attn_common.cuh"
+#include "tc_common.cuh"
+
+namespace pangu {
+namespace attn2 {
+
+using attn::ex2;
+using attn::kBiasPitch;
+using attn::kLog2e;
+using attn::kTileBytes;
+using attn::ldmatrix_x4;
+using attn::ldmatrix_x4_trans;
+using attn::mma_bf16;
+using attn::tile_off;
+using tc::pack_bf16;
+using tc::smem_u32;
+
+constexpr int kSoftmaxWarps = 16;
+constexpr int kTailWarps = 4;
+constexpr int kWarpTma = 16, kWarpMma = 17, kWarpTail0 = 20;     // warps 18, 19 only fill the warpgroup
+constexpr int kThreads = (kWarpTail0 + kTailWarps) * 32;           // 768 = 6 warpgroups
+constexpr int kConsumers = (kSoftmaxWarps + kTailWarps) * 32;      // 640 threads read the bias tile
+constexpr int kStages = 6;
+constexpr int kBiasBytes = 44032;                  // 144 x 152 bf16 = 43 776, padded to a multiple of 1024
+constexpr int kBufBytes = 3 * kTileBytes;          // q, k, v: 27 648 = 27 x 1024
+constexpr int kTmemCols = 512;
+constexpr int kColS = 144;                         // S/P buffer b: columns [144 b, 144 b + 144)
+constexpr int kColO = 288;                         // O buffer k: columns [288 + 32 k, +32), k < 4
+constexpr int kKeys0 = 80;                         // key split between the two threads of a score row: 80 + 64
+constexpr int kRunBytes = 12 * 64;                 // one run of 12 tokens x 32 channels
+constexpr int kBiasTileBytes = kWinTokens * kWinTokens * 2;
+// smem carve-up after the bias tile and the ring
+constexpr int kOffTables = kBiasBytes + kStages * kBufBytes;
+constexpr int kOffExch = kOffTables + 1024;        // [group][slot][max | sum][key half][128] floats
+constexpr int kExchBytes = 2 * 2 * 2 * 2 * 128 * 4;
+constexpr int kOffBars = kOffExch + kExchBytes;
+constexpr int kSmemBytes = kOffBars + 256 + 1024 /*alignment slack*/;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+// K-major operand, 64-byte rows (32 bf16 = the whole K extent), SWIZZLE_64B: 8-row atoms of 512 B.
+__device__ __forceinline__ uint64_t desc_k_sw64(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// MN-major operand (V as stored: [key][d], d contiguous = one 64-byte chunk), SWIZZLE_64B: SBO = 512 B between 8-key groups.
+__device__ __forceinline__ uint64_t desc_mn_sw64(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(512 >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+// tcgen05.wait::ld that also "produces" the 16 registers of the load it completes, so that no use of them can be
+// scheduled above the wait.
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
+// s0 += lo(w), s1 += hi(w) with w = two packed bf16: mixed-precision add (FHADD.BF16 with .H0/.H1 selectors), exact.
+__device__ __forceinline__ void add_bias2(uint32_t w, float& s0, float& s1) {
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t}"
+      : "+f"(s0), "+f"(s1) : "r"(w));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+struct Maps {
+  CUtensorMap own12, own6, hs12, hs6, hn12, hn6;           // qkv / southern halo / northern halo, boxes of 12 and 6 tokens
+  CUtensorMap own3d12;                                     // qkv as [Z*rows][W][3C]: boxes of 6 rows x 12 longitudes
+};
+
+// window type of tile u of this launch (band-local enumeration: u = zw * nhw + local h-window)
+__device__ __forceinline__ int tile_type(const WinGeom& g, const BandGeom& bd, int u) {
+  const int zw = u / bd.nhw, hwl = u - zw * bd.nhw;
+  return zw * g.nH + ((bd.wrap && hwl == bd.nhw - 1) ? g.nH - 1 : bd.hw0 + hwl);
+}
+// run r (= dz * 6 + dh) of window type t: token-row base inside the buffer of its class (0 pad, 1 own, 2 southern halo,
+// 3 northern halo); pad (layers.py:228) + roll (:237) + partition (:253-262) in closed form
+__device__ __forceinline__ void run_info(const WinGeom& g, const BandGeom& bd, int roll, int t, int r, int& rb, int& cls) {
+  const int zw = t / g.nH, hw = t - zw * g.nH;
+  const int dz = r / 6, dh = r - dz * 6;
+  int z = 2 * zw + dz, h = 6 * hw + dh;
+  if (roll == 1) { z += 1; if (z >= g.Z) z -= g.Z; h += 3; if (h >= g.Hp) h -= g.Hp; }
+  rb = -1; cls = 0;
+  if (roll == 2) { rb = t * kWinTokens + 12 * r; cls = 1; }
+  else if (h < g.H) {
+    const int hl = h - bd.h0;
+    if (hl >= 0 && hl < bd.hrows) { rb = (z * bd.hrows + hl) * g.W; cls = 1; }
+    else if (hl >= bd.hrows && hl < bd.hrows + bd.halo) { rb = (z * bd.halo + (hl - bd.hrows)) * g.W; cls = 2; }
+    else if (hl < 0 && hl >= -bd.halo_lo) { rb = (z * bd.halo_lo + (hl + bd.halo_lo)) * g.W; cls = 3; }
+  }
+}
+__device__ __forceinline__ long long run_token(const WinGeom& g, int roll, int l, int rb, int dw) {
+  if (roll == 2) return (long long)l * g.T * kWinTokens + rb + dw;
+  int w = 12 * l + (roll == 1 ? 6 : 0) + dw;
+  if (w >= g.W) w -= g.W;
+  return (long long)rb + w;
+}
+
+// Bring-up aid: clock64 stamps of CTA 0 for its first windows (slot = window & 7), when $PANGU_ATTN_DBG is set.
+// [slot][16]: 0 TMA issued, 1 S issued, 2 p_full passed, 3 PV issued (warps 16/17); 4 s_full passed, 5 max pass done,
+// 6 max exchanged, 7 P stored, 8 epilogue(i-2) done (first warp of the window's softmax group); 10 start, 11 end (tail
+// warp); 12 / 13 bias swap start / end (warp 0)
+__device__ long long g_attn_trace[8 * 16];
+
+__global__ void __launch_bounds__(kThreads, 1)
+window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __restrict__ qkv_bias,
+                           const __nv_bfloat16* __restrict__ earth_bias, __nv_bfloat16* __restrict__ out,
+                           __nv_bfloat16* __restrict__ halo_out, WinGeom g, BandGeom bd, int roll,
+                           float* __restrict__ lse, int dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(smem);                       // [144][152]
+  uint8_t* s_buf = smem + kBiasBytes;                                                   // kStages x {q,k,v}
+  // consumer-side tables of the current bias tile's window type
+  int* s_crun = reinterpret_cast<int*>(smem + kOffTables);                              // [12] run base
+  int* s_ccls = s_crun + 12;                                                            // [12] run class
+  // producer-private tables
+  int* s_prun = reinterpret_cast<int*>(smem + kOffTables + 384);                        // [12]
+  int* s_pcls = s_prun + 12;                                                            // [12]
+  int* s_stage_u = s_pcls + 12;                                                         // [kStages] tile whose pad rows the stage holds
+  uint4* s_padvals = reinterpret_cast<uint4*>(smem + kOffTables + 512);                 // [3 tensors][4 chunks] linear1 bias, bf16
+  float* s_exch = reinterpret_cast<float*>(smem + kOffExch);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+  uint64_t* full = bars;                 // [6] TMA -> MMA / tail warp (tx bytes)
+  uint64_t* empty = bars + 6;            // [6] 1 (tcgen05.commit after PV) + 1 (tail warp)
+  uint64_t* s_full = bars + 12;          // [2] S(i) complete in S buffer i & 1
+  uint64_t* p_full = bars + 14;          // [2] P(i) written (8 warps)
+  uint64_t* o_full = bars + 16;          // [4] O(i) complete in O buffer i & 3
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = g.C;
+  const int head = blockIdx.x % g.heads, team = blockIdx.x / g.heads, nteams = gridDim.x / g.heads;
+  const long long npairs = (long long)g.nZ * bd.nhw * g.nLon;
+  const int p0 = (int)(npairs * team / nteams), p1 = (int)(npairs * (team + 1) / nteams);
+  const int nwin = p1 - p0;
+  if (nwin <= 0) return;
+  const int u0 = p0 / g.nLon, last_ts = (p1 - 1) / g.nLon - u0;
+
+  // cooperative load of bias tile + tables of tile u by the consumer threads (ctid = index among them); the caller
+  // commits / waits the cp.async group and synchronises
+  auto load_tile = [&](int u, int ctid) {
+    const int t = tile_type(g, bd, u);
+    const __nv_bfloat16* src = earth_bias + ((long long)t * g.heads + head) * kWinTokens * kWinTokens;
+    for (int i = ctid; i < kWinTokens * 18; i += kConsumers) {
+      const int r = i / 18, c = i - r * 18;
+      attn::cp_async16(attn::smem_u32(s_bias + r * kBiasPitch + c * 8), src + r * kWinTokens + c * 8);
+    }
+    attn::cp_async_commit();
+    if (ctid >= 32 && ctid < 44) {
+      int rb, cls;
+      run_info(g, bd, roll, t, ctid - 32, rb, cls);
+      s_crun[ctid - 32] = rb;
+      s_ccls[ctid - 32] = cls;
+    }
+  };
+  // The shift mask (gen_mask, layers.py:187-216: -100 where the region ids of query and key differ) of a masked window
+  // type is folded into the staged bias tile, so the softmax loops never see it: every thread patches the 16-byte
+  // chunks it fetched itself, after its cp.async group has landed.  (bias - 144.27 rounds to about -144 in bf16: the
+  // probability underflows to 0 either way, as exp(-100 + s) does in the reference's fp32.)
+  auto patch_tile = [&](int u, int ctid) {
+    const int t = tile_type(g, bd, u);
+    const int zw = t / g.nH, hw = t - zw * g.nH;
+    if (roll != 1 || (zw != g.nZ - 1 && hw != g.nH - 1)) return;
+    auto rgroup = [&](int r) { return (zw == g.nZ - 1 ? 2 * (r / 6) : 0) + ((hw == g.nH - 1 && (r % 6) >= 3) ? 1 : 0); };
+    const float mask_l2 = kMaskValue * kLog2e;
+    for (int i = ctid; i < kWinTokens * 18; i += kConsumers) {
+      const int r = i / 18, c = i - r * 18;
+      const int gr = rgroup(r / 12);
+      const int g_first = rgroup((8 * c) / 12), g_last = rgroup((8 * c + 7) / 12);
+      if (g_first == gr && g_last == gr) continue;
+      __nv_bfloat16* ptr = s_bias + r * kBiasPitch + c * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (rgroup((8 * c + e) / 12) != gr) ptr[e] = __float2bfloat16_rn(__bfloat162float(ptr[e]) + mask_l2);
+    }
+  };
+  const bool is_consumer = warp < kSoftmaxWarps || warp >= kWarpTail0;
+  const int ctid = warp < kSoftmaxWarps ? tid : tid - (kWarpTail0 - kSoftmaxWarps) * 32;
+  auto swap_tile = [&](int ts) {                              // all consumer threads, in lock step per tile
+    named_bar(9, kConsumers);                                 // everybody has finished with the old tile
+    load_tile(u0 + ts, ctid);
+    attn::cp_async_wait<0>();
+    patch_tile(u0 + ts, ctid);
+    named_bar(9, kConsumers);
+  };
+
+  // ---- prologue
+  if (is_consumer) load_tile(u0, ctid);
+  if (warp == kWarpMma && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 2); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 8); }
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&o_full[i], 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == kWarpTma) {
+    if (lane == 0) { tc::tma_prefetch_desc(&maps.own12); tc::tma_prefetch_desc(&maps.own3d12); }
+    if (lane < 12) {                                          // pad-row values: (tensor s, 16-byte chunk c) of this head
+      const int s = lane >> 2, c = lane & 3;
+      const float* bsrc = qkv_bias + s * C + head * kHeadDim + c * 8;
+      uint4 o;
+      o.x = pack_bf16(bsrc[0], bsrc[1]); o.y = pack_bf16(bsrc[2], bsrc[3]);
+      o.z = pack_bf16(bsrc[4], bsrc[5]); o.w = pack_bf16(bsrc[6], bsrc[7]);
+      s_padvals[lane] = o;
+    }
+    if (lane < kStages) s_stage_u[lane] = -1;
+  }
+  if (warp == kWarpMma) tc::tmem_alloc(tmem_slot, kTmemCols);
+  tc::tcgen05_before_sync();
+  __syncthreads();
+  tc::tcgen05_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  if (is_consumer) {
+    attn::cp_async_wait<0>();
+    patch_tile(u0, ctid);
+    named_bar(9, kConsumers);
+  }
+
+  const bool trc = dbg && blockIdx.x == 0 && lane == 0;
+
+  // Register budget per warpgroup (768 threads start with 80 each, and that total is the pool): the TMA / MMA group
+  // shrinks to 56 so that the tail group -- whole mma.sync windows in registers -- can grow to 104.
+  // (the instruction sits at the top of each role branch so that ptxas budgets the branch accordingly)
+  if (warp >= kSoftmaxWarps && warp < kWarpTail0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");      // all four warps of the group, converged
+  if (warp == kWarpTma) {
+    // ==================================================================== TMA producer
+    int cur_u = -1, real_runs = 0;
+    bool box3d[2] = {false, false};
+    for (int i = 0; i < nwin; ++i) {
+      const int p = p0 + i, u = p / g.nLon, l = p - u * g.nLon;
+      const int st = i % kStages;
+      if (u != cur_u) {
+        cur_u = u;
+        const int t = tile_type(g, bd, u);
+        __syncwarp();
+        if (lane < 12) {
+          int rb, cls;
+          run_info(g, bd, roll, t, lane, rb, cls);
+          s_prun[lane] = rb;
+          s_pcls[lane] = cls;
+        }
+        __syncwarp();
+        real_runs = 0;
+        for (int r = 0; r < 12; ++r) real_runs += s_pcls[r] != 0;
+        // a half window (fixed dz: 6 latitude rows x 12 longitudes) whose rows are consecutive own rows is ONE 3-D box
+        // per tensor; otherwise (pad rows, halo rows, the latitude wrap) its runs are fetched one by one
+#pragma unroll
+        for (int dz = 0; dz < 2; ++dz) {
+          bool ok = roll != 2;
+          for (int dh = 0; dh < 6; ++dh) {
+            ok = ok && s_pcls[dz * 6 + dh] == 1;
+            if (dh > 0) ok = ok && s_prun[dz * 6 + dh] - s_prun[dz * 6 + dh - 1] == g.W;
+          }
+          box3d[dz] = ok;
+        }
+        if (u - u0 < last_ts && lane == 0) {                  // pull the next bias tile into L2 ahead of the swap
+          const int tn = tile_type(g, bd, u + 1);
+          prefetch_l2_bulk(earth_bias + ((long long)tn * g.heads + head) * kWinTokens * kWinTokens, kBiasTileBytes);
+        }
+      }
+      tc::mbar_wait(&empty[st], ((i / kStages) & 1) ^ 1);
+      if (real_runs < 12 && s_stage_u[st] != u) {             // pad rows of this window type into the stage
+        for (int r = 0; r < 12; ++r) {
+          if (s_pcls[r] != 0) continue;
+          for (int j = lane; j < 144; j += 32) {
+            const int k = r * 12 + j / 12, part = j % 12, s = part >> 2, c = part & 3;
+            *reinterpret_cast<uint4*>(s_buf + st * kBufBytes + s * kTileBytes + tile_off(k, c)) = s_padvals[part];
+          }
+        }
+        tc::fence_async_smem();                               // generic-proxy writes -> visible to the tensor core
+      }
+      __syncwarp();
+      if (lane == 0) {
+        s_stage_u[st] = u;
+        tc::mbar_expect_tx(&full[st], real_runs * 3 * kRunBytes);
+      }
+      __syncwarp();
+      const int w = 12 * l + (roll == 1 ? 6 : 0);
+      if (lane < 6) {                                         // (dz, tensor) pairs
+        const int dz = lane / 3, s = lane - dz * 3;
+        if (box3d[dz] && w + 12 <= g.W) {
+          const int row = s_prun[dz * 6] / g.W;
+          uint8_t* dst = s_buf + st * kBufBytes + s * kTileBytes + dz * 6 * kRunBytes;
+          tc::tma_load_3d(dst, &maps.own3d12, &full[st], s * C + head * kHeadDim, w, row);
+        }
+      }
+      for (int j = lane; j < 36; j += 32) {                   // (run, tensor) pairs of the half windows fetched run by run
+        const int r = j / 3, s = j - r * 3;
+        const int cls = s_pcls[r];
+        if (cls == 0 || (box3d[r / 6] && w + 12 <= g.W)) continue;
+        const int rb = s_prun[r];
+        uint8_t* dst = s_buf + st * kBufBytes + s * kTileBytes + r * kRunBytes;
+        const int c0 = s * C + head * kHeadDim;
+        if (roll == 2) {
+          tc::tma_load_2d(dst, &maps.own12, &full[st], c0, l * g.T * kWinTokens + rb);
+        } else if (w + 12 <= g.W) {
+          const CUtensorMap* m = cls == 1 ? &maps.own12 : (cls == 2 ? &maps.hs12 : &maps.hn12);
+          tc::tma_load_2d(dst, m, &full[st], c0, rb + w);
+        } else {                                              // last window of a rolled block: longitudes W-6..W-1, then 0..5
+          const CUtensorMap* m = cls == 1 ? &maps.own6 : (cls == 2 ? &maps.hs6 : &maps.hn6);
+          tc::tma_load_2d(dst, m, &full[st], c0, rb + w);
+          tc::tma_load_2d(dst + 6 * 64, m, &full[st], c0, rb);
+        }
+      }
+      __syncwarp();
+      if (trc) g_attn_trace[(i & 7) * 16 + 0] = clock64();
+    }
+  } else if (warp == kWarpMma) {
+    // ==================================================================== MMA issuer
+    constexpr uint32_t idesc_s = tc::make_idesc_bf16(128, 144, 0, 0);
+    constexpr uint32_t idesc_o = tc::make_idesc_bf16(128, 32, 0, 1);
+    auto issue_pv = [&](int i) {
+      const int st = i % kStages, sb = i & 1, ob = i & 3;
+      tc::mbar_wait(&p_full[sb], (i >> 1) & 1);
+      tc::tcgen05_after_sync();
+      if (trc) g_attn_trace[(i & 7) * 16 + 2] = clock64();
+      const uint32_t av = smem_u32(s_buf + st * kBufBytes + 2 * kTileBytes);
+      const uint32_t tP = tmem_base + sb * kColS, tO = tmem_base + kColO + 32 * ob;
+#pragma unroll
+      for (int k = 0; k < 9; ++k)                            // K = 144 keys: 16 keys = 8 packed TMEM columns / 1 KiB of V per step
+        if (tc::elect_one())                                 // P of keys 0..79 at columns [0,40), of keys 80..143 at [80,112)
+          tc::umma_bf16_ts(tO, tP + 8 * k + (k >= 5 ? 40 : 0), desc_mn_sw64(av + 1024 * k), idesc_o, k);
+      if (tc::elect_one()) { tc::umma_commit(&o_full[ob]); tc::umma_commit(&empty[st]); }
+      __syncwarp();
+      if (trc) g_attn_trace[(i & 7) * 16 + 3] = clock64();
+    };
+    // The tensor pipe executes in issue order: S(i) may overwrite S buffer i & 1 as soon as PV(i-2) has been ISSUED
+    // (softmax(i-2) is done with it by then: p_full), and PV(i) may overwrite O buffer i & 3 because the epilogue of
+    // window i-4 ran before its group arrived on p_full(i-2).
+    for (int i = 0; i < nwin; ++i) {
+      const int st = i % kStages, sb = i & 1;
+      tc::mbar_wait(&full[st], (i / kStages) & 1);
+      tc::tcgen05_after_sync();
+      const uint32_t aq = smem_u32(s_buf + st * kBufBytes), ak = aq + kTileBytes;
+#pragma unroll
+      for (int k = 0; k < 2; ++k)                            // K = 32: two 16-element steps, +32 B inside the 64 B swizzle span
+        if (tc::elect_one()) tc::umma_bf16(tmem_base + sb * kColS, desc_k_sw64(aq) + 2 * k, desc_k_sw64(ak) + 2 * k, idesc_s, k);
+      if (tc::elect_one()) tc::umma_commit(&s_full[sb]);
+      __syncwarp();
+      if (trc) g_attn_trace[(i & 7) * 16 + 1] = clock64();
+      if (i > 0) issue_pv(i - 1);
+    }
+    issue_pv(nwin - 1);
+  }
+  } else if (warp < kSoftmaxWarps) {
+    // ==================================================================== softmax: thread = (score row, 80 or 64 keys)
+    const int grp = warp >> 3, q = warp & 3, hf = (warp >> 2) & 1;
+    const int row = q * 32 + lane;
+    const int k0 = hf * kKeys0, nchunk = hf ? 4 : 5;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + grp * kColS + k0;
+    const uint32_t brow = smem_u32(s_bias + row * kBiasPitch + k0);
+    const uint32_t exg = smem_u32(s_exch + grp * 1024);       // [slot][max | sum][half][128] floats
+    const int rrun = row / 12, rdw = row - rrun * 12;
+    const bool trw = trc && (warp & 7) == 0;
+
+    int cur_ts = 0, cur_u = -1, t = 0;
+    int rcls = 0, rrb = -1;
+    __nv_bfloat16* dst_prev = nullptr;
+    float* lse_prev = nullptr;
+    float m_prev = 0.f;
+
+    auto epilogue = [&](int i, __nv_bfloat16* dst, float* lsep, float m) {
+      const int ob = i & 3, slot = (i >> 1) & 1;
+      tc::mbar_wait(&o_full[ob], (i >> 2) & 1);
+      tc::tcgen05_after_sync();
+      uint32_t o[16];
+      tc::tmem_ld_32x16(tmem_base + lane_addr + kColO + 32 * ob + hf * 16, o);
+      const uint32_t exs = exg + (slot * 512 + 256 + row) * 4;
+      const float sum = lds_f32(exs) + lds_f32(exs + 512);
+      const float inv = 1.0f / sum;
+      tmem_ld_wait16(o);
+      if (dst != nullptr) {
+        uint4 a, b;
+        a.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
+        a.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
+        a.z = pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
+        a.w = pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
+        b.x = pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+        b.y = pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+        b.z = pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+        b.w = pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+        uint4* d = reinterpret_cast<uint4*>(dst);
+        d[0] = a; d[1] = b;
+      }
+      if (lsep != nullptr) *lsep = m + log2f(sum);
+    };
+
+    for (int i = grp; i < nwin; i += 2) {
+      const int p = p0 + i, u = p / g.nLon, l = p - u * g.nLon;
+      const int slot = (i >> 1) & 1;
+      long long* tr = g_attn_trace + (i & 7) * 16;
+      while (cur_ts < u - u0) {
+        if (trc && warp == 0) g_attn_trace[12] = clock64();
+        swap_tile(++cur_ts);
+        if (trc && warp == 0) g_attn_trace[13] = clock64();
+      }
+      if (u != cur_u) {
+        cur_u = u;
+        t = tile_type(g, bd, u);
+        run_info(g, bd, roll, t, rrun, rrb, rcls);
+      }
+      __nv_bfloat16* dst_base = rcls == 1 ? out : (rcls == 2 ? halo_out : nullptr);
+      __nv_bfloat16* dst_cur = dst_base == nullptr ? nullptr
+                               : dst_base + run_token(g, roll, l, rrb, rdw) * C + head * kHeadDim + hf * 16;
+      float* lse_cur = (lse != nullptr && hf == 0) ? lse + (((long long)l * g.T + t) * g.heads + head) * kWinTokens + row : nullptr;
+
+      tc::mbar_wait(&s_full[grp], (i >> 1) & 1);
+      tc::tcgen05_after_sync();
+      if (trw) tr[4] = clock64();
+      const uint32_t exm = exg + slot * 2048, exs = exm + 1024;
+      float m;
+      {
+        // ---- pass 1: maximum of S + bias over my keys (a shift mask is part of the staged bias)
+        uint32_t va[16], vb[16];
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        tc::tmem_ld_32x16(tS, va);
+        tmem_ld_wait16(va);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          if (c < nchunk) {
+            uint32_t (&cur)[16] = (c & 1) ? vb : va;
+            uint32_t (&nxt)[16] = (c & 1) ? va : vb;
+            if (c + 1 < nchunk) tc::tmem_ld_32x16(tS + 16 * (c + 1), nxt);
+            const uint4 b0 = lds128(brow + 32 * c), b1 = lds128(brow + 32 * c + 16);
+            const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float s0 = __uint_as_float(cur[2 * e]), s1 = __uint_as_float(cur[2 * e + 1]);
+              add_bias2(bw[e], s0, s1);
+              mx0 = fmaxf(mx0, s0);
+              mx1 = fmaxf(mx1, s1);
+            }
+            if (c + 1 < nchunk) tmem_ld_wait16(nxt);
+          }
+        }
+        if (trw) tr[5] = clock64();
+        m = fmaxf(mx0, mx1);
+        sts_f32(exm + (hf * 128 + row) * 4, m);
+        tc::tmem_ld_32x16(tS, va);                            // first chunk of pass 2 flies during the exchange
+        named_bar(1 + grp * 4 + q, 64);                       // the two warps of this lane quarter
+        m = fmaxf(m, lds_f32(exm + ((hf ^ 1) * 128 + row) * 4));
+        tmem_ld_wait16(va);
+        if (trw) tr[6] = clock64();
+        // ---- pass 2: P = exp2(S + bias - m) -> bf16, packed over my own first columns; row sum
+        float sm0 = 0.f, sm1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          if (c < nchunk) {
+            uint32_t (&cur)[16] = (c & 1) ? vb : va;
+            uint32_t (&nxt)[16] = (c & 1) ? va : vb;
+            if (c + 1 < nchunk) tc::tmem_ld_32x16(tS + 16 * (c + 1), nxt);
+            const uint4 b0 = lds128(brow + 32 * c), b1 = lds128(brow + 32 * c + 16);
+            const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint32_t pk[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float s0 = __uint_as_float(cur[2 * e]), s1 = __uint_as_float(cur[2 * e + 1]);
+              add_bias2(bw[e], s0, s1);
+              const float e0 = ex2(s0 - m), e1 = ex2(s1 - m);
+              sm0 += e0;
+              sm1 += e1;
+              pk[e] = pack_bf16(e0, e1);
+            }
+            tmem_st_32x8(tS + 8 * c, pk);
+            if (c + 1 < nchunk) tmem_ld_wait16(nxt);
+          }
+        }
+        sts_f32(exs + (hf * 128 + row) * 4, sm0 + sm1);
+      }
+      tc::tmem_st_wait();
+      tc::tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&p_full[grp]);
+      if (trw) tr[7] = clock64();
+      if (i >= 2) epilogue(i - 2, dst_prev, lse_prev, m_prev);
+      dst_prev = dst_cur; lse_prev = lse_cur; m_prev = m;
+      if (trw) tr[8] = clock64();
+    }
+    {
+      const int cnt = nwin > grp ? (nwin - grp + 1) / 2 : 0;  // windows of this group
+      if (cnt > 0) epilogue(grp + 2 * (cnt - 1), dst_prev, lse_prev, m_prev);
+    }
+    while (cur_ts < last_ts) swap_tile(++cur_ts);
+  } else {
+    // ==================================================================== tail warps: rows 128..143 of window i = j (mod 4)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    constexpr int row0 = 128;
+    const int jt = warp - kWarpTail0;
+    const int gq = lane >> 2, tq = lane & 3, mi = lane >> 3, mr = lane & 7;
+    int cur_ts = 0;
+    for (int i = jt; i < nwin; i += kTailWarps) {
+      const int p = p0 + i, u = p / g.nLon, l = p - u * g.nLon;
+      const int st = i % kStages;
+      while (cur_ts < u - u0) swap_tile(++cur_ts);
+      const int t = tile_type(g, bd, u);
+      uint8_t* sq = s_buf + st * kBufBytes;
+      uint8_t* sk = sq + kTileBytes;
+      uint8_t* sv = sk + kTileBytes;
+      tc::mbar_wait(&full[st], (i / kStages) & 1);
+      if (trc) g_attn_trace[(i & 7) * 16 + 10] = clock64();
+      uint32_t qa[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const int r = row0 + (mi & 1) * 8 + mr, c = ks * 2 + (mi >> 1);
+        ldmatrix_x4(attn::smem_u32(sq + tile_off(r, c)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
+      }
+      float o_acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o_acc[a][c] = 0.f;
+      float m_lo = -INFINITY, m_hi = -INFINITY;
+      float l_acc[4] = {0.f, 0.f, 0.f, 0.f};                  // row sums of the bf16 P, from a ones-column MMA
+#pragma unroll 1
+      for (int kv0 = 0; kv0 < kWinTokens; kv0 += 48) {
+        float s_acc[6][4];
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {                      // accumulate on top of the (pre-scaled) bias
+          const int j = kv0 + nt * 8 + 2 * tq;
+          const __nv_bfloat162 b_lo = *reinterpret_cast<const __nv_bfloat162*>(s_bias + (row0 + gq) * kBiasPitch + j);
+          const __nv_bfloat162 b_hi = *reinterpret_cast<const __nv_bfloat162*>(s_bias + (row0 + gq + 8) * kBiasPitch + j);
+          s_acc[nt][0] = __low2float(b_lo); s_acc[nt][1] = __high2float(b_lo);
+          s_acc[nt][2] = __low2float(b_hi); s_acc[nt][3] = __high2float(b_hi);
+          uint32_t k0r, k1r, k2r, k3r;
+          ldmatrix_x4(attn::smem_u32(sk + tile_off(kv0 + nt * 8 + mr, mi)), k0r, k1r, k2r, k3r);
+          mma_bf16(s_acc[nt], qa[0], k0r, k1r);
+          mma_bf16(s_acc[nt], qa[1], k2r, k3r);
+        }
+        float mx_lo = m_lo, mx_hi = m_hi;
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+          mx_lo = fmaxf(mx_lo, fmaxf(s_acc[nt][0], s_acc[nt][1]));
+          mx_hi = fmaxf(mx_hi, fmaxf(s_acc[nt][2], s_acc[nt][3]));
+        }
+        mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+        mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+        mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+        mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+        const float a_lo = ex2(m_lo - mx_lo), a_hi = ex2(m_hi - mx_hi);     // 0 on the first block (m = -inf)
+        m_lo = mx_lo; m_hi = mx_hi;
+        l_acc[0] *= a_lo; l_acc[2] *= a_hi;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { o_acc[nt][0] *= a_lo; o_acc[nt][1] *= a_lo; o_acc[nt][2] *= a_hi; o_acc[nt][3] *= a_hi; }
+        uint32_t pa[3][4];
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) {
+          const float e0 = ex2(s_acc[nt][0] - m_lo), e1 = ex2(s_acc[nt][1] - m_lo);
+          const float e2 = ex2(s_acc[nt][2] - m_hi), e3 = ex2(s_acc[nt][3] - m_hi);
+          pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(e0, e1);
+          pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(e2, e3);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {
+          mma_bf16(l_acc, pa[kk], 0x3F803F80u, 0x3F803F80u);
+#pragma unroll
+          for (int dp = 0; dp < 2; ++dp) {
+            uint32_t v0, v1, v2, v3;
+            const int r = kv0 + kk * 16 + (mi & 1) * 8 + mr, c = dp * 2 + (mi >> 1);
+            ldmatrix_x4_trans(attn::smem_u32(sv + tile_off(r, c)), v0, v1, v2, v3);
+            mma_bf16(o_acc[dp * 2], pa[kk], v0, v1);
+            mma_bf16(o_acc[dp * 2 + 1], pa[kk], v2, v3);
+          }
+        }
+      }
+      const float inv_lo = 1.0f / l_acc[0], inv_hi = 1.0f / l_acc[2];
+      if (lse != nullptr && tq == 0) {
+        float* L = lse + (((long long)l * g.T + t) * g.heads + head) * kWinTokens + row0 + gq;
+        L[0] = m_lo + log2f(l_acc[0]);
+        L[8] = m_hi + log2f(l_acc[2]);
+      }
+      // rows 128..143 of the Q tile are outside the tensor core's M = 128 and only read by this warp (done): stage O
+      // there, then 64-byte coalesced row stores
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        *reinterpret_cast<uint32_t*>(sq + tile_off(row0 + gq, nt) + 4 * tq) = pack_bf16(o_acc[nt][0] * inv_lo, o_acc[nt][1] * inv_lo);
+        *reinterpret_cast<uint32_t*>(sq + tile_off(row0 + gq + 8, nt) + 4 * tq) = pack_bf16(o_acc[nt][2] * inv_hi, o_acc[nt][3] * inv_hi);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int idx = lane + it * 32, r = row0 + (idx >> 2), c = idx & 3;
+        const int rr = r / 12, dw = r - rr * 12;
+        const int cls = s_ccls[rr], rb = s_crun[rr];
+        __nv_bfloat16* dstp = cls == 1 ? out : (cls == 2 ? halo_out : nullptr);
+        if (dstp != nullptr) {
+          const uint4 val = *reinterpret_cast<const uint4*>(sq + tile_off(r, c));
+          *reinterpret_cast<uint4*>(dstp + run_token(g, roll, l, rb, dw) * C + head * kHeadDim + c * 8) = val;
+        }
+      }
+      __syncwarp();
+      // the staged rows were written through the generic proxy; the next TMA into this slot writes through the async proxy
+      tc::fence_async_smem();
+      if (lane == 0) tc::mbar_arrive(&empty[st]);
+      if (trc) g_attn_trace[(i & 7) * 16 + 11] = clock64();
+    }
+    while (cur_ts < last_ts) swap_tile(++cur_ts);
+  }
+  tc::tcgen05_before_sync();
+  __syncthreads();
+  tc::tcgen05_after_sync();
+  if (warp == kWarpMma) tc::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace attn2
+
+int debug_read_attn_trace(long long* out, int n) {
+  if (n > 8 * 16) n = 8 * 16;
+  cudaError_t e = cudaMemcpyFromSymbol(out, attn2::g_attn_trace, sizeof(long long) * n);
+  if (e != cudaSuccess) { set_error("debug_read_attn_trace: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
+  return PANGU_OK;
+}
+
+namespace tc { int num_sms(); }
+
+int launch_window_attention_tc(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias,
+                               const void* earth_bias, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
+                               int roll, cudaStream_t st, float* lse) {
+  using namespace attn2;
+  if (bd.nhw <= 0) return PANGU_OK;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { set_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
+    configured = true;
+  }
+  // token rows of the three tensors
+  const uint64_t own_rows = roll == 2 ? (uint64_t)g.nLon * g.T * kWinTokens : (uint64_t)g.Z * bd.hrows * g.W;
+  const uint64_t pitch = (uint64_t)3 * g.C * 2;
+  Maps maps;
+  auto enc = [&](CUtensorMap* m12, CUtensorMap* m6, const void* p, uint64_t rows) -> bool {
+    return tc::encode_tmap_2d(m12, 1, p, (uint64_t)3 * g.C, rows, pitch, 32, 12, 64) &&
+           tc::encode_tmap_2d(m6, 1, p, (uint64_t)3 * g.C, rows, pitch, 32, 6, 64);
+  };
+  if (!enc(&maps.own12, &maps.own6, qkv, own_rows)) return PANGU_ERR_CUDA;
+  maps.hs12 = maps.own12; maps.hs6 = maps.own6; maps.hn12 = maps.own12; maps.hn6 = maps.own6;
+  {   // [Z * rows][W][3C] view of the own rows (not meaningful for pre-partitioned windows, where it is never used)
+    const uint64_t rows3 = roll == 2 ? 1 : (uint64_t)g.Z * bd.hrows, W3 = roll == 2 ? 12 : (uint64_t)g.W;
+    if (!tc::encode_tmap_3d_bf16(&maps.own3d12, qkv, (uint64_t)3 * g.C, W3, rows3, pitch, pitch * W3, 32, 12, 6, 64)) return PANGU_ERR_CUDA;
+  }
+  if (bd.halo > 0 && !enc(&maps.hs12, &maps.hs6, halo_qkv, (uint64_t)g.Z * bd.halo * g.W)) return PANGU_ERR_CUDA;
+  if (bd.halo_lo > 0 && !enc(&maps.hn12, &maps.hn6, halo_lo_qkv, (uint64_t)g.Z * bd.halo_lo * g.W)) return PANGU_ERR_CUDA;
+  // teams of `heads` CTAs share a range of (window type, longitude window) pairs
+  if (g.heads > tc::num_sms()) { set_error("attention_tc: more heads (%d) than SMs", g.heads); return PANGU_ERR_BAD_ARG; }
+  const long long npairs = (long long)g.nZ * bd.nhw * g.nLon;
+  long long nteams = tc::num_sms() / g.heads;
+  static const int forced = []() { const char* e = getenv("PANGU_ATTN_TEAMS"); return e ? atoi(e) : 0; }();
+  if (forced > 0 && forced < nteams) nteams = forced;
+  if (nteams > npairs) nteams = npairs;
+  static const int dbg = []() { const char* e = getenv("PANGU_ATTN_DBG"); return e ? atoi(e) : 0; }();
+  window_attention_tc_kernel<<<(unsigned)(nteams * g.heads), kThreads, kSmemBytes, st>>>(
+      maps, qkv_bias, (const __nv_bfloat16*)earth_bias, (__nv_bfloat16*)out, (__nv_bfloat16*)halo_out, g, bd, roll, lse, dbg);
+  return check_launch("window_attention_tc");
+}
+
+}  // namespace pangu

@@ -79,6 +79,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 3-D tiled load: c0 = innermost coordinate.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // 2-D tiled store smem -> global (bulk async group of the issuing thread); rows/cols outside the tensor are clipped.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -269,6 +277,9 @@ bool encode_tmap_2d_bf16(CUtensorMap* map, const void* gptr, uint64_t inner, uin
 // must not exceed the swizzle span
 bool encode_tmap_2d(CUtensorMap* map, int is_bf16, const void* gptr, uint64_t inner, uint64_t rows,
                     uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_rows, int swizzle_bytes);
+
+bool encode_tmap_3d_bf16(CUtensorMap* map, const void* gptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                         uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes);
 
 int num_sms();
 

@@ -340,6 +340,32 @@ bool encode_tmap_2d(CUtensorMap* map, int is_bf16, const void* gptr, uint64_t in
   return true;
 }
 
+// 3-D bf16 tiled map: dims {d0 (contiguous), d1, d2}, strides in bytes for d1 / d2.
+bool encode_tmap_3d_bf16(CUtensorMap* map, const void* gptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                         uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2, int swizzle_bytes) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  if (!fn) return false;
+  if ((reinterpret_cast<uintptr_t>(gptr) & 15) || (stride1_bytes & 15) || (stride2_bytes & 15)) {
+    set_error("TMA operand must be 16-byte aligned with 16-byte-multiple strides");
+    return false;
+  }
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstride[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                               : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(gptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed with CUresult %d (dims %llu x %llu x %llu, box %u x %u x %u)", (int)r,
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, b0, b1, b2);
+    return false;
+  }
+  return true;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {
