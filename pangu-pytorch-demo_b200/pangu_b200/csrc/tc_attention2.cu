@@ -10,20 +10,21 @@
 //              box of 6 latitude rows) per q / k / v lands directly in the UMMA canonical SWIZZLE_64B layout; 6-stage
 //              smem ring; zero-pad rows equal linear1's bias (layers.py:228,419) and are written by the producer warp
 //              only when a stage changes window type
-//   S = Q K^T  tcgen05.mma M=128 N=144 K=32 (K-major operands), fp32 accumulator in TMEM, two S buffers
+//   S = Q K^T  tcgen05.mma M=128 N=144 K=32 (K-major operands), fp32 accumulator in TMEM
 //   softmax    TWO groups of 8 warps, group g takes windows i = g (mod 2) so that the MUFU-bound exp phase of one window
 //              overlaps the FMA/ALU-bound max phase of the next.  A thread owns (score row, 80 or 64 keys) and makes
 //              two passes over its TMEM columns in 16-column chunks: max of S + bias (+ mask), then exp2 -> bf16 P
 //              written back over its OWN first columns (tcgen05.st), so no registers hold a whole row.  The bf16 bias
 //              is added with the mixed-precision add (one FHADD.BF16 per score, no unpacking).
-//   O = P V    tcgen05.mma, A = P from TMEM (TS form), B = V from smem (MN-major), N=32 K=144, four O buffers
-//   epilogue   of window i-2 after the softmax of window i: 16 columns per thread -> one 32-byte sector at the
-//              un-rolled token position
+//   O = P V    tcgen05.mma, A = P from TMEM (TS form), B = V from smem (MN-major), N=32 K=144; O(i) lands in the dead
+//              score columns of its own buffer; three S/P/O buffers, so S(i+1) never queues behind PV(i)
+//   epilogue   of window i-2 between the two passes of window i (it fills the wait for the partner's row maximum):
+//              16 columns per thread -> one 32-byte sector at the un-rolled token position
 //   rows 128..143  (they do not fit M=128) run on four "tail" warps with mma.sync fragments on the same smem tiles,
 //              one whole window per warp (online softmax over three 48-key blocks, as tc_attention.cu)
 // When the window type changes, the 20 consumer warps swap the bias tile (the producer warp has already pulled it into
 // L2); TMA and MMA keep running ahead meanwhile.
-// Warps (768 threads, 512 TMEM columns): 0-15 softmax, 16 TMA producer, 17 MMA issuer + TMEM allocator, 20-23 tails.
+// Warps (768 threads, 512 TMEM columns): 0-15 softmax, 16 TMA producer, 17 S-MMA issuer + TMEM allocator, 18 PV-MMA issuer, 20-23 tails.
 #include <cstdlib>
 
 #include "attn_common.cuh"
@@ -45,15 +46,20 @@ using tc::smem_u32;
 
 constexpr int kSoftmaxWarps = 16;
 constexpr int kTailWarps = 4;
-constexpr int kWarpTma = 16, kWarpMma = 17, kWarpTail0 = 20;     // warps 18, 19 only fill the warpgroup
+constexpr int kWarpTma = 16, kWarpMma = 17, kWarpPv = 18, kWarpTail0 = 20;   // warp 19 only fills the warpgroup
 constexpr int kThreads = (kWarpTail0 + kTailWarps) * 32;           // 768 = 6 warpgroups
 constexpr int kConsumers = (kSoftmaxWarps + kTailWarps) * 32;      // 640 threads read the bias tile
 constexpr int kStages = 6;
+#ifdef PANGU_ATTN_TRACE
+constexpr bool kTrace = true;                      // clock64 stamps of CTA 0 (costs registers in the softmax loop)
+#else
+constexpr bool kTrace = false;
+#endif
 constexpr int kBiasBytes = 44032;                  // 144 x 152 bf16 = 43 776, padded to a multiple of 1024
 constexpr int kBufBytes = 3 * kTileBytes;          // q, k, v: 27 648 = 27 x 1024
 constexpr int kTmemCols = 512;
-constexpr int kColS = 144;                         // S/P buffer b: columns [144 b, 144 b + 144)
-constexpr int kColO = 288;                         // O buffer k: columns [288 + 32 k, +32), k < 4
+constexpr int kColS = 144;                         // S/P/O buffer b (3 of them): columns [144 b, 144 b + 144)
+constexpr int kColO = 112;                         // O(i) lands in the dead score columns [112, 144) of window i's buffer
 constexpr int kKeys0 = 80;                         // key split between the two threads of a score row: 80 + 64
 constexpr int kRunBytes = 12 * 64;                 // one run of 12 tokens x 32 channels
 constexpr int kBiasTileBytes = kWinTokens * kWinTokens * 2;
@@ -107,6 +113,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
@@ -155,6 +166,70 @@ __device__ __forceinline__ long long run_token(const WinGeom& g, int roll, int l
   return (long long)rb + w;
 }
 
+// Everything the bias-tile swap needs, kept in shared memory so that the (rare, out-of-line) swap does not hold
+// registers of the softmax / tail loops.
+struct SwapCtx {
+  const __nv_bfloat16* earth_bias;
+  __nv_bfloat16* s_bias;
+  int* s_crun;
+  int* s_ccls;
+  WinGeom g;
+  BandGeom bd;
+  int roll, head;
+};
+
+// Bias tile + tables of tile u, cooperatively by the consumer threads (ctid = index among them).  A thread FETCHES its
+// 16-byte chunks into registers before the barrier that retires the old tile (so the L2 / HBM latency overlaps the wait
+// for the slowest warp) and STORES them afterwards.  The shift mask (gen_mask, layers.py:187-216: -100 where the region
+// ids of query and key differ) of a masked window type is folded into the staged tile on the way, so the softmax loops
+// never see it.  (bias - 144.27 rounds to about -144 in bf16: the probability underflows to 0 either way, as
+// exp(-100 + s) does in the reference's fp32.)
+__device__ __noinline__ void swap_tile_fn(const SwapCtx* ctx, int u, int ctid, int first) {
+  constexpr int kChunksPerThread = (kWinTokens * 18 + kConsumers - 1) / kConsumers;     // 5
+  const WinGeom& g = ctx->g;
+  const int t = tile_type(g, ctx->bd, u);
+  const int roll = ctx->roll;
+  const uint4* src = reinterpret_cast<const uint4*>(ctx->earth_bias + ((long long)t * g.heads + ctx->head) * kWinTokens * kWinTokens);
+  uint4 r[kChunksPerThread];
+#pragma unroll
+  for (int k = 0; k < kChunksPerThread; ++k) {
+    const int i = ctid + k * kConsumers;
+    if (i < kWinTokens * 18) r[k] = __ldg(src + i);           // the tile is 144 x 18 chunks, contiguous
+  }
+  if (!first) named_bar(9, kConsumers);                       // everybody has finished with the old tile
+  const int zw = t / g.nH, hw = t - zw * g.nH;
+  const bool masked = roll == 1 && (zw == g.nZ - 1 || hw == g.nH - 1);
+  auto rgroup = [&](int rr) { return (zw == g.nZ - 1 ? 2 * (rr / 6) : 0) + ((hw == g.nH - 1 && (rr % 6) >= 3) ? 1 : 0); };
+  const float mask_l2 = kMaskValue * kLog2e;
+#pragma unroll
+  for (int k = 0; k < kChunksPerThread; ++k) {
+    const int i = ctid + k * kConsumers;
+    if (i >= kWinTokens * 18) continue;
+    const int row = i / 18, c = i - row * 18;
+    uint4 v = r[k];
+    if (masked) {
+      const int gr = rgroup(row / 12);
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+        if (rgroup((8 * c + 2 * e) / 12) != gr) lo += mask_l2;
+        if (rgroup((8 * c + 2 * e + 1) / 12) != gr) hi += mask_l2;
+        w[e] = pack_bf16(lo, hi);
+      }
+      v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(ctx->s_bias + row * kBiasPitch + c * 8) = v;
+  }
+  if (ctid >= 32 && ctid < 44) {
+    int rb, cls;
+    run_info(g, ctx->bd, roll, t, ctid - 32, rb, cls);
+    ctx->s_crun[ctid - 32] = rb;
+    ctx->s_ccls[ctid - 32] = cls;
+  }
+  named_bar(9, kConsumers);
+}
+
 // Bring-up aid: clock64 stamps of CTA 0 for its first windows (slot = window & 7), when $PANGU_ATTN_DBG is set.
 // [slot][16]: 0 TMA issued, 1 S issued, 2 p_full passed, 3 PV issued (warps 16/17); 4 s_full passed, 5 max pass done,
 // 6 max exchanged, 7 P stored, 8 epilogue(i-2) done (first warp of the window's softmax group); 10 start, 11 end (tail
@@ -178,14 +253,16 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
   int* s_pcls = s_prun + 12;                                                            // [12]
   int* s_stage_u = s_pcls + 12;                                                         // [kStages] tile whose pad rows the stage holds
   uint4* s_padvals = reinterpret_cast<uint4*>(smem + kOffTables + 512);                 // [3 tensors][4 chunks] linear1 bias, bf16
+  SwapCtx* s_ctx = reinterpret_cast<SwapCtx*>(smem + kOffTables + 768);
   float* s_exch = reinterpret_cast<float*>(smem + kOffExch);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint64_t* full = bars;                 // [6] TMA -> MMA / tail warp (tx bytes)
   uint64_t* empty = bars + 6;            // [6] 1 (tcgen05.commit after PV) + 1 (tail warp)
-  uint64_t* s_full = bars + 12;          // [2] S(i) complete in S buffer i & 1
-  uint64_t* p_full = bars + 14;          // [2] P(i) written (8 warps)
-  uint64_t* o_full = bars + 16;          // [4] O(i) complete in O buffer i & 3
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* s_full = bars + 12;          // [3] S(i) complete in TMEM buffer i % 3
+  uint64_t* p_full = bars + 15;          // [3] P(i) written (8 warps)
+  uint64_t* o_full = bars + 18;          // [3] O(i) complete
+  uint64_t* b_free = bars + 21;          // [3] O(i) read by the epilogue (8 warps): the buffer may take S(i + 3)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = g.C;
@@ -196,60 +273,20 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
   if (nwin <= 0) return;
   const int u0 = p0 / g.nLon, last_ts = (p1 - 1) / g.nLon - u0;
 
-  // cooperative load of bias tile + tables of tile u by the consumer threads (ctid = index among them); the caller
-  // commits / waits the cp.async group and synchronises
-  auto load_tile = [&](int u, int ctid) {
-    const int t = tile_type(g, bd, u);
-    const __nv_bfloat16* src = earth_bias + ((long long)t * g.heads + head) * kWinTokens * kWinTokens;
-    for (int i = ctid; i < kWinTokens * 18; i += kConsumers) {
-      const int r = i / 18, c = i - r * 18;
-      attn::cp_async16(attn::smem_u32(s_bias + r * kBiasPitch + c * 8), src + r * kWinTokens + c * 8);
-    }
-    attn::cp_async_commit();
-    if (ctid >= 32 && ctid < 44) {
-      int rb, cls;
-      run_info(g, bd, roll, t, ctid - 32, rb, cls);
-      s_crun[ctid - 32] = rb;
-      s_ccls[ctid - 32] = cls;
-    }
-  };
-  // The shift mask (gen_mask, layers.py:187-216: -100 where the region ids of query and key differ) of a masked window
-  // type is folded into the staged bias tile, so the softmax loops never see it: every thread patches the 16-byte
-  // chunks it fetched itself, after its cp.async group has landed.  (bias - 144.27 rounds to about -144 in bf16: the
-  // probability underflows to 0 either way, as exp(-100 + s) does in the reference's fp32.)
-  auto patch_tile = [&](int u, int ctid) {
-    const int t = tile_type(g, bd, u);
-    const int zw = t / g.nH, hw = t - zw * g.nH;
-    if (roll != 1 || (zw != g.nZ - 1 && hw != g.nH - 1)) return;
-    auto rgroup = [&](int r) { return (zw == g.nZ - 1 ? 2 * (r / 6) : 0) + ((hw == g.nH - 1 && (r % 6) >= 3) ? 1 : 0); };
-    const float mask_l2 = kMaskValue * kLog2e;
-    for (int i = ctid; i < kWinTokens * 18; i += kConsumers) {
-      const int r = i / 18, c = i - r * 18;
-      const int gr = rgroup(r / 12);
-      const int g_first = rgroup((8 * c) / 12), g_last = rgroup((8 * c + 7) / 12);
-      if (g_first == gr && g_last == gr) continue;
-      __nv_bfloat16* ptr = s_bias + r * kBiasPitch + c * 8;
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (rgroup((8 * c + e) / 12) != gr) ptr[e] = __float2bfloat16_rn(__bfloat162float(ptr[e]) + mask_l2);
-    }
-  };
   const bool is_consumer = warp < kSoftmaxWarps || warp >= kWarpTail0;
   const int ctid = warp < kSoftmaxWarps ? tid : tid - (kWarpTail0 - kSoftmaxWarps) * 32;
-  auto swap_tile = [&](int ts) {                              // all consumer threads, in lock step per tile
-    named_bar(9, kConsumers);                                 // everybody has finished with the old tile
-    load_tile(u0 + ts, ctid);
-    attn::cp_async_wait<0>();
-    patch_tile(u0 + ts, ctid);
-    named_bar(9, kConsumers);
-  };
+  auto swap_tile = [&](int ts) { swap_tile_fn(s_ctx, u0 + ts, ctid, 0); };   // all consumer threads, in lock step per tile
 
   // ---- prologue
-  if (is_consumer) load_tile(u0, ctid);
+  if (tid == 0) {
+    s_ctx->earth_bias = earth_bias; s_ctx->s_bias = s_bias; s_ctx->s_crun = s_crun; s_ctx->s_ccls = s_ccls;
+    s_ctx->g = g; s_ctx->bd = bd; s_ctx->roll = roll; s_ctx->head = head;
+  }
   if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 2); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 8); }
-    for (int i = 0; i < 4; ++i) tc::mbar_init(&o_full[i], 1);
+    for (int i = 0; i < 3; ++i) {
+      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 8); tc::mbar_init(&o_full[i], 1); tc::mbar_init(&b_free[i], 8);
+    }
     tc::fence_barrier_init();
   }
   if (warp == kWarpTma) {
@@ -269,19 +306,15 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
   __syncthreads();
   tc::tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  if (is_consumer) {
-    attn::cp_async_wait<0>();
-    patch_tile(u0, ctid);
-    named_bar(9, kConsumers);
-  }
+  if (is_consumer) swap_tile_fn(s_ctx, u0, ctid, 1);          // first bias tile (the TMA warp is already fetching windows)
 
-  const bool trc = dbg && blockIdx.x == 0 && lane == 0;
+  const bool trc = kTrace && dbg && blockIdx.x == 0 && lane == 0;
 
   // Register budget per warpgroup (768 threads start with 80 each, and that total is the pool): the TMA / MMA group
-  // shrinks to 56 so that the tail group -- whole mma.sync windows in registers -- can grow to 104.
+  // shrinks to 48 so that the tail group -- whole mma.sync windows in registers -- can grow to 112.
   // (the instruction sits at the top of each role branch so that ptxas budgets the branch accordingly)
   if (warp >= kSoftmaxWarps && warp < kWarpTail0) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");      // all four warps of the group, converged
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");      // all four warps of the group, converged
   if (warp == kWarpTma) {
     // ==================================================================== TMA producer
     int cur_u = -1, real_runs = 0;
@@ -366,41 +399,43 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       if (trc) g_attn_trace[(i & 7) * 16 + 0] = clock64();
     }
   } else if (warp == kWarpMma) {
-    // ==================================================================== MMA issuer
+    // ==================================================================== S = Q K^T issuer
+    // Three TMEM buffers: S(i) needs its operands (full) and buffer i % 3 back from the epilogue of window i-3 (b_free,
+    // in the middle of the softmax of window i-1).  The PV MMAs are issued by ANOTHER warp: issuing one tcgen05.mma
+    // costs this warp ~80 cycles of descriptor traffic, and an S queued behind nine PV issues would stall a whole
+    // softmax group.  No tensor-pipe ordering between S and PV is assumed; every hand-over has its mbarrier.
     constexpr uint32_t idesc_s = tc::make_idesc_bf16(128, 144, 0, 0);
-    constexpr uint32_t idesc_o = tc::make_idesc_bf16(128, 32, 0, 1);
-    auto issue_pv = [&](int i) {
-      const int st = i % kStages, sb = i & 1, ob = i & 3;
-      tc::mbar_wait(&p_full[sb], (i >> 1) & 1);
-      tc::tcgen05_after_sync();
-      if (trc) g_attn_trace[(i & 7) * 16 + 2] = clock64();
-      const uint32_t av = smem_u32(s_buf + st * kBufBytes + 2 * kTileBytes);
-      const uint32_t tP = tmem_base + sb * kColS, tO = tmem_base + kColO + 32 * ob;
-#pragma unroll
-      for (int k = 0; k < 9; ++k)                            // K = 144 keys: 16 keys = 8 packed TMEM columns / 1 KiB of V per step
-        if (tc::elect_one())                                 // P of keys 0..79 at columns [0,40), of keys 80..143 at [80,112)
-          tc::umma_bf16_ts(tO, tP + 8 * k + (k >= 5 ? 40 : 0), desc_mn_sw64(av + 1024 * k), idesc_o, k);
-      if (tc::elect_one()) { tc::umma_commit(&o_full[ob]); tc::umma_commit(&empty[st]); }
-      __syncwarp();
-      if (trc) g_attn_trace[(i & 7) * 16 + 3] = clock64();
-    };
-    // The tensor pipe executes in issue order: S(i) may overwrite S buffer i & 1 as soon as PV(i-2) has been ISSUED
-    // (softmax(i-2) is done with it by then: p_full), and PV(i) may overwrite O buffer i & 3 because the epilogue of
-    // window i-4 ran before its group arrived on p_full(i-2).
     for (int i = 0; i < nwin; ++i) {
-      const int st = i % kStages, sb = i & 1;
+      const int st = i % kStages, b = i % 3;
       tc::mbar_wait(&full[st], (i / kStages) & 1);
+      if (i >= 3) tc::mbar_wait(&b_free[b], ((i / 3) & 1) ^ 1);
       tc::tcgen05_after_sync();
       const uint32_t aq = smem_u32(s_buf + st * kBufBytes), ak = aq + kTileBytes;
 #pragma unroll
       for (int k = 0; k < 2; ++k)                            // K = 32: two 16-element steps, +32 B inside the 64 B swizzle span
-        if (tc::elect_one()) tc::umma_bf16(tmem_base + sb * kColS, desc_k_sw64(aq) + 2 * k, desc_k_sw64(ak) + 2 * k, idesc_s, k);
-      if (tc::elect_one()) tc::umma_commit(&s_full[sb]);
+        if (tc::elect_one()) tc::umma_bf16(tmem_base + b * kColS, desc_k_sw64(aq) + 2 * k, desc_k_sw64(ak) + 2 * k, idesc_s, k);
+      if (tc::elect_one()) tc::umma_commit(&s_full[b]);
       __syncwarp();
       if (trc) g_attn_trace[(i & 7) * 16 + 1] = clock64();
-      if (i > 0) issue_pv(i - 1);
     }
-    issue_pv(nwin - 1);
+  } else if (warp == kWarpPv) {
+    // ==================================================================== O = P V issuer
+    constexpr uint32_t idesc_o = tc::make_idesc_bf16(128, 32, 0, 1);
+    for (int i = 0; i < nwin; ++i) {
+      const int st = i % kStages, b = i % 3;
+      tc::mbar_wait(&p_full[b], (i / 3) & 1);
+      tc::tcgen05_after_sync();
+      if (trc) g_attn_trace[(i & 7) * 16 + 2] = clock64();
+      const uint32_t av = smem_u32(s_buf + st * kBufBytes + 2 * kTileBytes);
+      const uint32_t tP = tmem_base + b * kColS, tO = tP + kColO;
+#pragma unroll
+      for (int k = 0; k < 9; ++k)                            // K = 144 keys: 16 keys = 8 packed TMEM columns / 1 KiB of V per step
+        if (tc::elect_one())                                 // P of keys 0..79 at columns [0,40), of keys 80..143 at [80,112)
+          tc::umma_bf16_ts(tO, tP + 8 * k + (k >= 5 ? 40 : 0), desc_mn_sw64(av + 1024 * k), idesc_o, k);
+      if (tc::elect_one()) { tc::umma_commit(&o_full[b]); tc::umma_commit(&empty[st]); }
+      __syncwarp();
+      if (trc) g_attn_trace[(i & 7) * 16 + 3] = clock64();
+    }
   }
   } else if (warp < kSoftmaxWarps) {
     // ==================================================================== softmax: thread = (score row, 80 or 64 keys)
@@ -408,114 +443,119 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
     const int row = q * 32 + lane;
     const int k0 = hf * kKeys0, nchunk = hf ? 4 : 5;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const uint32_t tS = tmem_base + lane_addr + grp * kColS + k0;
     const uint32_t brow = smem_u32(s_bias + row * kBiasPitch + k0);
     const uint32_t exg = smem_u32(s_exch + grp * 1024);       // [slot][max | sum][half][128] floats
     const int rrun = row / 12, rdw = row - rrun * 12;
     const bool trw = trc && (warp & 7) == 0;
 
-    int cur_ts = 0, cur_u = -1, t = 0;
-    int rcls = 0, rrb = -1;
-    __nv_bfloat16* dst_prev = nullptr;
-    float* lse_prev = nullptr;
-    float m_prev = 0.f;
+    int tok_prev = -1;                                        // output token (x 2 + buffer class) of window i-2, or -1
 
-    auto epilogue = [&](int i, __nv_bfloat16* dst, float* lsep, float m) {
-      const int ob = i & 3, slot = (i >> 1) & 1;
-      tc::mbar_wait(&o_full[ob], (i >> 2) & 1);
+    // O(i) -> global (each thread 16 channels of its row = one 32-byte sector), then the TMEM buffer is released
+    auto epilogue = [&](int i, int tokc) {
+      const int b = i % 3, slot = (i >> 1) & 1;
+      tc::mbar_wait(&o_full[b], (i / 3) & 1);
       tc::tcgen05_after_sync();
       uint32_t o[16];
-      tc::tmem_ld_32x16(tmem_base + lane_addr + kColO + 32 * ob + hf * 16, o);
+      tc::tmem_ld_32x16(tmem_base + lane_addr + b * kColS + kColO + hf * 16, o);
       const uint32_t exs = exg + (slot * 512 + 256 + row) * 4;
       const float sum = lds_f32(exs) + lds_f32(exs + 512);
       const float inv = 1.0f / sum;
       tmem_ld_wait16(o);
-      if (dst != nullptr) {
-        uint4 a, b;
+      tc::tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&b_free[b]);
+      if (tokc >= 0) {
+        uint4 a, c;
         a.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
         a.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
         a.z = pack_bf16(__uint_as_float(o[4]) * inv, __uint_as_float(o[5]) * inv);
         a.w = pack_bf16(__uint_as_float(o[6]) * inv, __uint_as_float(o[7]) * inv);
-        b.x = pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
-        b.y = pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
-        b.z = pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
-        b.w = pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
-        uint4* d = reinterpret_cast<uint4*>(dst);
-        d[0] = a; d[1] = b;
+        c.x = pack_bf16(__uint_as_float(o[8]) * inv, __uint_as_float(o[9]) * inv);
+        c.y = pack_bf16(__uint_as_float(o[10]) * inv, __uint_as_float(o[11]) * inv);
+        c.z = pack_bf16(__uint_as_float(o[12]) * inv, __uint_as_float(o[13]) * inv);
+        c.w = pack_bf16(__uint_as_float(o[14]) * inv, __uint_as_float(o[15]) * inv);
+        __nv_bfloat16* base = (tokc & 1) ? halo_out : out;
+        uint4* d = reinterpret_cast<uint4*>(base + (long long)(tokc >> 1) * C + head * kHeadDim + hf * 16);
+        d[0] = a; d[1] = c;
       }
-      if (lsep != nullptr) *lsep = m + log2f(sum);
+      if (lse != nullptr && hf == 0) {                        // training only: log2-sum-exp of the row, for the backward
+        const int p = p0 + i, pu = p / g.nLon, pl = p - pu * g.nLon;
+        const float m = lds_f32(exg + (slot * 512 + row) * 4);        // the row maximum (both halves hold the merged value)
+        lse[((pl * g.T + tile_type(g, bd, pu)) * g.heads + head) * kWinTokens + row] = m + log2f(sum);
+      }
     };
 
-    for (int i = grp; i < nwin; i += 2) {
-      const int p = p0 + i, u = p / g.nLon, l = p - u * g.nLon;
-      const int slot = (i >> 1) & 1;
+    // tile by tile: the (out-of-line) bias swap stays outside the window loop, whose registers it would otherwise pin
+    int i = grp;
+#pragma unroll 1
+    for (int ts = 0; ts <= last_ts; ++ts) {
+    if (ts > 0) {
+      if (trc && warp == 0) g_attn_trace[12] = clock64();
+      swap_tile(ts);
+      if (trc && warp == 0) g_attn_trace[13] = clock64();
+    }
+    const int i_end = min(nwin, (u0 + ts + 1) * g.nLon - p0);    // windows [.., i_end) lie in tile u0 + ts
+#pragma unroll 1
+    for (; i < i_end; i += 2) {
+      const int slot = (i >> 1) & 1, b = i % 3;
+      const int l = p0 + i - (u0 + ts) * g.nLon;
       long long* tr = g_attn_trace + (i & 7) * 16;
-      while (cur_ts < u - u0) {
-        if (trc && warp == 0) g_attn_trace[12] = clock64();
-        swap_tile(++cur_ts);
-        if (trc && warp == 0) g_attn_trace[13] = clock64();
-      }
-      if (u != cur_u) {
-        cur_u = u;
-        t = tile_type(g, bd, u);
-        run_info(g, bd, roll, t, rrun, rrb, rcls);
-      }
-      __nv_bfloat16* dst_base = rcls == 1 ? out : (rcls == 2 ? halo_out : nullptr);
-      __nv_bfloat16* dst_cur = dst_base == nullptr ? nullptr
-                               : dst_base + run_token(g, roll, l, rrb, rdw) * C + head * kHeadDim + hf * 16;
-      float* lse_cur = (lse != nullptr && hf == 0) ? lse + (((long long)l * g.T + t) * g.heads + head) * kWinTokens + row : nullptr;
+      const int rcls = s_ccls[rrun], rrb = s_crun[rrun];      // tables of the current tile (rebuilt by every swap)
+      const int tok_cur = (rcls == 1 || (rcls == 2 && halo_out != nullptr)) ? (int)run_token(g, roll, l, rrb, rdw) * 2 + (rcls == 2) : -1;
+      const uint32_t tS = tmem_base + lane_addr + b * kColS + k0;
 
-      tc::mbar_wait(&s_full[grp], (i >> 1) & 1);
+      tc::mbar_wait(&s_full[b], (i / 3) & 1);
       tc::tcgen05_after_sync();
       if (trw) tr[4] = clock64();
       const uint32_t exm = exg + slot * 2048, exs = exm + 1024;
       float m;
       {
-        // ---- pass 1: maximum of S + bias over my keys (a shift mask is part of the staged bias)
-        uint32_t va[16], vb[16];
+        // ---- pass 1: maximum of S + bias over my keys (a shift mask is part of the staged bias).  One 16-column chunk
+        // in flight: a TMEM load completes in ~12 cycles, registers are what is scarce here (a spill costs an L2 trip).
         float mx0 = -INFINITY, mx1 = -INFINITY;
-        tc::tmem_ld_32x16(tS, va);
-        tmem_ld_wait16(va);
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
           if (c < nchunk) {
-            uint32_t (&cur)[16] = (c & 1) ? vb : va;
-            uint32_t (&nxt)[16] = (c & 1) ? va : vb;
-            if (c + 1 < nchunk) tc::tmem_ld_32x16(tS + 16 * (c + 1), nxt);
+            uint32_t v[16];
+            tc::tmem_ld_32x16(tS + 16 * c, v);
             const uint4 b0 = lds128(brow + 32 * c), b1 = lds128(brow + 32 * c + 16);
             const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            tmem_ld_wait16(v);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              float s0 = __uint_as_float(cur[2 * e]), s1 = __uint_as_float(cur[2 * e + 1]);
+              float s0 = __uint_as_float(v[2 * e]), s1 = __uint_as_float(v[2 * e + 1]);
               add_bias2(bw[e], s0, s1);
               mx0 = fmaxf(mx0, s0);
               mx1 = fmaxf(mx1, s1);
             }
-            if (c + 1 < nchunk) tmem_ld_wait16(nxt);
           }
         }
-        if (trw) tr[5] = clock64();
         m = fmaxf(mx0, mx1);
         sts_f32(exm + (hf * 128 + row) * 4, m);
-        tc::tmem_ld_32x16(tS, va);                            // first chunk of pass 2 flies during the exchange
+      }
+      if (trw) tr[5] = clock64();
+      // ---- the epilogue of window i-2 fills the wait for the partner warp's maximum
+      if (i >= 2) epilogue(i - 2, tok_prev);
+      if (trw) tr[8] = clock64();
+      {
         named_bar(1 + grp * 4 + q, 64);                       // the two warps of this lane quarter
         m = fmaxf(m, lds_f32(exm + ((hf ^ 1) * 128 + row) * 4));
-        tmem_ld_wait16(va);
+        sts_f32(exm + (hf * 128 + row) * 4, m);               // the merged maximum, for the lse of the epilogue
         if (trw) tr[6] = clock64();
         // ---- pass 2: P = exp2(S + bias - m) -> bf16, packed over my own first columns; row sum
         float sm0 = 0.f, sm1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
           if (c < nchunk) {
-            uint32_t (&cur)[16] = (c & 1) ? vb : va;
-            uint32_t (&nxt)[16] = (c & 1) ? va : vb;
-            if (c + 1 < nchunk) tc::tmem_ld_32x16(tS + 16 * (c + 1), nxt);
+            uint32_t v[16];
+            tc::tmem_ld_32x16(tS + 16 * c, v);
             const uint4 b0 = lds128(brow + 32 * c), b1 = lds128(brow + 32 * c + 16);
             const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            tmem_ld_wait16(v);
             uint32_t pk[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              float s0 = __uint_as_float(cur[2 * e]), s1 = __uint_as_float(cur[2 * e + 1]);
+              float s0 = __uint_as_float(v[2 * e]), s1 = __uint_as_float(v[2 * e + 1]);
               add_bias2(bw[e], s0, s1);
               const float e0 = ex2(s0 - m), e1 = ex2(s1 - m);
               sm0 += e0;
@@ -523,7 +563,6 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
               pk[e] = pack_bf16(e0, e1);
             }
             tmem_st_32x8(tS + 8 * c, pk);
-            if (c + 1 < nchunk) tmem_ld_wait16(nxt);
           }
         }
         sts_f32(exs + (hf * 128 + row) * 4, sm0 + sm1);
@@ -531,29 +570,28 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       tc::tmem_st_wait();
       tc::tcgen05_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&p_full[grp]);
+      if (lane == 0) tc::mbar_arrive(&p_full[b]);
       if (trw) tr[7] = clock64();
-      if (i >= 2) epilogue(i - 2, dst_prev, lse_prev, m_prev);
-      dst_prev = dst_cur; lse_prev = lse_cur; m_prev = m;
-      if (trw) tr[8] = clock64();
+      tok_prev = tok_cur;
     }
-    {
-      const int cnt = nwin > grp ? (nwin - grp + 1) / 2 : 0;  // windows of this group
-      if (cnt > 0) epilogue(grp + 2 * (cnt - 1), dst_prev, lse_prev, m_prev);
     }
-    while (cur_ts < last_ts) swap_tile(++cur_ts);
+    if (i >= 2) epilogue(i - 2, tok_prev);                    // the last window of this group
   } else {
     // ==================================================================== tail warps: rows 128..143 of window i = j (mod 4)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     constexpr int row0 = 128;
     const int jt = warp - kWarpTail0;
     const int gq = lane >> 2, tq = lane & 3, mi = lane >> 3, mr = lane & 7;
-    int cur_ts = 0;
-    for (int i = jt; i < nwin; i += kTailWarps) {
-      const int p = p0 + i, u = p / g.nLon, l = p - u * g.nLon;
+    int i = jt;
+#pragma unroll 1
+    for (int ts = 0; ts <= last_ts; ++ts) {
+    if (ts > 0) swap_tile(ts);
+    const int i_end = min(nwin, (u0 + ts + 1) * g.nLon - p0);
+    const int t = tile_type(g, bd, u0 + ts);
+#pragma unroll 1
+    for (; i < i_end; i += kTailWarps) {
+      const int l = p0 + i - (u0 + ts) * g.nLon;
       const int st = i % kStages;
-      while (cur_ts < u - u0) swap_tile(++cur_ts);
-      const int t = tile_type(g, bd, u);
       uint8_t* sq = s_buf + st * kBufBytes;
       uint8_t* sk = sq + kTileBytes;
       uint8_t* sv = sk + kTileBytes;
@@ -565,62 +603,57 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
         const int r = row0 + (mi & 1) * 8 + mr, c = ks * 2 + (mi >> 1);
         ldmatrix_x4(attn::smem_u32(sq + tile_off(r, c)), qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3]);
       }
+      // the whole 16 x 144 score block at once (no online rescaling chain: one warp per window must find its
+      // instruction-level parallelism inside the window)
+      const uint32_t b_lo = smem_u32(s_bias + (row0 + gq) * kBiasPitch + 2 * tq), b_hi = b_lo + 8 * kBiasPitch * 2;
+      float s_acc[18][4];
+#pragma unroll
+      for (int nt = 0; nt < 18; ++nt) {                       // accumulate on top of the (pre-scaled, pre-masked) bias
+        const uint32_t w_lo = lds32(b_lo + nt * 16), w_hi = lds32(b_hi + nt * 16);
+        s_acc[nt][0] = __uint_as_float(w_lo << 16); s_acc[nt][1] = __uint_as_float(w_lo & 0xffff0000u);
+        s_acc[nt][2] = __uint_as_float(w_hi << 16); s_acc[nt][3] = __uint_as_float(w_hi & 0xffff0000u);
+        uint32_t k0r, k1r, k2r, k3r;
+        ldmatrix_x4(attn::smem_u32(sk + tile_off(nt * 8 + mr, mi)), k0r, k1r, k2r, k3r);
+        mma_bf16(s_acc[nt], qa[0], k0r, k1r);
+        mma_bf16(s_acc[nt], qa[1], k2r, k3r);
+      }
+      float m_lo = -INFINITY, m_hi = -INFINITY, m_lo2 = -INFINITY, m_hi2 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 18; nt += 2) {
+        m_lo = fmaxf(m_lo, fmaxf(s_acc[nt][0], s_acc[nt][1]));
+        m_hi = fmaxf(m_hi, fmaxf(s_acc[nt][2], s_acc[nt][3]));
+        m_lo2 = fmaxf(m_lo2, fmaxf(s_acc[nt + 1][0], s_acc[nt + 1][1]));
+        m_hi2 = fmaxf(m_hi2, fmaxf(s_acc[nt + 1][2], s_acc[nt + 1][3]));
+      }
+      m_lo = fmaxf(m_lo, m_lo2); m_hi = fmaxf(m_hi, m_hi2);
+      m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 1));
+      m_lo = fmaxf(m_lo, __shfl_xor_sync(0xffffffffu, m_lo, 2));
+      m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 1));
+      m_hi = fmaxf(m_hi, __shfl_xor_sync(0xffffffffu, m_hi, 2));
+      uint32_t pa[9][4];                                      // P as A fragments, 9 k-steps of 16 keys
+#pragma unroll
+      for (int nt = 0; nt < 18; ++nt) {
+        const float e0 = ex2(s_acc[nt][0] - m_lo), e1 = ex2(s_acc[nt][1] - m_lo);
+        const float e2 = ex2(s_acc[nt][2] - m_hi), e3 = ex2(s_acc[nt][3] - m_hi);
+        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(e0, e1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(e2, e3);
+      }
       float o_acc[4][4];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) o_acc[a][c] = 0.f;
-      float m_lo = -INFINITY, m_hi = -INFINITY;
       float l_acc[4] = {0.f, 0.f, 0.f, 0.f};                  // row sums of the bf16 P, from a ones-column MMA
-#pragma unroll 1
-      for (int kv0 = 0; kv0 < kWinTokens; kv0 += 48) {
-        float s_acc[6][4];
 #pragma unroll
-        for (int nt = 0; nt < 6; ++nt) {                      // accumulate on top of the (pre-scaled) bias
-          const int j = kv0 + nt * 8 + 2 * tq;
-          const __nv_bfloat162 b_lo = *reinterpret_cast<const __nv_bfloat162*>(s_bias + (row0 + gq) * kBiasPitch + j);
-          const __nv_bfloat162 b_hi = *reinterpret_cast<const __nv_bfloat162*>(s_bias + (row0 + gq + 8) * kBiasPitch + j);
-          s_acc[nt][0] = __low2float(b_lo); s_acc[nt][1] = __high2float(b_lo);
-          s_acc[nt][2] = __low2float(b_hi); s_acc[nt][3] = __high2float(b_hi);
-          uint32_t k0r, k1r, k2r, k3r;
-          ldmatrix_x4(attn::smem_u32(sk + tile_off(kv0 + nt * 8 + mr, mi)), k0r, k1r, k2r, k3r);
-          mma_bf16(s_acc[nt], qa[0], k0r, k1r);
-          mma_bf16(s_acc[nt], qa[1], k2r, k3r);
-        }
-        float mx_lo = m_lo, mx_hi = m_hi;
+      for (int kk = 0; kk < 9; ++kk) {
+        mma_bf16(l_acc, pa[kk], 0x3F803F80u, 0x3F803F80u);
 #pragma unroll
-        for (int nt = 0; nt < 6; ++nt) {
-          mx_lo = fmaxf(mx_lo, fmaxf(s_acc[nt][0], s_acc[nt][1]));
-          mx_hi = fmaxf(mx_hi, fmaxf(s_acc[nt][2], s_acc[nt][3]));
-        }
-        mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
-        mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
-        mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
-        mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-        const float a_lo = ex2(m_lo - mx_lo), a_hi = ex2(m_hi - mx_hi);     // 0 on the first block (m = -inf)
-        m_lo = mx_lo; m_hi = mx_hi;
-        l_acc[0] *= a_lo; l_acc[2] *= a_hi;
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) { o_acc[nt][0] *= a_lo; o_acc[nt][1] *= a_lo; o_acc[nt][2] *= a_hi; o_acc[nt][3] *= a_hi; }
-        uint32_t pa[3][4];
-#pragma unroll
-        for (int nt = 0; nt < 6; ++nt) {
-          const float e0 = ex2(s_acc[nt][0] - m_lo), e1 = ex2(s_acc[nt][1] - m_lo);
-          const float e2 = ex2(s_acc[nt][2] - m_hi), e3 = ex2(s_acc[nt][3] - m_hi);
-          pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(e0, e1);
-          pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(e2, e3);
-        }
-#pragma unroll
-        for (int kk = 0; kk < 3; ++kk) {
-          mma_bf16(l_acc, pa[kk], 0x3F803F80u, 0x3F803F80u);
-#pragma unroll
-          for (int dp = 0; dp < 2; ++dp) {
-            uint32_t v0, v1, v2, v3;
-            const int r = kv0 + kk * 16 + (mi & 1) * 8 + mr, c = dp * 2 + (mi >> 1);
-            ldmatrix_x4_trans(attn::smem_u32(sv + tile_off(r, c)), v0, v1, v2, v3);
-            mma_bf16(o_acc[dp * 2], pa[kk], v0, v1);
-            mma_bf16(o_acc[dp * 2 + 1], pa[kk], v2, v3);
-          }
+        for (int dp = 0; dp < 2; ++dp) {
+          uint32_t v0, v1, v2, v3;
+          const int r = kk * 16 + (mi & 1) * 8 + mr, c = dp * 2 + (mi >> 1);
+          ldmatrix_x4_trans(attn::smem_u32(sv + tile_off(r, c)), v0, v1, v2, v3);
+          mma_bf16(o_acc[dp * 2], pa[kk], v0, v1);
+          mma_bf16(o_acc[dp * 2 + 1], pa[kk], v2, v3);
         }
       }
       const float inv_lo = 1.0f / l_acc[0], inv_hi = 1.0f / l_acc[2];
@@ -655,7 +688,7 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       if (lane == 0) tc::mbar_arrive(&empty[st]);
       if (trc) g_attn_trace[(i & 7) * 16 + 11] = clock64();
     }
-    while (cur_ts < last_ts) swap_tile(++cur_ts);
+    }
   }
   tc::tcgen05_before_sync();
   __syncthreads();
