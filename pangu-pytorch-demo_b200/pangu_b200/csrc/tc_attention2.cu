@@ -24,7 +24,7 @@
 //              one whole window per warp (online softmax over three 48-key blocks, as tc_attention.cu)
 // When the window type changes, the 20 consumer warps swap the bias tile (the producer warp has already pulled it into
 // L2); TMA and MMA keep running ahead meanwhile.
-// Warps (768 threads, 512 TMEM columns): 0-15 softmax, 16 TMA producer, 17 S-MMA issuer + TMEM allocator, 18 PV-MMA issuer, 20-23 tails.
+// Warps (768 threads, 512 TMEM columns): 0-15 softmax, 16 TMA producer, 17 S-MMA issuer + TMEM allocator, 18-19 PV-MMA issuers, 20-23 tails.
 #include <cstdlib>
 
 #include "attn_common.cuh"
@@ -46,7 +46,7 @@ using tc::smem_u32;
 
 constexpr int kSoftmaxWarps = 16;
 constexpr int kTailWarps = 4;
-constexpr int kWarpTma = 16, kWarpMma = 17, kWarpPv = 18, kWarpTail0 = 20;   // warp 19 only fills the warpgroup
+constexpr int kWarpTma = 16, kWarpMma = 17, kWarpPv = 18, kWarpTail0 = 20;   // PV issuers: warps 18, 19
 constexpr int kThreads = (kWarpTail0 + kTailWarps) * 32;           // 768 = 6 warpgroups
 constexpr int kConsumers = (kSoftmaxWarps + kTailWarps) * 32;      // 640 threads read the bias tile
 constexpr int kStages = 6;
@@ -59,7 +59,8 @@ constexpr int kBiasBytes = 44032;                  // 144 x 152 bf16 = 43 776, p
 constexpr int kBufBytes = 3 * kTileBytes;          // q, k, v: 27 648 = 27 x 1024
 constexpr int kTmemCols = 512;
 constexpr int kColS = 144;                         // S/P/O buffer b (3 of them): columns [144 b, 144 b + 144)
-constexpr int kColO = 112;                         // O(i) lands in the dead score columns [112, 144) of window i's buffer
+constexpr int kColO = 112;                         // O(i) lands in dead score columns of window i's buffer: keys 0..79 -> [112,144),
+constexpr int kColOb = 40;                         // keys 80..143 -> [40,72); the epilogue adds the two
 constexpr int kKeys0 = 80;                         // key split between the two threads of a score row: 80 + 64
 constexpr int kRunBytes = 12 * 64;                 // one run of 12 tokens x 32 channels
 constexpr int kBiasTileBytes = kWinTokens * kWinTokens * 2;
@@ -257,7 +258,7 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
   float* s_exch = reinterpret_cast<float*>(smem + kOffExch);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint64_t* full = bars;                 // [6] TMA -> MMA / tail warp (tx bytes)
-  uint64_t* empty = bars + 6;            // [6] 1 (tcgen05.commit after PV) + 1 (tail warp)
+  uint64_t* empty = bars + 6;            // [6] 2 (tcgen05.commit of the two PV issuers) + 1 (tail warp)
   uint64_t* s_full = bars + 12;          // [3] S(i) complete in TMEM buffer i % 3
   uint64_t* p_full = bars + 15;          // [3] P(i) written (8 warps)
   uint64_t* o_full = bars + 18;          // [3] O(i) complete
@@ -283,9 +284,9 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
     s_ctx->g = g; s_ctx->bd = bd; s_ctx->roll = roll; s_ctx->head = head;
   }
   if (warp == kWarpMma && lane == 0) {
-    for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 2); }
+    for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 3); }
     for (int i = 0; i < 3; ++i) {
-      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 8); tc::mbar_init(&o_full[i], 1); tc::mbar_init(&b_free[i], 8);
+      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 8); tc::mbar_init(&o_full[i], 2); tc::mbar_init(&b_free[i], 8);
     }
     tc::fence_barrier_init();
   }
@@ -418,23 +419,32 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       __syncwarp();
       if (trc) g_attn_trace[(i & 7) * 16 + 1] = clock64();
     }
-  } else if (warp == kWarpPv) {
-    // ==================================================================== O = P V issuer
+  } else {
+    // ==================================================================== O = P V issuers (warps 18 and 19)
+    // Issuing a tcgen05.mma costs the issuing warp ~100 cycles (descriptor build, R2UR, ELECT), so the nine K-steps of a
+    // window are split between two warps and two accumulators: keys 0..79 -> O_a, keys 80..143 -> O_b; the epilogue adds
+    // them.  Both land in score columns that are dead once P is written: O_a in [112,144), O_b in [40,72).
     constexpr uint32_t idesc_o = tc::make_idesc_bf16(128, 32, 0, 1);
+    const int part = warp - kWarpPv;
     for (int i = 0; i < nwin; ++i) {
       const int st = i % kStages, b = i % 3;
       tc::mbar_wait(&p_full[b], (i / 3) & 1);
       tc::tcgen05_after_sync();
-      if (trc) g_attn_trace[(i & 7) * 16 + 2] = clock64();
+      if (trc && part == 0) g_attn_trace[(i & 7) * 16 + 2] = clock64();
       const uint32_t av = smem_u32(s_buf + st * kBufBytes + 2 * kTileBytes);
-      const uint32_t tP = tmem_base + b * kColS, tO = tP + kColO;
+      const uint32_t tP = tmem_base + b * kColS;
+      if (part == 0) {
 #pragma unroll
-      for (int k = 0; k < 9; ++k)                            // K = 144 keys: 16 keys = 8 packed TMEM columns / 1 KiB of V per step
-        if (tc::elect_one())                                 // P of keys 0..79 at columns [0,40), of keys 80..143 at [80,112)
-          tc::umma_bf16_ts(tO, tP + 8 * k + (k >= 5 ? 40 : 0), desc_mn_sw64(av + 1024 * k), idesc_o, k);
+        for (int k = 0; k < 5; ++k)                          // 16 keys = 8 packed TMEM columns / 1 KiB of V per step
+          if (tc::elect_one()) tc::umma_bf16_ts(tP + kColO, tP + 8 * k, desc_mn_sw64(av + 1024 * k), idesc_o, k);
+      } else {
+#pragma unroll
+        for (int k = 5; k < 9; ++k)                          // P of keys 80..143 sits at columns [80,112)
+          if (tc::elect_one()) tc::umma_bf16_ts(tP + kColOb, tP + 8 * k + 40, desc_mn_sw64(av + 1024 * k), idesc_o, k - 5);
+      }
       if (tc::elect_one()) { tc::umma_commit(&o_full[b]); tc::umma_commit(&empty[st]); }
       __syncwarp();
-      if (trc) g_attn_trace[(i & 7) * 16 + 3] = clock64();
+      if (trc && part == 0) g_attn_trace[(i & 7) * 16 + 3] = clock64();
     }
   }
   } else if (warp < kSoftmaxWarps) {
@@ -455,12 +465,16 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       const int b = i % 3, slot = (i >> 1) & 1;
       tc::mbar_wait(&o_full[b], (i / 3) & 1);
       tc::tcgen05_after_sync();
-      uint32_t o[16];
+      uint32_t o[16], o2[16];
       tc::tmem_ld_32x16(tmem_base + lane_addr + b * kColS + kColO + hf * 16, o);
+      tc::tmem_ld_32x16(tmem_base + lane_addr + b * kColS + kColOb + hf * 16, o2);
       const uint32_t exs = exg + (slot * 512 + 256 + row) * 4;
       const float sum = lds_f32(exs) + lds_f32(exs + 512);
       const float inv = 1.0f / sum;
       tmem_ld_wait16(o);
+      tmem_ld_wait16(o2);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) + __uint_as_float(o2[e]));
       tc::tcgen05_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&b_free[b]);
