@@ -16,15 +16,15 @@
 //              two passes over its TMEM columns in 16-column chunks: max of S + bias (+ mask), then exp2 -> bf16 P
 //              written back over its OWN first columns (tcgen05.st), so no registers hold a whole row.  The bf16 bias
 //              is added with the mixed-precision add (one FHADD.BF16 per score, no unpacking).
-//   O = P V    tcgen05.mma, A = P from TMEM (TS form), B = V from smem (MN-major), N=32 K=144; O(i) lands in the dead
-//              score columns of its own buffer; three S/P/O buffers, so S(i+1) never queues behind PV(i)
-//   epilogue   of window i-2 between the two passes of window i (it fills the wait for the partner's row maximum):
-//              16 columns per thread -> one 32-byte sector at the un-rolled token position
+//   O = P V    tcgen05.mma, A = P from TMEM (TS form), B = V from smem (MN-major), N=32 K=144; three S/P buffers and two
+//              O buffers, S and PV issued by different warps, so S(i+2) is complete long before its group needs it
+//   epilogue   of window i-2 inside pass 2 of window i: 16 columns per thread -> one 32-byte sector at the un-rolled
+//              token position
 //   rows 128..143  (they do not fit M=128) run on four "tail" warps with mma.sync fragments on the same smem tiles,
 //              one whole window per warp (online softmax over three 48-key blocks, as tc_attention.cu)
 // When the window type changes, the 20 consumer warps swap the bias tile (the producer warp has already pulled it into
 // L2); TMA and MMA keep running ahead meanwhile.
-// Warps (768 threads, 512 TMEM columns): 0-15 softmax, 16 TMA producer, 17 S-MMA issuer + TMEM allocator, 18-19 PV-MMA issuers, 20-23 tails.
+// Warps (768 threads, 512 TMEM columns): 0-15 softmax, 16 TMA producer, 17 S-MMA issuer + TMEM allocator, 18 PV-MMA issuer, 20-23 tails.
 #include <cstdlib>
 
 #include "attn_common.cuh"
@@ -46,7 +46,7 @@ using tc::smem_u32;
 
 constexpr int kSoftmaxWarps = 16;
 constexpr int kTailWarps = 4;
-constexpr int kWarpTma = 16, kWarpMma = 17, kWarpPv = 18, kWarpTail0 = 20;   // PV issuers: warps 18, 19
+constexpr int kWarpTma = 16, kWarpMma = 17, kWarpPv = 18, kWarpTail0 = 20;   // warp 19 only fills the warpgroup
 constexpr int kThreads = (kWarpTail0 + kTailWarps) * 32;           // 768 = 6 warpgroups
 constexpr int kConsumers = (kSoftmaxWarps + kTailWarps) * 32;      // 640 threads read the bias tile
 constexpr int kStages = 6;
@@ -58,9 +58,8 @@ constexpr bool kTrace = false;
 constexpr int kBiasBytes = 44032;                  // 144 x 152 bf16 = 43 776, padded to a multiple of 1024
 constexpr int kBufBytes = 3 * kTileBytes;          // q, k, v: 27 648 = 27 x 1024
 constexpr int kTmemCols = 512;
-constexpr int kColS = 144;                         // S/P/O buffer b (3 of them): columns [144 b, 144 b + 144)
-constexpr int kColO = 112;                         // O(i) lands in dead score columns of window i's buffer: keys 0..79 -> [112,144),
-constexpr int kColOb = 40;                         // keys 80..143 -> [40,72); the epilogue adds the two
+constexpr int kColS = 144;                         // S/P buffer b (3 of them): columns [144 b, 144 b + 144)
+constexpr int kColO = 432;                         // O buffer k (2 of them): columns [432 + 32 k, +32)
 constexpr int kKeys0 = 80;                         // key split between the two threads of a score row: 80 + 64
 constexpr int kRunBytes = 12 * 64;                 // one run of 12 tokens x 32 channels
 constexpr int kBiasTileBytes = kWinTokens * kWinTokens * 2;
@@ -102,6 +101,14 @@ __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
                  "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                :: "memory");
 }
 // s0 += lo(w), s1 += hi(w) with w = two packed bf16: mixed-precision add (FHADD.BF16 with .H0/.H1 selectors), exact.
@@ -258,11 +265,14 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
   float* s_exch = reinterpret_cast<float*>(smem + kOffExch);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint64_t* full = bars;                 // [6] TMA -> MMA / tail warp (tx bytes)
-  uint64_t* empty = bars + 6;            // [6] 2 (tcgen05.commit of the two PV issuers) + 1 (tail warp)
+  uint64_t* empty = bars + 6;            // [6] 1 (tcgen05.commit after PV) + 1 (tail warp)
   uint64_t* s_full = bars + 12;          // [3] S(i) complete in TMEM buffer i % 3
   uint64_t* p_full = bars + 15;          // [3] P(i) written (8 warps)
-  uint64_t* o_full = bars + 18;          // [3] O(i) complete
-  uint64_t* b_free = bars + 21;          // [3] O(i) read by the epilogue (8 warps): the buffer may take S(i + 3)
+  uint64_t* o_full = bars + 18;          // [3] PV(i) complete: S/P buffer i % 3 may take S(i + 3)
+  uint64_t* o_rdy = bars + 21;           // [2] PV(i) complete: O buffer i & 1 may be read by the epilogue.  (Two barriers
+                                         // for one event: each must be unable to complete twice before its waiter looks --
+                                         // the next PV into O buffer i & 1 needs this epilogue's group, the next PV out of
+                                         // S/P buffer i % 3 needs the S that waits on o_full.)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -284,10 +294,11 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
     s_ctx->g = g; s_ctx->bd = bd; s_ctx->roll = roll; s_ctx->head = head;
   }
   if (warp == kWarpMma && lane == 0) {
-    for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 3); }
+    for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 2); }
     for (int i = 0; i < 3; ++i) {
-      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 8); tc::mbar_init(&o_full[i], 2); tc::mbar_init(&b_free[i], 8);
+      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 8); tc::mbar_init(&o_full[i], 1);
     }
+    tc::mbar_init(&o_rdy[0], 1); tc::mbar_init(&o_rdy[1], 1);
     tc::fence_barrier_init();
   }
   if (warp == kWarpTma) {
@@ -401,15 +412,16 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
     }
   } else if (warp == kWarpMma) {
     // ==================================================================== S = Q K^T issuer
-    // Three TMEM buffers: S(i) needs its operands (full) and buffer i % 3 back from the epilogue of window i-3 (b_free,
-    // in the middle of the softmax of window i-1).  The PV MMAs are issued by ANOTHER warp: issuing one tcgen05.mma
-    // costs this warp ~80 cycles of descriptor traffic, and an S queued behind nine PV issues would stall a whole
-    // softmax group.  No tensor-pipe ordering between S and PV is assumed; every hand-over has its mbarrier.
+    // Three S/P buffers: S(i) needs its operands (full) and buffer i % 3, which is free once PV(i-3) has read P(i-3)
+    // (o_full) -- about a PV after the softmax of window i-3 ended, i.e. S(i) is complete well before the softmax
+    // group of window i has finished window i-2.  The PV MMAs are issued by ANOTHER warp: issuing one tcgen05.mma costs
+    // the issuing warp ~100 cycles (descriptor build, R2UR, ELECT), and an S queued behind nine PV issues would stall a
+    // whole softmax group.  No tensor-pipe ordering between S and PV is assumed; every hand-over has its mbarrier.
     constexpr uint32_t idesc_s = tc::make_idesc_bf16(128, 144, 0, 0);
     for (int i = 0; i < nwin; ++i) {
       const int st = i % kStages, b = i % 3;
       tc::mbar_wait(&full[st], (i / kStages) & 1);
-      if (i >= 3) tc::mbar_wait(&b_free[b], ((i / 3) & 1) ^ 1);
+      if (i >= 3) tc::mbar_wait(&o_full[b], ((i / 3) & 1) ^ 1);
       tc::tcgen05_after_sync();
       const uint32_t aq = smem_u32(s_buf + st * kBufBytes), ak = aq + kTileBytes;
 #pragma unroll
@@ -419,32 +431,25 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       __syncwarp();
       if (trc) g_attn_trace[(i & 7) * 16 + 1] = clock64();
     }
-  } else {
-    // ==================================================================== O = P V issuers (warps 18 and 19)
-    // Issuing a tcgen05.mma costs the issuing warp ~100 cycles (descriptor build, R2UR, ELECT), so the nine K-steps of a
-    // window are split between two warps and two accumulators: keys 0..79 -> O_a, keys 80..143 -> O_b; the epilogue adds
-    // them.  Both land in score columns that are dead once P is written: O_a in [112,144), O_b in [40,72).
+  } else if (warp == kWarpPv) {
+    // ==================================================================== O = P V issuer
+    // O(i) goes to O buffer i & 1: its previous content, O(i-2), was read by the epilogue in the middle of the softmax of
+    // window i (same group), i.e. before that group arrived on p_full(i).
     constexpr uint32_t idesc_o = tc::make_idesc_bf16(128, 32, 0, 1);
-    const int part = warp - kWarpPv;
     for (int i = 0; i < nwin; ++i) {
       const int st = i % kStages, b = i % 3;
       tc::mbar_wait(&p_full[b], (i / 3) & 1);
       tc::tcgen05_after_sync();
-      if (trc && part == 0) g_attn_trace[(i & 7) * 16 + 2] = clock64();
+      if (trc) g_attn_trace[(i & 7) * 16 + 2] = clock64();
       const uint32_t av = smem_u32(s_buf + st * kBufBytes + 2 * kTileBytes);
-      const uint32_t tP = tmem_base + b * kColS;
-      if (part == 0) {
+      const uint32_t tP = tmem_base + b * kColS, tO = tmem_base + kColO + 32 * (i & 1);
 #pragma unroll
-        for (int k = 0; k < 5; ++k)                          // 16 keys = 8 packed TMEM columns / 1 KiB of V per step
-          if (tc::elect_one()) tc::umma_bf16_ts(tP + kColO, tP + 8 * k, desc_mn_sw64(av + 1024 * k), idesc_o, k);
-      } else {
-#pragma unroll
-        for (int k = 5; k < 9; ++k)                          // P of keys 80..143 sits at columns [80,112)
-          if (tc::elect_one()) tc::umma_bf16_ts(tP + kColOb, tP + 8 * k + 40, desc_mn_sw64(av + 1024 * k), idesc_o, k - 5);
-      }
-      if (tc::elect_one()) { tc::umma_commit(&o_full[b]); tc::umma_commit(&empty[st]); }
+      for (int k = 0; k < 9; ++k)                            // K = 144 keys: 16 keys = 8 packed TMEM columns / 1 KiB of V per step
+        if (tc::elect_one())                                 // P of keys 0..79 at columns [0,40), of keys 80..143 at [80,112)
+          tc::umma_bf16_ts(tO, tP + 8 * k + (k >= 5 ? 40 : 0), desc_mn_sw64(av + 1024 * k), idesc_o, k);
+      if (tc::elect_one()) { tc::umma_commit(&o_rdy[i & 1]); tc::umma_commit(&o_full[b]); tc::umma_commit(&empty[st]); }
       __syncwarp();
-      if (trc && part == 0) g_attn_trace[(i & 7) * 16 + 3] = clock64();
+      if (trc) g_attn_trace[(i & 7) * 16 + 3] = clock64();
     }
   }
   } else if (warp < kSoftmaxWarps) {
@@ -460,24 +465,17 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
 
     int tok_prev = -1;                                        // output token (x 2 + buffer class) of window i-2, or -1
 
-    // O(i) -> global (each thread 16 channels of its row = one 32-byte sector), then the TMEM buffer is released
+    // O(i) -> global (each thread 16 channels of its row = one 32-byte sector)
     auto epilogue = [&](int i, int tokc) {
-      const int b = i % 3, slot = (i >> 1) & 1;
-      tc::mbar_wait(&o_full[b], (i / 3) & 1);
+      const int slot = (i >> 1) & 1;
+      tc::mbar_wait(&o_rdy[i & 1], (i >> 1) & 1);
       tc::tcgen05_after_sync();
-      uint32_t o[16], o2[16];
-      tc::tmem_ld_32x16(tmem_base + lane_addr + b * kColS + kColO + hf * 16, o);
-      tc::tmem_ld_32x16(tmem_base + lane_addr + b * kColS + kColOb + hf * 16, o2);
+      uint32_t o[16];
+      tc::tmem_ld_32x16(tmem_base + lane_addr + kColO + 32 * (i & 1) + hf * 16, o);
       const uint32_t exs = exg + (slot * 512 + 256 + row) * 4;
       const float sum = lds_f32(exs) + lds_f32(exs + 512);
       const float inv = 1.0f / sum;
       tmem_ld_wait16(o);
-      tmem_ld_wait16(o2);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) + __uint_as_float(o2[e]));
-      tc::tcgen05_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&b_free[b]);
       if (tokc >= 0) {
         uint4 a, c;
         a.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
@@ -509,6 +507,19 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       if (trc && warp == 0) g_attn_trace[13] = clock64();
     }
     const int i_end = min(nwin, (u0 + ts + 1) * g.nLon - p0);    // windows [.., i_end) lie in tile u0 + ts
+    float bmax = -INFINITY;                                   // maximum of my part of this tile's bias row (incl. mask)
+    if (i < i_end) {
+#pragma unroll
+      for (int c = 0; c < 10; ++c) {
+        if (c < 2 * nchunk) {
+          const uint4 bb = lds128(brow + 16 * c);
+          const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            bmax = fmaxf(bmax, fmaxf(__uint_as_float(bw[e] << 16), __uint_as_float(bw[e] & 0xffff0000u)));
+        }
+      }
+    }
 #pragma unroll 1
     for (; i < i_end; i += 2) {
       const int slot = (i >> 1) & 1, b = i % 3;
@@ -524,33 +535,42 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       const uint32_t exm = exg + slot * 2048, exs = exm + 1024;
       float m;
       {
-        // ---- pass 1: maximum of S + bias over my keys (a shift mask is part of the staged bias).  One 16-column chunk
-        // in flight: a TMEM load completes in ~12 cycles, registers are what is scarce here (a spill costs an L2 trip).
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        // ---- pass 1: an UPPER BOUND of the row maximum of S + bias over my keys: max(S) + max(bias).  Softmax is
+        // invariant under the shift, and bf16 P / fp32 sums keep their relative precision over the whole exponent range,
+        // so any bound within ~100 (log2 units) of the true maximum gives the same result; this one is off by at most
+        // the spread of the bias row (the -100 of a masked key only makes the bound looser by the spread of S).  It
+        // saves the bias reads and adds of a full pass.
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          if (c < nchunk) {
-            uint32_t v[16];
-            tc::tmem_ld_32x16(tS + 16 * c, v);
-            const uint4 b0 = lds128(brow + 32 * c), b1 = lds128(brow + 32 * c + 16);
-            const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            tmem_ld_wait16(v);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(tS + 32 * c, v);
+          tmem_ld_wait32(v);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float s0 = __uint_as_float(v[2 * e]), s1 = __uint_as_float(v[2 * e + 1]);
-              add_bias2(bw[e], s0, s1);
-              mx0 = fmaxf(mx0, s0);
-              mx1 = fmaxf(mx1, s1);
-            }
+          for (int e = 0; e < 32; e += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(v[e]));
+            mx1 = fmaxf(mx1, __uint_as_float(v[e + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(v[e + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
           }
         }
-        m = fmaxf(mx0, mx1);
+        if (hf == 0) {
+          uint32_t v[16];
+          tc::tmem_ld_32x16(tS + 64, v);
+          tmem_ld_wait16(v);
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(v[e]));
+            mx1 = fmaxf(mx1, __uint_as_float(v[e + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(v[e + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
+          }
+        }
+        mx0 = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) + bmax;
+        m = mx0;
         sts_f32(exm + (hf * 128 + row) * 4, m);
       }
       if (trw) tr[5] = clock64();
-      // ---- the epilogue of window i-2 fills the wait for the partner warp's maximum
-      if (i >= 2) epilogue(i - 2, tok_prev);
-      if (trw) tr[8] = clock64();
       {
         named_bar(1 + grp * 4 + q, 64);                       // the two warps of this lane quarter
         m = fmaxf(m, lds_f32(exm + ((hf ^ 1) * 128 + row) * 4));
@@ -560,6 +580,9 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
         float sm0 = 0.f, sm1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
+          // the epilogue of window i-2 sits inside pass 2: PV(i-2), issued when this group finished window i-2, has
+          // completed by now, and O buffer i & 1 is drained before this group's arrival on p_full lets PV(i) refill it
+          if (c == 2 && i >= 2) epilogue(i - 2, tok_prev);
           if (c < nchunk) {
             uint32_t v[16];
             tc::tmem_ld_32x16(tS + 16 * c, v);
