@@ -41,3 +41,36 @@ def test_rollout_matches_manual_chain():
             prev = (o.clone(), os_.clone())
             n += 1
         assert n == 3
+
+
+def test_ort_like_session_equals_rollout_step_and_chains_on_device():
+    """InferenceSession.run (the onnxruntime call shape of inference/inference_singleOutput.py:146-147) must return what
+    Rollout.step returns for the same numpy fields, and feeding its outputs back (the scripts' chained-forecast loop) must
+    equal re-uploading them."""
+    import numpy as np
+    from models.pangu_model import PanguModel
+    from pangu_b200.rollout import Rollout
+    from pangu_b200.session import InferenceSession
+    model = PanguModel(device="cpu")
+    model.load_state_dict(orc.synth_params(seed=0), strict=True)
+    model = model.cuda().eval().set_compute_dtype("bf16")
+    inp, inp_s, stats, maps, const_h = orc.synth_inputs(seed=1)
+    g = torch.Generator().manual_seed(11)
+    last = (torch.randn(1, 4, 1, 1, generator=g), torch.rand(1, 4, 1, 1, generator=g) + 0.5,
+            torch.randn(1, 5, 13, 1, 1, generator=g), torch.rand(1, 5, 13, 1, 1, generator=g) + 0.5)
+    x = inp.numpy().astype(np.float32).squeeze()              # as the scripts prepare them: [5,13,721,1440], [4,721,1440]
+    xs = inp_s.numpy().astype(np.float32).squeeze()
+    sess = InferenceSession(model, stats, last, maps, const_h)
+    out, out_s = sess.run(None, {"input": x, "input_surface": xs})
+    assert out.shape == (5, 13, 721, 1440) and out_s.shape == (4, 721, 1440) and out.dtype == np.float32
+    assert sess.h2d_bytes == x.nbytes + xs.nbytes
+    want, want_s = Rollout(model, stats, last, maps, const_h, graph=False).step(inp.cuda()[0], inp_s.cuda()[0])
+    assert np.array_equal(out, want[0].cpu().numpy()) and np.array_equal(out_s, want_s[0].cpu().numpy())
+    # chained call on the returned arrays: stays on the device ...
+    out2, out2_s = sess.run(None, {"input": out, "input_surface": out_s})
+    assert sess.h2d_bytes == 0
+    # ... and equals a call on copies of them (which goes through the host)
+    out2b, out2b_s = sess.run(["output_surface", "output"], {"input": out.copy(), "input_surface": out_s.copy()})[::-1]
+    assert sess.h2d_bytes > 0
+    assert np.array_equal(out2, out2b) and np.array_equal(out2_s, out2b_s)
+    assert np.isfinite(out2).all() and not np.array_equal(out2, out)

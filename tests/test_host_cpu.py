@@ -88,6 +88,23 @@ def test_no_cpu_fallback():
         m(inp, inp_s, None, None, None)
 
 
+def test_ort_like_session_surface_and_no_cpu_path():
+    """pangu_b200.session.InferenceSession mirrors the onnxruntime call of inference/inference_singleOutput.py:146-147;
+    without a CUDA model it must refuse to construct (no CPU forecast path)."""
+    from models.pangu_model import PanguModel
+    from pangu_b200.abi import PanguError
+    from pangu_b200.session import InferenceSession
+    m = PanguModel(device="cpu").eval()
+    z = torch.zeros(1)
+    with pytest.raises(PanguError, match="CUDA"):
+        InferenceSession(m, (z, z, z, z), (z, z, z, z), z, z)
+    s = InferenceSession.__new__(InferenceSession)               # the metadata surface needs no device
+    assert [(a.name, a.shape) for a in s.get_inputs()] == [("input", [5, 13, 721, 1440]), ("input_surface", [4, 721, 1440])]
+    assert [a.name for a in s.get_outputs()] == ["output", "output_surface"]
+    with pytest.raises(PanguError, match="float32"):
+        InferenceSession._as_f32(__import__("numpy").zeros((4, 721, 1440)), (4, 721, 1440), "input_surface")
+
+
 def test_product_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "pangu-pytorch-demo_b200")
     for dp, _, files in os.walk(pkg):
