@@ -306,6 +306,15 @@ int pangu_weighted_l1_loss(const float* out, const float* target, const float* m
                            const float* weight, int32_t planes, int32_t planes_per_var, int64_t plane_elems,
                            float scale, float* loss_sum, float* d_out, void* stream);
 
+/* Latitude-weighted verification scores in one pass (era5_data/score.py:126-161
+ * weighted_rmse_torch_channels with its optional mask, :181-201 weighted_acc_torch_channels).  pred / target fp32
+ * [planes][H][W]; mask [H][W] or NULL (= 1); clim [planes] or NULL (= 0): the climatology subtracted from both fields for the
+ * anomaly correlation (models/pangu_sample.py:549-556); lat_weight [H] = the reference's latitude_weighting_factor_torch.
+ * sums [planes][5] fp64 (zeroed by the call) = { sum w m (p-t)^2, sum w m, sum w a b, sum w a^2, sum w b^2 } with a = p - clim,
+ * b = t - clim; RMSE = sqrt(sums[0] / (H W)) without a mask, sqrt(sums[0] / sums[1]) with one; ACC = sums[2] / sqrt(sums[3] sums[4]). */
+int pangu_lat_weighted_score_sums(const float* pred, const float* target, const float* mask, const float* clim,
+                                  const float* lat_weight, int32_t planes, int32_t H, int32_t W, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

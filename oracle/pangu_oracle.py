@@ -408,6 +408,35 @@ def grads(fn, tensors, gouts):
     return {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(leaves, gs)}
 
 
+# ---------------------------------------------------------------------------------------------
+# Verification scores (era5_data/score.py), the step after the forward in models/pangu_sample.py:test()
+# ---------------------------------------------------------------------------------------------
+def latitude_weights(num_lat: int) -> torch.Tensor:
+    """era5_data/score.py:99-106 (lat, latitude_weighting_factor_torch): fp32, the reference's constant 3.1416."""
+    j = torch.arange(start=0, end=num_lat)
+    lat = 90. - j * 180. / float(num_lat - 1)
+    c = torch.cos(3.1416 / 180. * lat)
+    return num_lat * c / torch.sum(c)
+
+
+def weighted_rmse_channels(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor = None) -> torch.Tensor:
+    """era5_data/score.py:126-161 weighted_rmse_torch_channels: [n,c,h,w] or [c,h,w] -> per-channel latitude-weighted RMSE;
+    with a mask the weighted squared error is summed over the valid points and divided by their summed weight."""
+    w = latitude_weights(pred.shape[-2]).reshape(-1, 1)
+    se = (pred - target) ** 2.
+    if mask is None:
+        return torch.sqrt(torch.mean(w * se, dim=(-1, -2)))
+    m = mask.reshape((1,) * (pred.dim() - 2) + tuple(mask.shape))
+    return torch.sqrt((w * m * se).sum(dim=(-1, -2)) / (w * m).sum(dim=(-1, -2)))
+
+
+def weighted_acc_channels(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """era5_data/score.py:181-201 weighted_acc_torch_channels (inputs are anomalies, models/pangu_sample.py:549-556)."""
+    w = latitude_weights(pred.shape[-2]).reshape(-1, 1)
+    return torch.sum(w * pred * target, dim=(-1, -2)) / torch.sqrt(
+        torch.sum(w * pred * pred, dim=(-1, -2)) * torch.sum(w * target * target, dim=(-1, -2)))
+
+
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a = a.double().flatten()
     b = b.double().flatten()

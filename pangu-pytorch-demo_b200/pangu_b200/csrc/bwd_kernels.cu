@@ -249,6 +249,70 @@ weighted_l1_loss_kernel(const float4* __restrict__ out, const float4* __restrict
   }
 }
 
+
+// Latitude-weighted verification scores in one pass over prediction and target (era5_data/score.py:126-161
+// weighted_rmse_torch_channels incl. its optional mask, :181-201 weighted_acc_torch_channels; the reference makes ~10
+// full-tensor passes per score and calls them once per variable, models/pangu_sample.py:531-569).  For every plane p
+// (one variable at one level, [H][W]) five sums, with w = latitude weight of the row, m = mask (or 1), a = pred - clim[p],
+// b = target - clim[p]:   { sum w m (pred-target)^2,  sum w m,  sum w a b,  sum w a^2,  sum w b^2 }.
+// Grid (planes, row chunks); fp32 partial sums per thread (a few hundred terms), fp64 from the warp reduction on.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+lat_weighted_score_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ mask,
+                          const float* __restrict__ clim, const float* __restrict__ lat_w, int H, int W,
+                          double* __restrict__ sums) {
+  const int plane = blockIdx.x;
+  const int rows_per = (H + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(H, r0 + rows_per);
+  const float c = clim != nullptr ? __ldg(clim + plane) : 0.f;
+  const float* pp = pred + (long long)plane * H * W;
+  const float* tp = target + (long long)plane * H * W;
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = r0; r < r1; ++r) {
+    const float w = __ldg(lat_w + r);
+    float e2 = 0.f, wm = 0.f, ab = 0.f, aa = 0.f, bb = 0.f;
+    for (int x = threadIdx.x * VEC; x < W; x += blockDim.x * VEC) {
+      float pv[VEC], tv[VEC], mv[VEC];
+      if constexpr (VEC == 4) {                                 // W % 4 == 0 and 16-byte aligned bases (checked by the host)
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(pp + (long long)r * W + x));
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(tp + (long long)r * W + x));
+        pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
+        tv[0] = t4.x; tv[1] = t4.y; tv[2] = t4.z; tv[3] = t4.w;
+        if (mask != nullptr) {
+          const float4 m4 = __ldg(reinterpret_cast<const float4*>(mask + (long long)r * W + x));
+          mv[0] = m4.x; mv[1] = m4.y; mv[2] = m4.z; mv[3] = m4.w;
+        } else { mv[0] = mv[1] = mv[2] = mv[3] = 1.f; }
+      } else {
+        pv[0] = __ldg(pp + (long long)r * W + x); tv[0] = __ldg(tp + (long long)r * W + x);
+        mv[0] = mask != nullptr ? __ldg(mask + (long long)r * W + x) : 1.f;
+      }
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float d = pv[i] - tv[i], a = pv[i] - c, b = tv[i] - c;
+        e2 = fmaf(mv[i] * d, d, e2); wm += mv[i];
+        ab = fmaf(a, b, ab); aa = fmaf(a, a, aa); bb = fmaf(b, b, bb);
+      }
+    }
+    acc[0] = fmaf(w, e2, acc[0]); acc[1] = fmaf(w, wm, acc[1]);
+    acc[2] = fmaf(w, ab, acc[2]); acc[3] = fmaf(w, aa, acc[3]); acc[4] = fmaf(w, bb, acc[4]);
+  }
+  __shared__ double part[8][5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    double v = (double)acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double v = 0.0;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) v += part[wq][threadIdx.x];
+    atomicAdd(sums + plane * 5 + threadIdx.x, v);
+  }
+}
+
 static unsigned row_grid(long long M, int warps_per_cta) {
   long long want = (M + warps_per_cta - 1) / warps_per_cta;
   const long long cap = 148LL * 8;
@@ -356,4 +420,19 @@ extern "C" int pangu_weighted_l1_loss(const float* out, const float* target, con
   weighted_l1_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>((const float4*)out, (const float4*)target, mean, stdv, weight,
                                                               planes_per_var, plane_elems / 4, total4, scale, loss_sum, (float4*)d_out);
   return check_launch("weighted_l1_loss");
+}
+
+extern "C" int pangu_lat_weighted_score_sums(const float* pred, const float* target, const float* mask, const float* clim,
+                                             const float* lat_weight, int32_t planes, int32_t H, int32_t W, double* sums,
+                                             void* stream) {
+  if (!pred || !target || !lat_weight || !sums || planes <= 0 || H <= 0 || W <= 0) { set_error("lat_weighted_score_sums: bad argument"); return PANGU_ERR_BAD_ARG; }
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 5 * planes, as_stream(stream));
+  if (e != cudaSuccess) { set_error("lat_weighted_score_sums: cudaMemsetAsync: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
+  int chunks = (148 * 8 + planes - 1) / planes;                 // ~8 CTAs per SM in total
+  if (chunks > H) chunks = H;
+  const dim3 grid((unsigned)planes, (unsigned)chunks);
+  const bool vec = W % 4 == 0 && (((uintptr_t)pred | (uintptr_t)target | (uintptr_t)mask) & 15) == 0;
+  if (vec) lat_weighted_score_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(pred, target, mask, clim, lat_weight, H, W, sums);
+  else     lat_weighted_score_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(pred, target, mask, clim, lat_weight, H, W, sums);
+  return check_launch("lat_weighted_score_sums");
 }

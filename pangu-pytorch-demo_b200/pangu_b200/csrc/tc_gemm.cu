@@ -419,7 +419,8 @@ static int launch_gemm_t(const void* A, long long lda, const void* W, GemmArgs& 
 }  // namespace tc
 
 int launch_tc_linear_pair(const void* A, long long lda, const void* W, const float* bias, void* out,
-                          long long ldo, long long M, int K, int N, int act, int out_dtype, void* shadow, cudaStream_t st);
+                          long long ldo, long long M, int K, int N, int act, int out_dtype, void* shadow, cudaStream_t st,
+                          void* aux = nullptr, int aux_mode = 0, float* colsum = nullptr);
 
 // A2 != nullptr: the A operand is the channel concat cat(A[M,K1], A2[M,K-K1]) (models/pangu_model.py:98), read
 // from the two tensors directly.  shadow != nullptr (fp32 output only): also write a bf16 copy of the output.

@@ -30,7 +30,26 @@ struct Gemm2Args {
   long long ldo;
   int out_dtype, act;
   __nv_bfloat16* shadow;      // optional bf16 copy of an fp32 output
+  // Fine-tune fusions on a bf16 output (aux bf16 [M, N], row pitch ldo):
+  //   G2_AUX_PRE_OUT : aux <- A.W^T + bias (the pre-activation the backward needs), out <- act(...) in the same pass;
+  //   G2_AUX_GELU_BWD: out <- (A.W^T + bias) * GELU'(aux), colsum[n] += sum_m out[m, n] (bias gradient) -- the dgrad of
+  //                    Mlp.linear2 fused with the GELU backward (models/layers.py:313).
+  __nv_bfloat16* aux;
+  float* colsum;
+  int aux_mode;
 };
+enum { G2_AUX_NONE = 0, G2_AUX_PRE_OUT = 1, G2_AUX_GELU_BWD = 2 };
+
+// d/dx of gelu_fast: 0.5 (1 + t) + 0.5 x (1 - t^2) u'(x),  t = tanh(u), u = x (k1 + k3 x^2 + k5 x^4).
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
+  const float x2 = xc * xc;
+  const float p = fmaf(x2, fmaf(x2, -3.51519787e-4f, 3.70056658e-2f), 7.97507861e-1f);
+  const float du = fmaf(x2, fmaf(x2, 5.0f * -3.51519787e-4f, 3.0f * 3.70056658e-2f), 7.97507861e-1f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xc * p));
+  return fmaf(0.5f * xc * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
+}
 
 template <int KB>                                 // K / 64
 struct Gemm2Cfg {
@@ -158,6 +177,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int acc = 0;
     uint32_t tphase = 0;
     uint32_t v[32];
+    // GELU_BWD: the aux (pre-activation) chunk of this warp is fetched ONE CHUNK AHEAD into registers, in the
+    // row-contiguous pattern of the write-out loop (lane -> row (lane>>2)+8i, 16-byte column group lane&3).
+    const bool gelu_bwd = a.aux_mode == G2_AUX_GELU_BWD;
+    uint4 pre_cur[4], pre_nxt[4];
+    auto load_aux = [&](int pt_, int nt_, int c_, uint4 (&dst)[4]) {
+      const long long mb = (long long)pt_ * 256 + rank * 128 + q * 32;
+      const int n_ = nt_ * G2_BN + c_ * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long m = mb + (lane >> 2) + 8 * i;
+        dst[i] = (pt_ < a.pair_tiles && m < a.M)
+                     ? __ldg(reinterpret_cast<const uint4*>(a.aux + m * a.ldo + n_ + (lane & 3) * 8)) : make_uint4(0, 0, 0, 0);
+      }
+    };
+    if (gelu_bwd) load_aux(pair0, 0, hf, pre_cur);
     for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
       const long long m_base = (long long)pt * 256 + rank * 128 + q * 32;
       for (int nt = 0; nt < a.n_tiles; ++nt) {
@@ -167,6 +201,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t taddr = lane_base + acc * G2_BN;
 #pragma unroll 1
         for (int c = hf; c < G2_BN / 32; c += 2) {
+          if (gelu_bwd) {
+            int c2 = c + 2, nt2 = nt, pt2 = pt;
+            if (c2 >= G2_BN / 32) { c2 = hf; if (++nt2 == a.n_tiles) { nt2 = 0; pt2 += npairs; } }
+            load_aux(pt2, nt2, c2, pre_nxt);
+          }
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
           const int n = nt * G2_BN + c * 32;
@@ -180,6 +219,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
             }
           }
+          if (a.aux_mode == G2_AUX_PRE_OUT) {     // the pre-activation tile, staged in the second half of the warp's 4 KiB
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              *reinterpret_cast<uint4*>(stg + 2048 + g2_stg_b16(lane, cc)) =
+                  make_uint4(pack_bf16(f[8 * cc], f[8 * cc + 1]), pack_bf16(f[8 * cc + 2], f[8 * cc + 3]),
+                             pack_bf16(f[8 * cc + 4], f[8 * cc + 5]), pack_bf16(f[8 * cc + 6], f[8 * cc + 7]));
+          }
           if (a.act == PANGU_ACT_GELU_ERF) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
@@ -192,12 +238,57 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                              pack_bf16(f[8 * cc + 4], f[8 * cc + 5]), pack_bf16(f[8 * cc + 6], f[8 * cc + 7]));
             __syncwarp();
             __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
+            if (!gelu_bwd) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = (lane >> 2) + 8 * i, cc = lane & 3;
-              const uint4 val = *reinterpret_cast<const uint4*>(stg + g2_stg_b16(rr, cc));
-              const long long m = m_base + rr;
-              if (m < a.M) *reinterpret_cast<uint4*>(out + m * a.ldo + n + cc * 8) = val;
+              for (int i = 0; i < 4; ++i) {
+                const int rr = (lane >> 2) + 8 * i, cc = lane & 3;
+                const uint4 val = *reinterpret_cast<const uint4*>(stg + g2_stg_b16(rr, cc));
+                const long long m = m_base + rr;
+                if (m < a.M) {
+                  *reinterpret_cast<uint4*>(out + m * a.ldo + n + cc * 8) = val;
+                  if (a.aux_mode == G2_AUX_PRE_OUT)
+                    *reinterpret_cast<uint4*>(a.aux + m * a.ldo + n + cc * 8) =
+                        *reinterpret_cast<const uint4*>(stg + 2048 + g2_stg_b16(rr, cc));
+                }
+              }
+            } else {
+              float cs[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) cs[j] = 0.f;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = (lane >> 2) + 8 * i, cc = lane & 3;
+                uint4 val = *reinterpret_cast<const uint4*>(stg + g2_stg_b16(rr, cc));
+                __nv_bfloat162* gp = reinterpret_cast<__nv_bfloat162*>(&val);
+                const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&pre_cur[i]);
+                const long long m = m_base + rr;
+                if (m < a.M) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 gf = __bfloat1622float2(gp[j]), xf = __bfloat1622float2(xp[j]);
+                    const __nv_bfloat162 o = __floats2bfloat162_rn(gf.x * gelu_fast_grad(xf.x), gf.y * gelu_fast_grad(xf.y));
+                    gp[j] = o;
+                    const float2 of = __bfloat1622float2(o);     // sum what the wgrad GEMM will see
+                    cs[2 * j] += of.x; cs[2 * j + 1] += of.y;
+                  }
+                  *reinterpret_cast<uint4*>(out + m * a.ldo + n + cc * 8) = val;
+                }
+              }
+              if (a.colsum != nullptr) {                          // 8 lanes share a column group: reduce, then 2 x red.v4
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 4);
+                  cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+                  cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+                }
+                if (lane < 4) {
+                  float* dst = a.colsum + n + lane * 8;
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]), "f"(cs[3]) : "memory");
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(cs[4]), "f"(cs[5]), "f"(cs[6]), "f"(cs[7]) : "memory");
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) pre_cur[i] = pre_nxt[i];
             }
           } else {
 #pragma unroll
@@ -260,11 +351,14 @@ static int launch_gemm2_t(const void* A, long long lda, const void* W, Gemm2Args
 // Returns PANGU_ERR_UNSUPPORTED (without touching the error string) when the shape is not one this kernel
 // covers; the caller then uses the generic tiled GEMM.
 int launch_tc_linear_pair(const void* A, long long lda, const void* W, const float* bias, void* out,
-                          long long ldo, long long M, int K, int N, int act, int out_dtype, void* shadow, cudaStream_t st) {
+                          long long ldo, long long M, int K, int N, int act, int out_dtype, void* shadow, cudaStream_t st,
+                          void* aux, int aux_mode, float* colsum) {
   if ((K != 192 && K != 384) || N % tc::G2_BN != 0 || M < 2048 || lda % 8 || ldo % 8) return PANGU_ERR_UNSUPPORTED;
+  if (aux_mode != tc::G2_AUX_NONE && (aux == nullptr || out_dtype != PANGU_BF16)) { set_error("linear(bf16): aux modes need an aux tensor and a bf16 output"); return PANGU_ERR_BAD_ARG; }
   tc::Gemm2Args a{};
   a.M = M; a.N = N; a.bias = bias; a.out = out; a.ldo = ldo; a.out_dtype = out_dtype; a.act = act;
   a.shadow = reinterpret_cast<__nv_bfloat16*>(shadow);
+  a.aux = reinterpret_cast<__nv_bfloat16*>(aux); a.aux_mode = aux_mode; a.colsum = colsum;
   return K == 192 ? tc::launch_gemm2_t<3>(A, lda, W, a, st) : tc::launch_gemm2_t<6>(A, lda, W, a, st);
 }
 

@@ -1,0 +1,73 @@
+"""Latitude-weighted RMSE / ACC: oracle pinned to outputs of the reference's era5_data/score.py
+(tests/golden/make_score_golden.py), CUDA one-pass kernel against the oracle and the goldens."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pangu_oracle as orc
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_score_goldens.npz"))
+T = lambda k: torch.from_numpy(G[k])
+
+
+def test_oracle_scores_match_reference_goldens():
+    assert np.array_equal(orc.latitude_weights(33).numpy(), G["lat_weight"])               # same fp32 expression
+    for p, t, r, rm, a in (("pred3", "targ3", "rmse3", "rmse3_masked", "acc3"), ("pred4", "targ4", "rmse4", "rmse4_masked", "acc4")):
+        np.testing.assert_allclose(orc.weighted_rmse_channels(T(p), T(t)).numpy(), G[r], rtol=2e-6)
+        np.testing.assert_allclose(orc.weighted_rmse_channels(T(p), T(t), T("mask")).numpy(), G[rm], rtol=2e-6)
+        np.testing.assert_allclose(orc.weighted_acc_channels(T(p), T(t)).numpy(), G[a], rtol=2e-6)
+    np.testing.assert_allclose(orc.weighted_rmse_channels(T("pred4"), T("targ4")).mean(0).numpy(), G["rmse4_mean"], rtol=2e-6)
+
+
+def test_score_module_refuses_cpu_tensors():
+    from pangu_b200 import score
+    from pangu_b200.abi import PanguError
+    with pytest.raises(PanguError, match="CUDA"):
+        score.weighted_rmse_torch_channels(T("pred3"), T("targ3"))
+
+
+@pytest.mark.gpu
+def test_cuda_scores_match_reference_goldens():
+    from pangu_b200 import score
+    assert torch.equal(score.latitude_weights(33, "cuda").cpu(), T("lat_weight"))
+    for p, t, r, rm, a in (("pred3", "targ3", "rmse3", "rmse3_masked", "acc3"), ("pred4", "targ4", "rmse4", "rmse4_masked", "acc4")):
+        pc, tc = T(p).cuda(), T(t).cuda()
+        np.testing.assert_allclose(score.weighted_rmse_torch_channels(pc, tc).cpu().numpy(), G[r], rtol=1e-5)   # tolerance: fp32 sums
+        np.testing.assert_allclose(score.weighted_rmse_torch_channels(pc, tc, T("mask").cuda()).cpu().numpy(), G[rm], rtol=1e-5)
+        np.testing.assert_allclose(score.weighted_acc_torch_channels(pc, tc).cpu().numpy(), G[a], rtol=1e-5)
+    np.testing.assert_allclose(score.weighted_rmse_torch(T("pred4").cuda(), T("targ4").cuda()).cpu().numpy(), G["rmse4_mean"], rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_cuda_scores_full_resolution_against_the_oracle():
+    """The 69 planes of one forecast (5 x 13 upper-air + 4 surface) at 721 x 1440, with climatology and mask."""
+    from pangu_b200 import score
+    g = torch.Generator().manual_seed(5)
+    pred = torch.randn(69, 721, 1440, generator=g) * 2.0 + 3.0
+    targ = pred + 0.3 * torch.randn(69, 721, 1440, generator=g)
+    clim = torch.randn(69, generator=g) + 3.0
+    mask = (torch.rand(721, 1440, generator=g) > 0.25).float()
+    pc, tc = pred.cuda(), targ.cuda()
+    rmse, acc = score.scores(pc, tc, clim=clim.cuda())
+    rmse_m, _ = score.scores(pc, tc, mask=mask.cuda())
+    a, b = pred.double() - clim.double()[:, None, None], targ.double() - clim.double()[:, None, None]
+    np.testing.assert_allclose(rmse.cpu().numpy(), orc.weighted_rmse_channels(pred.double(), targ.double()).numpy(), rtol=1e-5)
+    np.testing.assert_allclose(rmse_m.cpu().numpy(), orc.weighted_rmse_channels(pred.double(), targ.double(), mask.double()).numpy(), rtol=1e-5)
+    np.testing.assert_allclose(acc.cpu().numpy(), orc.weighted_acc_channels(a, b).numpy(), rtol=1e-5)
+    # size-independent properties: a perfect forecast has RMSE 0 and ACC 1; scaling the error scales the RMSE
+    r0, a0 = score.scores(pc, pc, clim=clim.cuda())
+    assert float(r0.abs().max()) == 0.0 and float((a0 - 1).abs().max()) <= 1e-6
+    r2, _ = score.scores(pc, pc + 2.0 * (tc - pc))
+    np.testing.assert_allclose(r2.cpu().numpy(), 2.0 * rmse.cpu().numpy(), rtol=1e-5)
+    # one pass: 2 x 286 MB read
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        score.score_sums(pc, tc, clim=clim.cuda())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print("lat_weighted_score_sums: %.3f ms, %.0f GB/s" % (ms, 2 * pred.numel() * 4 / ms / 1e6))
