@@ -240,6 +240,19 @@ int pangu_concat_cast_bf16(const float* a, const float* b, void* out, int64_t n,
 int pangu_linear_bf16_add(const void* A, int64_t lda, const void* W, const float* bias, const float* addend,
                           float* out, int64_t ldo, int64_t M, int32_t K, int32_t N, void* stream);
 
+/* bf16 linear with a second bf16 tensor `aux` [M, N] (row pitch ldo) attached to its epilogue -- the two Mlp fusions of
+ * the fine-tune step (models/layers.py:311-317 and its autograd):
+ *   PANGU_AUX_PRE_OUT : aux <- A.W^T + bias, out <- act(A.W^T + bias): Mlp.linear1 leaves the pre-activation the backward
+ *                       needs and the GELU output in ONE pass;
+ *   PANGU_AUX_GELU_BWD: out <- (A.W^T + bias) * GELU'(aux), colsum[n] += sum_m out[m, n] (fp32, or NULL): the dgrad of
+ *                       Mlp.linear2 fused with the GELU backward and linear1's bias gradient.
+ * Shapes of the CTA-pair GEMM only (K in {192, 384}, N % 192 == 0, M >= 2048); PANGU_ERR_UNSUPPORTED otherwise (the
+ * caller then runs the separate kernels). */
+typedef enum { PANGU_AUX_PRE_OUT = 1, PANGU_AUX_GELU_BWD = 2 } pangu_aux_mode;
+int pangu_linear_bf16_aux(const void* A, int64_t lda, const void* W, const float* bias, void* out, void* aux,
+                          int64_t ldo, int64_t M, int32_t K, int32_t N, int act, int aux_mode, float* colsum,
+                          void* stream);
+
 /* dW[n_out, k_in] += dY[M, n_out]^T . X[M, k_in] -- weight gradient of nn.Linear / Conv1d(k=1)
  * (models/layers.py:88,113,312,315,419,481,522,542,566,591,608).  dY, X bf16 row-major [tokens, channels] exactly as
  * the passes leave them (read MN-major by tcgen05.mma; no transposes), dW fp32 with row pitch ldw.  Split over

@@ -83,8 +83,7 @@ def block_forward_train(blk, x0, x0b, Z, H, W, roll, s1, s2):
     sv["x1b"] = x1b
     if s2 != 0.0:
         w1, b1 = wc.bf16("m1", mlp.linear1.weight), f(mlp.linear1.bias)
-        h_pre = ops.linear(x1b, w1, b1)
-        h = ops.linear(x1b, w1, b1, act=PF.ACT_GELU)                    # second pass of the GEMM beats an elementwise pass
+        h_pre, h = ops.linear_gelu_pre(x1b, w1, b1)                     # one GEMM pass leaves both (aux epilogue)
         y2 = ops.linear(h, wc.bf16("m2", mlp.linear2.weight), f(mlp.linear2.bias), out_dtype=F32)
         gam2, bet2 = PF._affine(blk.norm2, s2)
         x2, x2b = ops.ln_residual(y2, gam2, bet2, residual=x1, want_bf16=True, eps=blk.norm2.eps)
@@ -114,10 +113,9 @@ def block_backward(blk, sv, Z, H, W, roll, s1, s2, g2):
         dg2, db2n, db2 = _zeros(C, dev), _zeros(C, dev), _zeros(C, dev)
         dy2 = ops.ln_backward(g2, sv["y2"], f(blk.norm2.weight), scale=s2, dgamma=dg2, dbeta=db2n, dcolsum=db2, eps=blk.norm2.eps)
         dw2 = ops.linear_wgrad(dy2, sv["h"])
-        dh = ops.linear(dy2, _wT(wc, "m2", mlp.linear2.weight), None)   # [N, 4C] bf16
-        del dy2
         db1 = _zeros(4 * C, dev)
-        ops.gelu_backward_bf16(dh, sv["h_pre"], db1)                    # dh <- dh * gelu'(h_pre)
+        dh = ops.linear_gelu_backward(dy2, _wT(wc, "m2", mlp.linear2.weight), sv["h_pre"], db1)   # [N, 4C] bf16, * gelu'(h_pre)
+        del dy2
         dw1 = ops.linear_wgrad(dh, x1b)
         g1 = ops.linear_add(dh, _wT(wc, "m1", mlp.linear1.weight), None, addend=g2)
         del dh

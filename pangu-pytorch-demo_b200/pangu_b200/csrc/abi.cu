@@ -41,6 +41,10 @@ int launch_tc_linear(const void* A, long long lda, const void* W, const float* b
 int launch_tc_linear_ln(const void* A, long long lda, const void* W, const float* bias,
                         const float* gamma, const float* beta, const float* residual, float* x_out,
                         void* x_out_bf16, long long M, int K, int C, float eps, cudaStream_t st);
+// tc_gemm2.cu
+int launch_tc_linear_pair(const void* A, long long lda, const void* W, const float* bias, void* out,
+                          long long ldo, long long M, int K, int N, int act, int out_dtype, void* shadow, cudaStream_t st,
+                          void* aux, int aux_mode, float* colsum);
 // tc_mlp.cu
 int launch_tc_mlp(const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
                   const float* gamma, const float* beta, const float* residual, float* x_out,
@@ -88,6 +92,18 @@ extern "C" int pangu_linear_bf16_ex(const void* A, int64_t lda, const void* A2, 
   if (!A || !W || !out || M < 0 || K <= 0 || N <= 0) { set_error("linear_ex: bad argument"); return PANGU_ERR_BAD_ARG; }
   if (act != PANGU_ACT_NONE && act != PANGU_ACT_GELU_ERF) { set_error("linear_ex: unknown activation %d", act); return PANGU_ERR_BAD_ARG; }
   return launch_tc_linear(A, lda, W, bias, out, ldo, M, K, N, act, out_dtype, as_stream(stream), out_bf16_shadow, A2, lda2, K1);
+}
+
+extern "C" int pangu_linear_bf16_aux(const void* A, int64_t lda, const void* W, const float* bias, void* out, void* aux,
+                                     int64_t ldo, int64_t M, int32_t K, int32_t N, int act, int aux_mode, float* colsum,
+                                     void* stream) {
+  if (!A || !W || !out || !aux || M < 0 || K <= 0 || N <= 0) { set_error("linear_bf16_aux: bad argument"); return PANGU_ERR_BAD_ARG; }
+  if (aux_mode != PANGU_AUX_PRE_OUT && aux_mode != PANGU_AUX_GELU_BWD) { set_error("linear_bf16_aux: unknown aux mode %d", aux_mode); return PANGU_ERR_BAD_ARG; }
+  if (act != PANGU_ACT_NONE && act != PANGU_ACT_GELU_ERF) { set_error("linear_bf16_aux: unknown activation %d", act); return PANGU_ERR_BAD_ARG; }
+  if (M == 0) return PANGU_OK;
+  const int rc = launch_tc_linear_pair(A, lda, W, bias, out, ldo, M, K, N, act, PANGU_BF16, nullptr, as_stream(stream), aux, aux_mode, colsum);
+  if (rc == PANGU_ERR_UNSUPPORTED) set_error("linear_bf16_aux: shape M=%lld K=%d N=%d is not covered by the CTA-pair GEMM (K in {192,384}, N %% 192 == 0, M >= 2048)", (long long)M, K, N);
+  return rc;
 }
 
 extern "C" int pangu_ln_residual(const void* y, int y_dtype, const float* gamma, const float* beta,

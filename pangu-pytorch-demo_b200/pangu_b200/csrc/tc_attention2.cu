@@ -43,6 +43,7 @@ using attn::mma_bf16;
 using attn::tile_off;
 using tc::pack_bf16;
 using tc::smem_u32;
+using tc::prefetch_l2_bulk;
 
 constexpr int kSoftmaxWarps = 16;
 constexpr int kTailWarps = 4;
@@ -136,9 +137,6 @@ __device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
 }
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 struct Maps {

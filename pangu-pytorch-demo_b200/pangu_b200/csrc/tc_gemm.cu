@@ -201,6 +201,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long m_base = (long long)(tile / a.n_tiles) * BM + q * 32;
       const int n0 = (tile % a.n_tiles) * BN;
       if constexpr (LN) { ln.m_base = m_base; ln.prefetch(); }     // residual tiles fly while the MMAs finish
+      if (!LN && a.addend != nullptr && a.out_dtype != PANGU_BF16) {
+        // dgrad + residual-gradient add: this tile's addend rows go to L2 while its (long-K) main loop runs, so the
+        // loads of the write-out loop below are L2 hits (lane -> row, warp half -> half of the BN columns)
+        const long long m = m_base + lane;
+        if (m < a.M) prefetch_l2_bulk(a.addend + m * a.ldo + n0 + hf * (BN / 2), (BN / 2) * 4);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tcgen05_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;

@@ -21,6 +21,7 @@ constexpr int kG2Threads = 384;
 constexpr int kG2EpiWarps = 8;
 constexpr int G2_BN = 192;                        // N tile (per CTA pair); each CTA holds 96 rows of W
 constexpr int G2_SLOT = (G2_BN / 2) * 128;        // one [96 x 64] bf16 k-block of this CTA's W half: 12 KiB
+constexpr int G2_MAX_N = 1536;                    // widest linear of the model (Mlp.linear1 at C = 384)
 
 struct Gemm2Args {
   long long M;
@@ -40,15 +41,24 @@ struct Gemm2Args {
 };
 enum { G2_AUX_NONE = 0, G2_AUX_PRE_OUT = 1, G2_AUX_GELU_BWD = 2 };
 
-// d/dx of gelu_fast: 0.5 (1 + t) + 0.5 x (1 - t^2) u'(x),  t = tanh(u), u = x (k1 + k3 x^2 + k5 x^4).
-__device__ __forceinline__ float gelu_fast_grad(float x) {
-  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
-  const float x2 = xc * xc;
-  const float p = fmaf(x2, fmaf(x2, -3.51519787e-4f, 3.70056658e-2f), 7.97507861e-1f);
-  const float du = fmaf(x2, fmaf(x2, 5.0f * -3.51519787e-4f, 3.0f * 3.70056658e-2f), 7.97507861e-1f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xc * p));
-  return fmaf(0.5f * xc * du, fmaf(-t, t, 1.0f), fmaf(0.5f, t, 0.5f));
+// d/dx of gelu_fast for two values at once in packed fp16 (as gelu_fast_h2, tc_common.cuh): with t = tanh(u),
+// u = x (k1 + k3 x^2 + k5 x^4):  0.5 (1 + t) + 0.5 x (1 - t^2) (k1 + 3 k3 x^2 + 5 k5 x^4).  ~13 half2 ops + one MUFU per
+// PAIR; |error| ~1e-3, below the bf16 rounding of the product it scales.
+__device__ __forceinline__ float2 gelu_fast_grad_h2(float xa, float xb) {
+  const __half2 lim = __float2half2_rn(8.0f), hf = __float2half2_rn(0.5f);
+  const __half2 xc = __hmin2(__hmax2(__floats2half2_rn(xa, xb), __hneg2(lim)), lim);
+  const __half2 x2 = __hmul2(xc, xc);
+  __half2 p = __hfma2(x2, __float2half2_rn(-3.51519787e-4f), __float2half2_rn(3.70056658e-2f));
+  p = __hfma2(x2, p, __float2half2_rn(7.97507861e-1f));
+  __half2 du = __hfma2(x2, __float2half2_rn(5.0f * -3.51519787e-4f), __float2half2_rn(3.0f * 3.70056658e-2f));
+  du = __hfma2(x2, du, __float2half2_rn(7.97507861e-1f));
+  const __half2 u = __hmul2(xc, p);
+  uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 s = __hfma2(__hneg2(t), t, __float2half2_rn(1.0f));
+  const __half2 a = __hmul2(__hmul2(xc, hf), du);
+  return __half22float2(__hfma2(a, s, __hfma2(t, hf, hf)));
 }
 
 template <int KB>                                 // K / 64
@@ -56,9 +66,11 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = KB * 16384;      // this CTA's 128 rows x K
   static constexpr int EPI_BYTES = kG2EpiWarps * 4096;
   static constexpr int BAR_BYTES = 512;
-  static constexpr int AVAIL = 227 * 1024 - 1024 - BAR_BYTES - A_BYTES - EPI_BYTES;
+  static constexpr int BIAS_BYTES = G2_MAX_N * 4;   // the bias vector, read by the epilogue as broadcast LDS (an LDG per chunk
+                                                    // was the largest epilogue stall in the ncu source page)
+  static constexpr int AVAIL = 227 * 1024 - 1024 - BAR_BYTES - BIAS_BYTES - A_BYTES - EPI_BYTES;
   static constexpr int NSLOT = AVAIL / G2_SLOT > 8 ? 8 : AVAIL / G2_SLOT;
-  static constexpr int SMEM_BYTES = 1024 + A_BYTES + NSLOT * G2_SLOT + EPI_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + A_BYTES + NSLOT * G2_SLOT + EPI_BYTES + BAR_BYTES + BIAS_BYTES;
   static_assert(NSLOT >= 4, "W ring too shallow");
 };
 
@@ -83,6 +95,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* w_full = bars + 6;       // [NSLOT]
   uint64_t* w_empty = bars + 6 + NSLOT;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * NSLOT);
+  float* s_bias = reinterpret_cast<float*>(epi_smem + Cfg::EPI_BYTES + Cfg::BAR_BYTES);
+  for (int i = threadIdx.x; i < a.N; i += kG2Threads) s_bias[i] = a.bias != nullptr ? __ldg(a.bias + i) : 0.f;   // visible after the __syncthreads below
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -173,7 +187,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int q = warp & 3, hf = (warp - 4) >> 2;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t t_empty_L0 = mapa_u32(smem_u32(&t_empty[0]), 0), t_empty_L1 = mapa_u32(smem_u32(&t_empty[1]), 0);
-    uint8_t* stg = epi_smem + (warp - 4) * 4096;
+    const uint32_t stg = smem_u32(epi_smem) + (warp - 4) * 4096;
+    const uint32_t s_bias_u32 = smem_u32(s_bias);
     int acc = 0;
     uint32_t tphase = 0;
     uint32_t v[32];
@@ -191,10 +206,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                      ? __ldg(reinterpret_cast<const uint4*>(a.aux + m * a.ldo + n_ + (lane & 3) * 8)) : make_uint4(0, 0, 0, 0);
       }
     };
-    if (gelu_bwd) load_aux(pair0, 0, hf, pre_cur);
+    // ... and the CTA's whole [128 x 192] aux tile is pulled into L2 one N tile ahead (lane -> row, warp half -> 96
+    // columns = 192 B): the register prefetch then pays an L2 hit, not a DRAM round trip (16 KB in flight per SM was
+    // the limit: 2.6 TB/s).
+    auto prefetch_aux_tile = [&](int pt_, int nt_) {
+      const long long m = (long long)pt_ * 256 + rank * 128 + q * 32 + lane;
+      if (pt_ < a.pair_tiles && m < a.M) prefetch_l2_bulk(a.aux + m * a.ldo + nt_ * G2_BN + hf * (G2_BN / 2), G2_BN);
+    };
+    if (gelu_bwd) { prefetch_aux_tile(pair0, 0); load_aux(pair0, 0, hf, pre_cur); }
     for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
       const long long m_base = (long long)pt * 256 + rank * 128 + q * 32;
       for (int nt = 0; nt < a.n_tiles; ++nt) {
+        if (gelu_bwd) {
+          if (nt + 1 < a.n_tiles) prefetch_aux_tile(pt, nt + 1); else prefetch_aux_tile(pt + npairs, 0);
+        }
         mbar_wait(&t_full[acc], (tphase >> acc) & 1);
         tphase ^= 1u << acc;
         tcgen05_after_sync();
@@ -212,19 +237,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (a.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n + j));
-              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-            }
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = lds128f(s_bias_u32 + (n + j) * 4);
+            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
           }
           if (a.aux_mode == G2_AUX_PRE_OUT) {     // the pre-activation tile, staged in the second half of the warp's 4 KiB
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc)
-              *reinterpret_cast<uint4*>(stg + 2048 + g2_stg_b16(lane, cc)) =
-                  make_uint4(pack_bf16(f[8 * cc], f[8 * cc + 1]), pack_bf16(f[8 * cc + 2], f[8 * cc + 3]),
-                             pack_bf16(f[8 * cc + 4], f[8 * cc + 5]), pack_bf16(f[8 * cc + 6], f[8 * cc + 7]));
+              sts128(stg + 2048 + g2_stg_b16(lane, cc), pack_bf16(f[8 * cc], f[8 * cc + 1]), pack_bf16(f[8 * cc + 2], f[8 * cc + 3]),
+                     pack_bf16(f[8 * cc + 4], f[8 * cc + 5]), pack_bf16(f[8 * cc + 6], f[8 * cc + 7]));
           }
           if (a.act == PANGU_ACT_GELU_ERF) {
 #pragma unroll
@@ -233,22 +255,20 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (a.out_dtype == PANGU_BF16) {
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc)
-              *reinterpret_cast<uint4*>(stg + g2_stg_b16(lane, cc)) =
-                  make_uint4(pack_bf16(f[8 * cc], f[8 * cc + 1]), pack_bf16(f[8 * cc + 2], f[8 * cc + 3]),
-                             pack_bf16(f[8 * cc + 4], f[8 * cc + 5]), pack_bf16(f[8 * cc + 6], f[8 * cc + 7]));
+              sts128(stg + g2_stg_b16(lane, cc), pack_bf16(f[8 * cc], f[8 * cc + 1]), pack_bf16(f[8 * cc + 2], f[8 * cc + 3]),
+                     pack_bf16(f[8 * cc + 4], f[8 * cc + 5]), pack_bf16(f[8 * cc + 6], f[8 * cc + 7]));
             __syncwarp();
             __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
             if (!gelu_bwd) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int rr = (lane >> 2) + 8 * i, cc = lane & 3;
-                const uint4 val = *reinterpret_cast<const uint4*>(stg + g2_stg_b16(rr, cc));
+                const uint4 val = lds128(stg + g2_stg_b16(rr, cc));
                 const long long m = m_base + rr;
                 if (m < a.M) {
                   *reinterpret_cast<uint4*>(out + m * a.ldo + n + cc * 8) = val;
                   if (a.aux_mode == G2_AUX_PRE_OUT)
-                    *reinterpret_cast<uint4*>(a.aux + m * a.ldo + n + cc * 8) =
-                        *reinterpret_cast<const uint4*>(stg + 2048 + g2_stg_b16(rr, cc));
+                    *reinterpret_cast<uint4*>(a.aux + m * a.ldo + n + cc * 8) = lds128(stg + 2048 + g2_stg_b16(rr, cc));
                 }
               }
             } else {
@@ -258,7 +278,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int rr = (lane >> 2) + 8 * i, cc = lane & 3;
-                uint4 val = *reinterpret_cast<const uint4*>(stg + g2_stg_b16(rr, cc));
+                uint4 val = lds128(stg + g2_stg_b16(rr, cc));
                 __nv_bfloat162* gp = reinterpret_cast<__nv_bfloat162*>(&val);
                 const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&pre_cur[i]);
                 const long long m = m_base + rr;
@@ -266,10 +286,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     const float2 gf = __bfloat1622float2(gp[j]), xf = __bfloat1622float2(xp[j]);
-                    const __nv_bfloat162 o = __floats2bfloat162_rn(gf.x * gelu_fast_grad(xf.x), gf.y * gelu_fast_grad(xf.y));
-                    gp[j] = o;
-                    const float2 of = __bfloat1622float2(o);     // sum what the wgrad GEMM will see
-                    cs[2 * j] += of.x; cs[2 * j + 1] += of.y;
+                    const float2 d = gelu_fast_grad_h2(xf.x, xf.y);
+                    const float ox = gf.x * d.x, oy = gf.y * d.y;
+                    gp[j] = __floats2bfloat162_rn(ox, oy);
+                    cs[2 * j] += ox; cs[2 * j + 1] += oy;
                   }
                   *reinterpret_cast<uint4*>(out + m * a.ldo + n + cc * 8) = val;
                 }
@@ -293,13 +313,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           } else {
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc)
-              *reinterpret_cast<float4*>(stg + g2_stg_f32(lane, cc)) = make_float4(f[4 * cc], f[4 * cc + 1], f[4 * cc + 2], f[4 * cc + 3]);
+              sts128(stg + g2_stg_f32(lane, cc), __float_as_uint(f[4 * cc]), __float_as_uint(f[4 * cc + 1]), __float_as_uint(f[4 * cc + 2]), __float_as_uint(f[4 * cc + 3]));
             __syncwarp();
             float* out = reinterpret_cast<float*>(a.out);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = (lane >> 3) + 4 * i, cc = lane & 7;
-              const float4 val = *reinterpret_cast<const float4*>(stg + g2_stg_f32(rr, cc));
+              const float4 val = lds128f(stg + g2_stg_f32(rr, cc));
               const long long m = m_base + rr;
               if (m < a.M) {
                 *reinterpret_cast<float4*>(out + m * a.ldo + n + cc * 4) = val;
@@ -353,7 +373,7 @@ static int launch_gemm2_t(const void* A, long long lda, const void* W, Gemm2Args
 int launch_tc_linear_pair(const void* A, long long lda, const void* W, const float* bias, void* out,
                           long long ldo, long long M, int K, int N, int act, int out_dtype, void* shadow, cudaStream_t st,
                           void* aux, int aux_mode, float* colsum) {
-  if ((K != 192 && K != 384) || N % tc::G2_BN != 0 || M < 2048 || lda % 8 || ldo % 8) return PANGU_ERR_UNSUPPORTED;
+  if ((K != 192 && K != 384) || N % tc::G2_BN != 0 || N > tc::G2_MAX_N || M < 2048 || lda % 8 || ldo % 8) return PANGU_ERR_UNSUPPORTED;
   if (aux_mode != tc::G2_AUX_NONE && (aux == nullptr || out_dtype != PANGU_BF16)) { set_error("linear(bf16): aux modes need an aux tensor and a bf16 output"); return PANGU_ERR_BAD_ARG; }
   tc::Gemm2Args a{};
   a.M = M; a.N = N; a.bias = bias; a.out = out; a.ldo = ldo; a.out_dtype = out_dtype; a.act = act;

@@ -455,6 +455,46 @@ def gelu_backward_bf16(dh, h_pre, dcolsum=None):
     return dh
 
 
+def pair_gemm_covers(M, K, N):
+    """Shapes of the A-resident CTA-pair GEMM (csrc/tc_gemm2.cu), the kernel that carries the aux epilogues."""
+    return K in (192, 384) and N % 192 == 0 and N <= 1536 and M >= 2048
+
+
+def linear_gelu_pre(a, w, bias):
+    """Mlp.linear1 for the fine-tune step: (h_pre, h) = (a @ w.T + bias, GELU(h_pre)), both bf16, from ONE GEMM pass
+    (PANGU_AUX_PRE_OUT); shapes the CTA-pair GEMM does not cover run the GEMM twice (still CUDA)."""
+    _chk(a, torch.bfloat16, "a")
+    _chk(w, torch.bfloat16, "w")
+    _chk(bias, torch.float32, "bias")
+    M, K = a.shape
+    N = w.shape[0]
+    if not pair_gemm_covers(M, K, N):
+        return linear(a, w, bias), linear(a, w, bias, act=ACT_GELU)
+    h_pre = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    h = torch.empty_like(h_pre)
+    _call("gemm_bf16[K=%d,N=%d,gelu+pre]" % (K, N), "pangu_linear_bf16_aux",
+          (_ptr(a), K, _ptr(w), _ptr(bias), _ptr(h), _ptr(h_pre), N, M, K, N, ACT_GELU, 1, None, _stream(),),
+          flops=2.0 * M * K * N, nbytes=float(a.numel() * 2 + 4 * M * N + w.numel() * 2))
+    return h_pre, h
+
+
+def linear_gelu_backward(dy, w_t, h_pre, dcolsum=None):
+    """dh_pre = (dy @ w_t.T) * GELU'(h_pre) (bf16) and dcolsum [F] += its column sums: the dgrad of Mlp.linear2 with the
+    GELU backward in its epilogue (PANGU_AUX_GELU_BWD); other shapes: GEMM + gelu_backward_bf16."""
+    _chk(dy, torch.bfloat16, "dy")
+    _chk(w_t, torch.bfloat16, "w_t")
+    _chk(h_pre, torch.bfloat16, "h_pre")
+    M, K = dy.shape
+    N = w_t.shape[0]
+    if not pair_gemm_covers(M, K, N):
+        return gelu_backward_bf16(linear(dy, w_t, None), h_pre, dcolsum)
+    dh = torch.empty((M, N), dtype=torch.bfloat16, device=dy.device)
+    _call("gemm_bf16[K=%d,N=%d,gelu_bwd]" % (K, N), "pangu_linear_bf16_aux",
+          (_ptr(dy), K, _ptr(w_t), None, _ptr(dh), _ptr(h_pre), N, M, K, N, ACT_NONE, 2, _ptr(dcolsum), _stream(),),
+          flops=2.0 * M * K * N, nbytes=float(dy.numel() * 2 + 4 * M * N + w_t.numel() * 2))
+    return dh
+
+
 def window_attention_train(qkv, qkv_bias, earth_bias, Z, H, W, heads, roll):
     """Pre-scaled bf16 window attention that also returns the log2-sum-exp rows for the backward kernel."""
     _chk(qkv, torch.bfloat16, "qkv")

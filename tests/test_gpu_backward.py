@@ -106,6 +106,35 @@ def test_gelu_forward_backward(dev, F):
     assert orc.rel_l2(col, out.float().sum(0)) <= 1e-4
 
 
+@pytest.mark.parametrize("M,C", [(5000, 192), (4133, 384), (2048, 192), (256 * 74 + 77, 384)])
+def test_mlp_aux_epilogues_of_the_pair_gemm(dev, M, C):
+    """PANGU_AUX_PRE_OUT / PANGU_AUX_GELU_BWD (include/pangu_b200.h): Mlp.linear1 leaving (h_pre, GELU(h_pre)) in one pass
+    must equal the two separate GEMM passes bit for bit; the dgrad of linear2 with GELU' in its epilogue is compared with
+    torch autograd through the exact erf GELU on the SAME bf16 operands (rel-L2 <= 4e-3, the bound of the stand-alone
+    gelu_backward kernel test: bf16 rounding of the product + the fitted tanh form)."""
+    from pangu_b200 import ops
+    g = _gen(M + C)
+    F = 4 * C
+    assert ops.pair_gemm_covers(M, C, F)
+    x = torch.randn(M, C, generator=g).to(dev).bfloat16()
+    w1 = (torch.randn(F, C, generator=g) * C ** -0.5).to(dev).bfloat16()
+    b1 = torch.randn(F, generator=g).to(dev) * 0.1
+    h_pre, h = ops.linear_gelu_pre(x, w1, b1)
+    assert torch.equal(h_pre, ops.linear(x, w1, b1)) and torch.equal(h, ops.linear(x, w1, b1, act=ops.ACT_GELU))
+    dy = torch.randn(M, C, generator=g).to(dev).bfloat16()
+    w2t = (torch.randn(F, C, generator=g) * C ** -0.5).to(dev).bfloat16()        # linear2.weight^T: [4C, C]
+    col = torch.zeros(F, device=dev)
+    dh = ops.linear_gelu_backward(dy, w2t, h_pre, col)
+    hp = h_pre.float().requires_grad_()
+    torch.nn.functional.gelu(hp).backward(dy.float() @ w2t.float().t())
+    assert orc.rel_l2(dh.float(), hp.grad) <= 4e-3
+    # bias gradient: column sums of the UN-rounded products, against the fp32 reference (2e-3 of the column's absolute sum)
+    assert float(((col - hp.grad.sum(0)).abs() / hp.grad.abs().sum(0)).max()) <= 2e-3
+    # un-covered shapes run the separate kernels and agree with the fused ones on the rows they share
+    dh_small = ops.linear_gelu_backward(dy[:1000].contiguous(), w2t, h_pre[:1000].contiguous())
+    assert orc.rel_l2(dh_small.float(), dh[:1000].float()) <= 4e-3
+
+
 def test_colsum(dev):
     from pangu_b200 import ops
     g = _gen(3)
