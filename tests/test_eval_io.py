@@ -1,4 +1,4 @@
-"""Latitude-weighted RMSE / ACC: oracle pinned to outputs of the reference's era5_data/score.py
+"""Either side of the forward: latitude-weighted RMSE / ACC: oracle pinned to outputs of the reference's era5_data/score.py
 (tests/golden/make_score_golden.py), CUDA one-pass kernel against the oracle and the goldens."""
 import os
 
@@ -71,3 +71,34 @@ def test_cuda_scores_full_resolution_against_the_oracle():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     print("lat_weighted_score_sums: %.3f ms, %.0f GB/s" % (ms, 2 * pred.numel() * 4 / ms / 1e6))
+
+
+# ------------------------------------------------------------------------------------------ input pipeline
+def test_prefetcher_refuses_to_run_without_cuda():
+    from pangu_b200.abi import PanguError
+    from pangu_b200.prefetch import DataPrefetcher
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(PanguError, match="CUDA"):
+        DataPrefetcher([(torch.zeros(1),) * 5])
+
+
+@pytest.mark.gpu
+def test_prefetcher_returns_every_batch_in_order_and_wraps_around():
+    """Contract of era5_data/utils_data.py:20-57 (next() -> 5 device tensors, len(), wrap-around), minus its skipped batch."""
+    from pangu_b200.prefetch import DataPrefetcher
+    g = torch.Generator().manual_seed(11)
+    batches = [(torch.randn(1, 5, 13, 40, 64, generator=g), torch.randn(1, 4, 40, 64, generator=g),
+                torch.randn(1, 5, 13, 40, 64, generator=g), torch.randn(1, 4, 40, 64, generator=g),
+                torch.tensor([[2018010100 + i, 2018010200 + i]])) for i in range(3)]
+    pf = DataPrefetcher(batches)
+    assert len(pf) == 3
+    side = torch.cuda.Stream()
+    for i in range(7):                                     # 7 > 2 * len: wraps around twice, pinned slots are reused
+        with torch.cuda.stream(side if i % 2 else torch.cuda.current_stream()):
+            got = pf.next()
+            assert len(got) == 5 and all(t.is_cuda for t in got)
+            acc = [t.clone() for t in got]                 # consumed on the caller's stream
+        torch.cuda.synchronize()
+        for a, want in zip(acc, batches[i % 3]):
+            assert torch.equal(a.cpu(), want)
