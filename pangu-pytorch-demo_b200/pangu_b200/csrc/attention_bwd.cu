@@ -2,13 +2,19 @@
 // pad / roll / partition / reverse / crop, :224-293), the counterpart of tc_attention.cu.
 //
 // One CTA owns ONE (window type t, head) bias tile and walks a chunk of longitude windows.  Per (window, head),
-// with the forward's log2-sum-exp L_i of every score row (written by the forward kernel) and D_i = dO_i . O_i:
-//   row pass   (warp = 16 query rows):  S = q k^T + bias (+mask), P = exp2(S - L), dP = dO v^T, dS = P (dP - D),
-//                                       dQ = scale * dS k,  dBias += dS  (fragment-resident fp32 accumulators that
-//                                       live across the whole longitude walk; one reduction per CTA at the end)
-//   column pass(warp = 16 key rows):    S^T, P^T, dP^T, dS^T recomputed in transposed fragments so that
+// with the forward's log2-sum-exp L_i of every score row (written by the forward kernel) and D_i = dO_i . O_i, the
+// two passes run CONCURRENTLY on the same staged tiles, nine warps each.  ncu (profiles/r1_attention_bwd.md): the kernel
+// sits at ~60 % of the shared-memory wavefront peak (ldmatrix operand fragments re-read by every warp, the transposed
+// bias reads, the dBias read-modify-write) with HMMA at 22 %; three row tiles per warp halve the wavefronts but leave
+// 6 warps per SM and run slower (latency), so the next step for this kernel is tcgen05 like the forward.
+//   row pass   (warps 0-8, 16 query rows each):  S = q k^T + bias (+mask), P = exp2(S - L), dP = dO v^T,
+//                                       dS = P (dP - D), dQ = scale * dS k,  dBias += dS into an fp32 [144 x 144] tile
+//                                       in shared memory that lives across the whole longitude walk (each warp owns
+//                                       its 16 rows: plain read-modify-write; one reduction per CTA at the end)
+//   column pass(warps 9-17, 16 key rows each):   S^T, P^T, dP^T, dS^T recomputed in transposed fragments so that
 //                                       dV = P^T dO and dK = dS^T q stay warp-local (no smem round trip of the
 //                                       144 x 144 matrices, no atomics on the activations)
+// After a CTA barrier the q / k / v tiles of the window are dead and serve as the staging tiles of dq / dk / dv.
 // Gradients of real tokens are written at their un-rolled token position of dqkv [N, 3C]; zero-pad rows were
 // linear1(0) = bias in the forward (layers.py:228,419), so they only feed linear1's bias gradient: the kernel sums
 // dq/dk/dv over ALL window rows (real and pad) into dqkv_bias [3C], which IS that bias gradient.  q, k, bias arrive pre-scaled like in the forward (scale*log2e folded into q, log2e
@@ -23,14 +29,19 @@ namespace attn_bwd {
 
 using namespace attn;
 
-constexpr int kWarps = 9;
+constexpr int kPassWarps = 9;                           // 144 rows / 16
+constexpr int kWarps = 2 * kPassWarps;
 constexpr int kThreads = kWarps * 32;
+constexpr int kDbPitch = 152;                           // fp32 per dBias row in smem: pitch % 32 == 24, so the four rows a half-warp
+                                                        // touches with one LDS.64 / STS.64 fall into disjoint 8-bank groups
 constexpr int kTiles = 5;                               // q, k, v, dO, O
 constexpr int kBufBytes = kTiles * kTileBytes;
-constexpr int kSmemBytes = kWinTokens * kBiasPitch * 2 + 2 * kBufBytes + kWinTokens * 4 /*rowbase*/ + kWinTokens * 4 /*dw*/ +
-                           160 /*gid*/ + 2 * kWinTokens * 4 /*L*/ + kWinTokens * 4 /*D*/ + 16;
+constexpr int kSmemBytes = kWinTokens * kBiasPitch * 2 + 2 * kBufBytes + kWinTokens * kDbPitch * 4 /*dBias*/ +
+                           kWinTokens * 4 /*rowbase*/ + kWinTokens * 4 /*dw*/ + 160 /*gid*/ + 2 * kWinTokens * 4 /*L*/ +
+                           kWinTokens * 4 /*D*/ + 16;
+static_assert(kSmemBytes <= 227 * 1024, "attention backward: shared memory");
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 1)          // 18 warps: 5 on one SM sub-partition -> 16 K registers / 5 warps = 96 per thread
 window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ qkv_bias,
                             const __nv_bfloat16* __restrict__ earth_bias, const __nv_bfloat16* __restrict__ o,
                             const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse,
@@ -39,7 +50,8 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
   extern __shared__ __align__(128) uint8_t smem[];
   __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(smem);                       // [144][152]
   uint8_t* s_buf = smem + kWinTokens * kBiasPitch * 2;                                  // 2 x {q,k,v,dO,O}
-  int* s_rowbase = reinterpret_cast<int*>(s_buf + 2 * kBufBytes);
+  float* s_dbias = reinterpret_cast<float*>(s_buf + 2 * kBufBytes);                     // [144][kDbPitch] fp32
+  int* s_rowbase = reinterpret_cast<int*>(s_dbias + kWinTokens * kDbPitch);
   int* s_dw = s_rowbase + kWinTokens;
   uint8_t* s_gid = reinterpret_cast<uint8_t*>(s_dw + kWinTokens);
   float* s_L = reinterpret_cast<float*>(s_gid + 160);                                   // [2][144]
@@ -66,6 +78,7 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
     }
     s_gid[k] = (uint8_t)shift_group(g, t, k);
   }
+  for (int i = tid; i < kWinTokens * kDbPitch; i += kThreads) s_dbias[i] = 0.f;
   {
     const __nv_bfloat16* src = earth_bias + ((long long)t * g.heads + head) * kWinTokens * kWinTokens;
     for (int i = tid; i < kWinTokens * 18; i += kThreads) {
@@ -113,21 +126,15 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
   const float ln2 = 0.6931471805599453f;
   const float mask_l2 = kMaskValue * kLog2e;
   const int gq = lane >> 2, tq = lane & 3;
-  const int row0 = warp * 16;
+  const bool row_role = warp < kPassWarps;                  // warp-uniform
+  const int row0 = (row_role ? warp : warp - kPassWarps) * 16;
   const int mi = lane >> 3, mr = lane & 7;
   const bool masked_type = roll == 1 && ((t / g.nH == g.nZ - 1) || (t % g.nH == g.nH - 1));
   const int gid_lo = s_gid[row0 + gq], gid_hi = s_gid[row0 + gq + 8];       // valid after the barrier above
 
-  float dbias_acc[3][6][4];
+  float colsum[2][4][2];                                    // row role: [0] = dq; column role: [0] = dk, [1] = dv
 #pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = 0; b < 6; ++b)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) dbias_acc[a][b][c] = 0.f;
-  float colsum[3][4][2];
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) colsum[a][b][0] = colsum[a][b][1] = 0.f;
 
@@ -163,17 +170,16 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
     }
     __syncthreads();
 
-    // stage a 16 x 32 fragment tile (this warp's rows) through the dead O rows and write tensor s of dqkv
-    auto emit = [&](float (&acc)[4][4], auto s_tag, float mult) {
+    // stage a 16 x 32 fragment tile (this warp's rows) through a dead operand tile and write tensor s of dqkv
+    auto emit = [&](float (&acc)[4][4], auto s_tag, float mult, uint8_t* stage, float (&cs)[4][2]) {
       constexpr int s = decltype(s_tag)::value;
-      __syncwarp();
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const float v0 = acc[nt][0] * mult, v1 = acc[nt][1] * mult, v2 = acc[nt][2] * mult, v3 = acc[nt][3] * mult;
-        *reinterpret_cast<uint32_t*>(so + tile_off(row0 + gq, nt) + 4 * tq) = pack_bf16(v0, v1);
-        *reinterpret_cast<uint32_t*>(so + tile_off(row0 + gq + 8, nt) + 4 * tq) = pack_bf16(v2, v3);
-        colsum[s][nt][0] += v0 + v2;                        // every window row, pad rows included, is a row of linear1's output
-        colsum[s][nt][1] += v1 + v3;
+        *reinterpret_cast<uint32_t*>(stage + tile_off(row0 + gq, nt) + 4 * tq) = pack_bf16(v0, v1);
+        *reinterpret_cast<uint32_t*>(stage + tile_off(row0 + gq + 8, nt) + 4 * tq) = pack_bf16(v2, v3);
+        cs[nt][0] += v0 + v2;                               // every window row, pad rows included, is a row of linear1's output
+        cs[nt][1] += v1 + v3;
       }
       __syncwarp();
 #pragma unroll
@@ -181,15 +187,20 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
         const int idx = lane + i * 32, r = row0 + (idx >> 2), c = idx & 3;
         const int dwc = s_dw[r];
         if ((dwc >> 8) != 0) {
-          const uint4 val = *reinterpret_cast<const uint4*>(so + tile_off(r, c));
+          const uint4 val = *reinterpret_cast<const uint4*>(stage + tile_off(r, c));
           *reinterpret_cast<uint4*>(dqkv + token_of(l, dwc, s_rowbase[r]) * 3 * C + s * C + head * kHeadDim + c * 8) = val;
         }
       }
-      __syncwarp();
     };
 
+    float acc_a[4][4], acc_b[4][4];                         // row role: dq in acc_a; column role: dk in acc_a, dv in acc_b
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc_a[i][j] = acc_b[i][j] = 0.f;
+
     // ------------------------------------------------------------------ row pass: dQ, dBias
-    {
+    if (row_role) {
       uint32_t qa[2][4], da[2][4];
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
@@ -199,12 +210,8 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
       }
       const float L_lo = sL[row0 + gq], L_hi = sL[row0 + gq + 8];
       const float D_lo = s_D[row0 + gq], D_hi = s_D[row0 + gq + 8];
-      float dq_acc[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dq_acc[i][j] = 0.f;
-#pragma unroll
+      float (&dq_acc)[4][4] = acc_a;
+#pragma unroll 1
       for (int kvb = 0; kvb < 3; ++kvb) {
         const int kv0 = kvb * 48;
         uint32_t dsa[3][4];
@@ -234,8 +241,13 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
           }
           const float ds0 = ex2(s_acc[0] - L_lo) * (dp[0] - D_lo), ds1 = ex2(s_acc[1] - L_lo) * (dp[1] - D_lo);
           const float ds2 = ex2(s_acc[2] - L_hi) * (dp[2] - D_hi), ds3 = ex2(s_acc[3] - L_hi) * (dp[3] - D_hi);
-          dbias_acc[kvb][nt][0] += ds0; dbias_acc[kvb][nt][1] += ds1;
-          dbias_acc[kvb][nt][2] += ds2; dbias_acc[kvb][nt][3] += ds3;
+          {                                                 // dBias += dS: this warp owns rows row0 .. row0+15 of the tile
+            float2* p_lo = reinterpret_cast<float2*>(s_dbias + (row0 + gq) * kDbPitch + j);
+            float2* p_hi = reinterpret_cast<float2*>(s_dbias + (row0 + gq + 8) * kDbPitch + j);
+            float2 a_lo = *p_lo, a_hi = *p_hi;
+            a_lo.x += ds0; a_lo.y += ds1; a_hi.x += ds2; a_hi.y += ds3;
+            *p_lo = a_lo; *p_hi = a_hi;
+          }
           dsa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds0, ds1);
           dsa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(ds2, ds3);
         }
@@ -251,11 +263,8 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
           }
         }
       }
-      emit(dq_acc, std::integral_constant<int, 0>{}, scale);
-    }
-
+    } else {
     // ------------------------------------------------------------------ column pass: dK, dV (this warp's 16 KEY rows)
-    {
       uint32_t ka[2][4], va[2][4];
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
@@ -263,11 +272,8 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
         ldmatrix_x4(smem_u32(sk + tile_off(r, c)), ka[ks][0], ka[ks][1], ka[ks][2], ka[ks][3]);
         ldmatrix_x4(smem_u32(sv + tile_off(r, c)), va[ks][0], va[ks][1], va[ks][2], va[ks][3]);
       }
-      float dk_acc[4][4], dv_acc[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dk_acc[i][j] = dv_acc[i][j] = 0.f;
+      float (&dk_acc)[4][4] = acc_a;
+      float (&dv_acc)[4][4] = acc_b;
       const int jl = row0 + gq, jh = row0 + gq + 8;
 #pragma unroll 1
       for (int ib = 0; ib < 3; ++ib) {
@@ -295,7 +301,8 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
             if (g0 != gid_hi) st[2] += mask_l2;
             if (g1 != gid_hi) st[3] += mask_l2;
           }
-          const float Li0 = sL[i], Li1 = sL[i + 1], Di0 = s_D[i], Di1 = s_D[i + 1];
+          const float2 Li = *reinterpret_cast<const float2*>(sL + i), Di = *reinterpret_cast<const float2*>(s_D + i);   // i is even
+          const float Li0 = Li.x, Li1 = Li.y, Di0 = Di.x, Di1 = Di.y;
           const float p0 = ex2(st[0] - Li0), p1 = ex2(st[1] - Li1), p2 = ex2(st[2] - Li0), p3 = ex2(st[3] - Li1);
           pta[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
           pta[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
@@ -317,8 +324,13 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
           }
         }
       }
-      emit(dk_acc, std::integral_constant<int, 1>{}, ln2);
-      emit(dv_acc, std::integral_constant<int, 2>{}, 1.0f);
+    }
+    __syncthreads();                                        // both passes are done with q / k / v: the tiles become staging
+    if (row_role) {
+      emit(acc_a, std::integral_constant<int, 0>{}, scale, sq, colsum[0]);
+    } else {
+      emit(acc_a, std::integral_constant<int, 1>{}, ln2, sk, colsum[0]);
+      emit(acc_b, std::integral_constant<int, 2>{}, 1.0f, sv, colsum[1]);
     }
     __syncthreads();                                        // buffer b may be refilled by the next prefetch
   }
@@ -327,31 +339,29 @@ window_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const float* 
   // ---- per-CTA reductions: Earth-specific bias gradient (dS summed over this CTA's longitude windows) ...
   {
     float* dst = dbias + ((long long)t * g.heads + head) * kWinTokens * kWinTokens;
-#pragma unroll
-    for (int kvb = 0; kvb < 3; ++kvb)
-#pragma unroll
-      for (int nt = 0; nt < 6; ++nt) {
-        const int j = kvb * 48 + nt * 8 + 2 * tq;
-        atomicAdd(dst + (row0 + gq) * kWinTokens + j, dbias_acc[kvb][nt][0]);
-        atomicAdd(dst + (row0 + gq) * kWinTokens + j + 1, dbias_acc[kvb][nt][1]);
-        atomicAdd(dst + (row0 + gq + 8) * kWinTokens + j, dbias_acc[kvb][nt][2]);
-        atomicAdd(dst + (row0 + gq + 8) * kWinTokens + j + 1, dbias_acc[kvb][nt][3]);
-      }
+    for (int i = tid; i < kWinTokens * (kWinTokens / 4); i += kThreads) {     // 16-byte vector reductions: 5184 per CTA
+      const int r = i / (kWinTokens / 4), c = (i - r * (kWinTokens / 4)) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(s_dbias + r * kDbPitch + c);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + r * kWinTokens + c), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
   }
   // ---- ... and linear1's bias gradient: column sums of dq / dk / dv over all rows this CTA produced
   {
 #pragma unroll
-    for (int s = 0; s < 3; ++s)
+    for (int a = 0; a < 2; ++a) {
+      if (row_role && a == 1) break;
+      const int sidx = row_role ? 0 : 1 + a;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          float v = colsum[s][nt][e];
+          float v = colsum[a][nt][e];
           v += __shfl_xor_sync(0xffffffffu, v, 4);
           v += __shfl_xor_sync(0xffffffffu, v, 8);
           v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (gq == 0) atomicAdd(dqkv_bias + s * C + head * kHeadDim + nt * 8 + 2 * tq + e, v);
+          if (gq == 0) atomicAdd(dqkv_bias + sidx * C + head * kHeadDim + nt * 8 + 2 * tq + e, v);
         }
+    }
   }
 }
 

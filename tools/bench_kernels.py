@@ -91,6 +91,20 @@ def main():
                 ms = timeit(lambda: ops.window_attention(qkv, qb, eb, Z, H, W, heads, roll))
                 print(f"[{tag}] attention roll={roll}     {ms:7.3f} ms  {nwin * heads * 4.0 * 144 * 144 * 32 / ms / 1e9:7.0f} TF/s  "
                       f"{(M * C * 8 + eb.numel() * 2) / ms / 1e6:6.0f} GB/s")
+        if "attnbwd" in which:
+            T = (Z // 2) * ((H + 5) // 6)
+            qkv = (torch.randn(M, 3 * C, device="cuda", generator=g) * 0.5).bfloat16()
+            qb = torch.zeros(3 * C, device="cuda")
+            eb = (torch.randn(T, heads, 144, 144, device="cuda", generator=g) * 0.02).bfloat16()
+            nwin = (W // 12) * T
+            d_eb = torch.zeros(T, heads, 144, 144, device="cuda")
+            d_pad = torch.zeros(3 * C, device="cuda")
+            for roll in (0, 1):
+                o, lse = ops.window_attention_train(qkv, qb, eb, Z, H, W, heads, roll)
+                do = torch.randn(M, C, device="cuda", generator=g).bfloat16()
+                ms = timeit(lambda: ops.window_attention_backward(qkv, qb, eb, o, do, lse, Z, H, W, heads, roll, d_eb, d_pad))
+                print(f"[{tag}] attention bwd roll={roll} {ms:7.3f} ms  {nwin * heads * 14.0 * 144 * 144 * 32 / ms / 1e9:7.0f} TF/s  "
+                      f"{(M * C * 16 + eb.numel() * 6) / ms / 1e6:6.0f} GB/s")
 
 
 if __name__ == "__main__":
