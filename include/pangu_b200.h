@@ -83,6 +83,13 @@ int pangu_window_source_index(int64_t* idx, const pangu_geom* g, int roll, void*
 int pangu_shift_mask(float* mask, const pangu_geom* g, void* stream);
 /* EarthAttention3D._construct_index, models/layers.py:371-411: int64 [144*144]. */
 int pangu_position_index(int64_t* idx, void* stream);
+/* Compact Earth-specific bias (the paper's parameterisation, commented out in the reference at
+ * models/layers.py:355,442-449): full[t, h, i, j] = table[position_index[i*144+j], t, h], table fp32 [3312, T, heads],
+ * full fp32 [T, heads, 144, 144] (the reference's parameter without its leading 1).  Bit-exact gather. */
+int pangu_bias_table_expand(const float* table, float* full, int32_t T, int32_t heads, void* stream);
+/* Its adjoint: d_table[idx, t, h] += sum of d_full[t, h, i, j] over the pairs (i, j) with position_index = idx (the gradient of
+ * a compact table from the dense bias gradient the attention backward produces); deterministic, no atomics. */
+int pangu_bias_table_reduce(const float* d_full, float* d_table, int32_t T, int32_t heads, void* stream);
 
 /* ------------------------------------------------------------------ dense linears */
 

@@ -136,6 +136,13 @@ def position_index() -> np.ndarray:
     return idx.reshape(-1).astype(np.int64)
 
 
+def expand_bias_table(table: np.ndarray) -> np.ndarray:
+    """The compact-bias gather the reference keeps as commented code (models/layers.py:442-449): table [3312, T, heads] ->
+    table[position_index].view(144, 144, T, heads).permute(2, 3, 0, 1).unsqueeze(0) = [1, T, heads, 144, 144]."""
+    T, heads = table.shape[1:]
+    return np.ascontiguousarray(table[position_index()].reshape(WIN_TOKENS, WIN_TOKENS, T, heads).transpose(2, 3, 0, 1))[None]
+
+
 # --------------------------------------------------------------------------------------
 # Floating-point modules (fp32, CPU)
 # --------------------------------------------------------------------------------------

@@ -39,6 +39,8 @@ _PROTOS = {
     "pangu_window_source_index": (c_int, [c_void_p, POINTER(Geom), c_int, c_void_p]),
     "pangu_shift_mask": (c_int, [c_void_p, POINTER(Geom), c_void_p]),
     "pangu_position_index": (c_int, [c_void_p, c_void_p]),
+    "pangu_bias_table_expand": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "pangu_bias_table_reduce": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "pangu_linear": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
                              c_int, c_int, c_int, c_void_p]),
     "pangu_linear_bf16_ex": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,

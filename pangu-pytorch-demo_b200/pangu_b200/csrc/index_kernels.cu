@@ -58,6 +58,45 @@ __global__ void position_index_kernel(long long* __restrict__ idx) {
   idx[gid] = (long long)(zi + 2 * zj) * (23 * 36) + (hi + 6 * hj) * 23 + (wi - wj + 11);
 }
 
+__device__ __forceinline__ int bias_table_index(int i, int j) {
+  const int zi = i / 72, hi = (i / 12) % 6, wi = i % 12;
+  const int zj = j / 72, hj = (j / 12) % 6, wj = j % 12;
+  return (zi + 2 * zj) * (23 * 36) + (hi + 6 * hj) * 23 + (wi - wj + 11);
+}
+
+// Compact Earth-specific bias (the parameterisation of the paper, kept in the reference as commented code,
+// models/layers.py:355,442-449): full[t, h, i, j] = table[position_index[i*144+j], t, h].  One thread per output element,
+// writes coalesced; the [3312, T, heads] table (<= 10 MB) stays in L2.
+__global__ void __launch_bounds__(256)
+bias_table_expand_kernel(const float* __restrict__ table, float* __restrict__ full, int T, int heads) {
+  const long long total = (long long)T * heads * kWinTokens * kWinTokens;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const int ij = (int)(g % (kWinTokens * kWinTokens));
+    const int th = (int)(g / (kWinTokens * kWinTokens));           // t * heads + h
+    full[g] = __ldg(table + (long long)bias_table_index(ij / kWinTokens, ij % kWinTokens) * T * heads + th);
+  }
+}
+
+// Adjoint: d_table[idx, t, h] += sum over the (i, j) pairs that share idx.  (zi, zj) and (hi, hj) are determined by idx; only
+// the longitude offset d = wi - wj is shared, by 12 - |d| pairs: a deterministic gather-reduce, no atomics.
+__global__ void __launch_bounds__(256)
+bias_table_reduce_kernel(const float* __restrict__ d_full, float* __restrict__ d_table, int T, int heads) {
+  const long long total = 3312LL * T * heads;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const int th = (int)(g % ((long long)T * heads));
+    const int idx = (int)(g / ((long long)T * heads));
+    const int zz = idx / (23 * 36), r = idx - zz * (23 * 36), hh = r / 23, d = r - hh * 23 - 11;
+    const int zi = zz & 1, zj = zz >> 1, hi = hh % 6, hj = hh / 6;
+    const float* src = d_full + (long long)th * kWinTokens * kWinTokens;
+    float acc = 0.f;
+    for (int wj = max(0, -d); wj < min(12, 12 - d); ++wj) {
+      const int wi = wj + d;
+      acc += __ldg(src + (zi * 72 + hi * 12 + wi) * kWinTokens + (zj * 72 + hj * 12 + wj));
+    }
+    d_table[g] += acc;
+  }
+}
+
 static int window_move(const void* src, void* dst, const pangu_geom* gg, int roll, int elem_bytes,
                        void* stream, bool reverse) {
   WinGeom g;
@@ -115,4 +154,16 @@ extern "C" int pangu_position_index(int64_t* idx, void* stream) {
   if (!idx) { set_error("position_index: null"); return PANGU_ERR_BAD_ARG; }
   position_index_kernel<<<(kWinTokens * kWinTokens + 255) / 256, 256, 0, as_stream(stream)>>>((long long*)idx);
   return check_launch("position_index");
+}
+
+extern "C" int pangu_bias_table_expand(const float* table, float* full, int32_t T, int32_t heads, void* stream) {
+  if (!table || !full || T <= 0 || heads <= 0) { set_error("bias_table_expand: bad argument"); return PANGU_ERR_BAD_ARG; }
+  bias_table_expand_kernel<<<148 * 8, 256, 0, as_stream(stream)>>>(table, full, T, heads);
+  return check_launch("bias_table_expand");
+}
+
+extern "C" int pangu_bias_table_reduce(const float* d_full, float* d_table, int32_t T, int32_t heads, void* stream) {
+  if (!d_full || !d_table || T <= 0 || heads <= 0) { set_error("bias_table_reduce: bad argument"); return PANGU_ERR_BAD_ARG; }
+  bias_table_reduce_kernel<<<148 * 8, 256, 0, as_stream(stream)>>>(d_full, d_table, T, heads);
+  return check_launch("bias_table_reduce");
 }

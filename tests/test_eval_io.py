@@ -102,3 +102,65 @@ def test_prefetcher_returns_every_batch_in_order_and_wraps_around():
         torch.cuda.synchronize()
         for a, want in zip(acc, batches[i % 3]):
             assert torch.equal(a.cpu(), want)
+
+
+# ------------------------------------------------------------------------------------------ weights
+def test_oracle_compact_bias_gather_is_the_reference_formula():
+    """models/layers.py:442-449 (commented there): table[position_index].view(144, 144, T, heads).permute(2, 3, 0, 1)[None]."""
+    rng = np.random.default_rng(3)
+    table = rng.standard_normal((3312, 5, 2)).astype(np.float32)
+    full = orc.expand_bias_table(table)
+    assert full.shape == (1, 5, 2, 144, 144)
+    idx = torch.from_numpy(orc.position_index())
+    want = torch.from_numpy(table)[idx].view(144, 144, 5, 2).permute(2, 3, 0, 1).unsqueeze(0)
+    assert torch.equal(torch.from_numpy(full), want)
+    # every table row is used, by 12 - |d| pairs
+    cnt = np.bincount(orc.position_index(), minlength=3312)
+    assert cnt.min() == 1 and cnt.max() == 12 and cnt.sum() == 144 * 144
+
+
+def test_load_named_weights_follows_the_onnx2torch_shape_rules():
+    """models/onnx2torch.py:124-161: 1-D / 3-D / 5-D copied, 2-D transposed, rows without a source name skipped, frozen."""
+    from pangu_b200.abi import PanguError
+    from pangu_b200.weights import load_named_weights
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(3, 5)
+            self.conv = torch.nn.Conv1d(4, 6, kernel_size=1)
+            self.bias5 = torch.nn.Parameter(torch.zeros(1, 2, 3, 4, 4))
+            self.untouched = torch.nn.Parameter(torch.ones(2))
+
+    m = Tiny()
+    rng = np.random.default_rng(0)
+    w = {"a": rng.standard_normal((3, 5)).astype(np.float32), "b": rng.standard_normal(5).astype(np.float32),
+         "c": rng.standard_normal((6, 4, 1)).astype(np.float32), "d": rng.standard_normal(6).astype(np.float32),
+         "e": rng.standard_normal((1, 2, 3, 4, 4)).astype(np.float32)}
+    name_map = [("lin.weight", "a"), ("lin.bias", "b"), ("conv.weight", "c"), ("conv.bias", "d"), ("bias5", "e"), ("untouched", float("nan"))]
+    assert load_named_weights(m, w, name_map) == 5
+    assert np.array_equal(m.lin.weight.detach().numpy(), w["a"].T) and np.array_equal(m.conv.weight.detach().numpy(), w["c"])
+    assert np.array_equal(m.bias5.detach().numpy(), w["e"]) and float(m.untouched.sum()) == 2.0
+    assert not m.lin.weight.requires_grad and m.untouched.requires_grad
+    with pytest.raises(PanguError, match="gives"):
+        load_named_weights(Tiny(), {**w, "b": np.zeros(4, np.float32)}, name_map)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,heads", [(124, 6), (64, 12), (3, 1)])
+def test_cuda_compact_bias_expand_is_bit_exact_and_reduce_is_its_adjoint(T, heads):
+    from pangu_b200.weights import expand_bias_table, reduce_bias_grad
+    g = torch.Generator().manual_seed(T)
+    table = torch.randn(3312, T, heads, generator=g)
+    full = expand_bias_table(table.cuda())
+    assert np.array_equal(full.cpu().numpy(), orc.expand_bias_table(table.numpy()))                      # index work: bit-exact
+    d_full = torch.randn(1, T, heads, 144, 144, generator=g)
+    d_table = reduce_bias_grad(d_full.cuda())
+    want = torch.zeros(3312, T * heads, dtype=torch.float64)
+    want.index_add_(0, torch.from_numpy(orc.position_index()), d_full[0].double().permute(2, 3, 0, 1).reshape(144 * 144, T * heads))
+    np.testing.assert_allclose(d_table.cpu().double().reshape(3312, -1).numpy(), want.numpy(), rtol=0, atol=2e-5)   # <= 12 fp32 terms
+    lhs = float((full.cpu().double() * d_full.double()).sum())                                           # <expand(t), g> = <t, reduce(g)>
+    rhs = float((table.double() * d_table.cpu().double()).sum())
+    assert abs(lhs - rhs) <= 1e-6 * max(1.0, abs(lhs))
+    acc = reduce_bias_grad(d_full.cuda(), d_table.clone())                                               # accumulates
+    np.testing.assert_allclose(acc.cpu().numpy(), 2 * d_table.cpu().numpy(), rtol=1e-6)
