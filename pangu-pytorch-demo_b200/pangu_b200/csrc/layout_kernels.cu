@@ -141,13 +141,32 @@ patch_recover_kernel(const float* __restrict__ y, float* __restrict__ out, int l
   }
 }
 
-// DownSample: 2x2 merge + LN(4C) (layers.py:501-519); one warp per output row.
+// 2- and 4-element vector accesses of the row kernels below (8 / 16 bytes per lane instead of 2 / 4)
+__device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
+  const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st2(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+
+// DownSample: 2x2 merge + LN(4C) (layers.py:501-519); one warp per output row, a lane owns groups of 4 consecutive
+// features (C % 4 == 0, so a group never straddles two source tokens): 16-byte loads, 8- / 16-byte stores.
 template <typename TO, int kPerLane>
 __global__ void __launch_bounds__(256)
 downsample_merge_ln_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                            const float* __restrict__ beta, TO* __restrict__ out, int Z, int H, int W,
                            int C, float eps) {
   constexpr int F = kPerLane * 32;                 // 4C
+  constexpr int G = kPerLane / 4;                  // groups of 4 per lane
+  static_assert(kPerLane % 4 == 0, "downsample_merge_ln: 4-element groups");
   const int H2 = (H + 1) / 2, W2 = W / 2;
   const long long rows = (long long)Z * H2 * W2;
   const int lane = threadIdx.x & 31;
@@ -156,35 +175,42 @@ downsample_merge_ln_kernel(const float* __restrict__ x, const float* __restrict_
   const int w2 = (int)(row % W2);
   const long long zh = row / W2;
   const int h2 = (int)(zh % H2), z = (int)(zh / H2);
-  float v[kPerLane];
+  float4 v[G];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kPerLane; ++i) {
-    const int f = i * 32 + lane;
+  for (int i = 0; i < G; ++i) {
+    const int f = (i * 32 + lane) * 4;
     const int q = f / C, c = f - q * C;            // f = dh*2C + dw*C + c
     const int h = 2 * h2 + (q >> 1), w = 2 * w2 + (q & 1);
-    v[i] = (h < H) ? __ldg(x + (((long long)z * H + h) * W + w) * C + c) : 0.f;
-    s += v[i];
+    v[i] = (h < H) ? __ldg(reinterpret_cast<const float4*>(x + (((long long)z * H + h) * W + w) * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mean = warp_sum(s) * (1.0f / F);
   float qv = 0.f;
 #pragma unroll
-  for (int i = 0; i < kPerLane; ++i) { const float d = v[i] - mean; qv = fmaf(d, d, qv); }
+  for (int i = 0; i < G; ++i) {
+    const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+    qv = fmaf(d0, d0, qv); qv = fmaf(d1, d1, qv); qv = fmaf(d2, d2, qv); qv = fmaf(d3, d3, qv);
+  }
   const float rstd = rsqrtf(warp_sum(qv) * (1.0f / F) + eps);
 #pragma unroll
-  for (int i = 0; i < kPerLane; ++i) {
-    const int f = i * 32 + lane;
-    out[row * F + f] = from_f32<TO>((v[i] - mean) * rstd * __ldg(gamma + f) + __ldg(beta + f));
+  for (int i = 0; i < G; ++i) {
+    const int f = (i * 32 + lane) * 4;
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + f)), be = __ldg(reinterpret_cast<const float4*>(beta + f));
+    st4(out + row * F + f, (v[i].x - mean) * rstd * ga.x + be.x, (v[i].y - mean) * rstd * ga.y + be.y,
+        (v[i].z - mean) * rstd * ga.z + be.z, (v[i].w - mean) * rstd * ga.w + be.w);
   }
 }
 
-// UpSample: pixel shuffle + crop + LN(C') (layers.py:546-563); one warp per output row.
+// UpSample: pixel shuffle + crop + LN(C') (layers.py:546-563); one warp per output row, a lane owns pairs of features.
 template <typename TI, typename TO, int kPerLane>
 __global__ void __launch_bounds__(256)
 upsample_shuffle_ln_kernel(const TI* __restrict__ y, const float* __restrict__ gamma,
                            const float* __restrict__ beta, TO* __restrict__ out, int Z, int H2, int W2,
                            int H, float eps) {
   constexpr int Co = kPerLane * 32;
+  constexpr int G = kPerLane / 2;                  // pairs per lane
+  static_assert(kPerLane % 2 == 0, "upsample_shuffle_ln: 2-element groups");
   const int W = 2 * W2;
   const long long rows = (long long)Z * H * W;
   const int lane = threadIdx.x & 31;
@@ -194,19 +220,20 @@ upsample_shuffle_ln_kernel(const TI* __restrict__ y, const float* __restrict__ g
   const long long zh = row / W;
   const int h = (int)(zh % H), z = (int)(zh / H);
   const TI* src = y + (((long long)z * H2 + (h >> 1)) * W2 + (w >> 1)) * (4 * Co) + ((h & 1) * 2 + (w & 1)) * Co;
-  float v[kPerLane];
+  float2 v[G];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kPerLane; ++i) { v[i] = to_f32<TI>(src[i * 32 + lane]); s += v[i]; }
+  for (int i = 0; i < G; ++i) { v[i] = ld2(src + (i * 32 + lane) * 2); s += v[i].x + v[i].y; }
   const float mean = warp_sum(s) * (1.0f / Co);
   float qv = 0.f;
 #pragma unroll
-  for (int i = 0; i < kPerLane; ++i) { const float d = v[i] - mean; qv = fmaf(d, d, qv); }
+  for (int i = 0; i < G; ++i) { const float d0 = v[i].x - mean, d1 = v[i].y - mean; qv = fmaf(d0, d0, qv); qv = fmaf(d1, d1, qv); }
   const float rstd = rsqrtf(warp_sum(qv) * (1.0f / Co) + eps);
 #pragma unroll
-  for (int i = 0; i < kPerLane; ++i) {
-    const int c = i * 32 + lane;
-    out[row * Co + c] = from_f32<TO>((v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c));
+  for (int i = 0; i < G; ++i) {
+    const int c = (i * 32 + lane) * 2;
+    const float2 ga = __ldg(reinterpret_cast<const float2*>(gamma + c)), be = __ldg(reinterpret_cast<const float2*>(beta + c));
+    st2(out + row * Co + c, (v[i].x - mean) * rstd * ga.x + be.x, (v[i].y - mean) * rstd * ga.y + be.y);
   }
 }
 
