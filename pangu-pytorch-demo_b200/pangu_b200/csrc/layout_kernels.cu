@@ -141,22 +141,6 @@ patch_recover_kernel(const float* __restrict__ y, float* __restrict__ out, int l
   }
 }
 
-// 2- and 4-element vector accesses of the row kernels below (8 / 16 bytes per lane instead of 2 / 4)
-__device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-__device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
-  const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
-  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
-}
-__device__ __forceinline__ void st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
-__device__ __forceinline__ void st2(__nv_bfloat16* p, float a, float b) {
-  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
-}
-__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
-__device__ __forceinline__ void st4(__nv_bfloat16* p, float a, float b, float c, float d) {
-  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
-  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
-}
-
 // DownSample: 2x2 merge + LN(4C) (layers.py:501-519); one warp per output row, a lane owns groups of 4 consecutive
 // features (C % 4 == 0, so a group never straddles two source tokens): 16-byte loads, 8- / 16-byte stores.
 template <typename TO, int kPerLane>
