@@ -316,6 +316,8 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
   __syncthreads();
   tc::tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  tc::griddep_wait();                                         // PDL (tc_common.cuh): the set-up overlapped the predecessor's tail
+  tc::griddep_launch_dependents();
   if (is_consumer) swap_tile_fn(s_ctx, u0, ctid, 1);          // first bias tile (the TMA warp is already fetching windows)
 
   const bool trc = kTrace && dbg && blockIdx.x == 0 && lane == 0;
@@ -777,8 +779,10 @@ int launch_window_attention_tc(const void* qkv, const void* halo_qkv, const void
   if (forced > 0 && forced < nteams) nteams = forced;
   if (nteams > npairs) nteams = npairs;
   static const int dbg = []() { const char* e = getenv("PANGU_ATTN_DBG"); return e ? atoi(e) : 0; }();
-  window_attention_tc_kernel<<<(unsigned)(nteams * g.heads), kThreads, kSmemBytes, st>>>(
-      maps, qkv_bias, (const __nv_bfloat16*)earth_bias, (__nv_bfloat16*)out, (__nv_bfloat16*)halo_out, g, bd, roll, lse, dbg);
+  cudaError_t le = tc::launch_pdl(window_attention_tc_kernel, dim3((unsigned)(nteams * g.heads)), dim3(kThreads), kSmemBytes, st,
+                                  maps, qkv_bias, (const __nv_bfloat16*)earth_bias, (__nv_bfloat16*)out, (__nv_bfloat16*)halo_out, g, bd,
+                                  roll, lse, dbg);
+  if (le != cudaSuccess) { set_error("window_attention_tc: launch: %s", cudaGetErrorString(le)); return PANGU_ERR_CUDA; }
   return check_launch("window_attention_tc");
 }
 

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <cstdio>
 
 #include "common.cuh"
@@ -284,6 +285,15 @@ bool encode_tmap_3d_bf16(CUtensorMap* map, const void* gptr, uint64_t d0, uint64
 int num_sms();
 
 // ---------------------------------------------------------------- misc math
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute (launch_pdl below)
+// may start while its predecessor in the stream is still running, as soon as every CTA of the predecessor has executed
+// launch_dependents (or exited) and SM resources are free -- in practice: its CTAs set up barriers / TMEM / tensor maps
+// on SMs whose previous CTA has already exited (the tail of a persistent kernel).  griddep_wait() blocks until ALL
+// prerequisite grids have completed and their memory is visible; every global access of the kernel comes after it.
+// Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Pull `bytes` (multiple of 16, 16-byte aligned) of global memory into L2 without a destination: no registers, no smem.
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -341,6 +351,25 @@ __device__ __forceinline__ uint32_t gelu_fast_h2(float a, float b) {
 // Instruction descriptor for kind::f16 with fp16 A/B operands and fp32 accumulation.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Host: launch with the PDL attribute ($PANGU_B200_PDL=0: plain launch).  Only the persistent tensor-core kernels use it --
+// a waiting dependent CTA holds a whole SM's shared memory, which must not be taken from a predecessor that still has
+// CTAs to schedule.
+inline bool pdl_enabled() {
+  static const bool on = []() { const char* e = getenv("PANGU_B200_PDL"); return e == nullptr || atoi(e) != 0; }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 }  // namespace tc

@@ -125,6 +125,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();                                // PDL: the set-up above overlapped the predecessor's tail; its results from here on
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
@@ -418,7 +420,8 @@ static int launch_gemm_t(const void* A, long long lda, const void* W, GemmArgs& 
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(tmA, tmA2, tmB, tmOut, tmXb, tmRes, a);
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kThreads), Cfg::SMEM_BYTES, st, tmA, tmA2, tmB, tmOut, tmXb, tmRes, a);
+  if (le != cudaSuccess) { set_error("gemm_bf16: launch: %s", cudaGetErrorString(le)); return PANGU_ERR_CUDA; }
   return check_launch("gemm_bf16");
 }
 

@@ -119,6 +119,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   cluster_sync_all();
+  griddep_wait();                                // PDL (tc_common.cuh): everything above overlapped the predecessor's tail
+  griddep_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -362,7 +364,8 @@ static int launch_gemm2_t(const void* A, long long lda, const void* W, Gemm2Args
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = a.pair_tiles < max_pairs ? a.pair_tiles : max_pairs;
-  kern<<<2 * pairs, kG2Threads, Cfg::SMEM_BYTES, st>>>(tmA, tmW, a);
+  cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(kG2Threads), Cfg::SMEM_BYTES, st, tmA, tmW, a);
+  if (le != cudaSuccess) { set_error("gemm2_bf16: launch: %s", cudaGetErrorString(le)); return PANGU_ERR_CUDA; }
   return check_launch("gemm2_bf16");
 }
 

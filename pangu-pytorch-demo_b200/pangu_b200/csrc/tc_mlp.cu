@@ -141,6 +141,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   cluster_sync_all();                                         // both CTAs own their TMEM before any MMA
+  griddep_wait();                                             // PDL (tc_common.cuh): the set-up overlapped the predecessor's tail
+  griddep_launch_dependents();
   if (a.stagger > 0 && (pair0 & 1)) {
     const long long t0 = clock64();
     while (clock64() - t0 < a.stagger) __nanosleep(200);
@@ -403,7 +405,8 @@ static int launch_mlp_t(const void* x, const void* w1, const void* w2, MlpArgs& 
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = a.pair_tiles < max_pairs ? a.pair_tiles : max_pairs;
-  kern<<<2 * pairs, kMlpThreads, Cfg::SMEM_BYTES, st>>>(tmX, tmW1, tmW2, tmOut, tmXb, tmRes, a);
+  cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(kMlpThreads), Cfg::SMEM_BYTES, st, tmX, tmW1, tmW2, tmOut, tmXb, tmRes, a);
+  if (le != cudaSuccess) { set_error("mlp_fused: launch: %s", cudaGetErrorString(le)); return PANGU_ERR_CUDA; }
   return check_launch("mlp_fused");
 }
 

@@ -40,3 +40,22 @@ with torch.no_grad():
         ms = timeit(lambda: emulate_bands(model, world, *args))
         print(f"bands x{world} back to back on one GPU: {ms:.2f} ms total = {ms / world:.2f} ms per band on average "
               f"({ms / base:.3f} x un-sharded)")
+
+    # per kernel class: where the small per-rank problem loses (eager launches with CUDA events around each)
+    from pangu_b200 import ops  # noqa: E402
+
+    def classes(fn):
+        fn()
+        torch.cuda.synchronize()
+        ops.start_kernel_timing()
+        fn()
+        torch.cuda.synchronize()
+        return ops.stop_kernel_timing()
+
+    t1 = classes(lambda: model(*args))
+    t8 = classes(lambda: emulate_bands(model, 8, *args))
+    print(f"{'kernel class':42s} {'x1 ms':>8s} {'x8 ms':>8s}  ratio")
+    for k in sorted(t1, key=lambda k: -t1[k][1]):
+        if k in t8:
+            print(f"{k:42s} {t1[k][1]:8.3f} {t8[k][1]:8.3f}  {t8[k][1] / t1[k][1]:.2f}")
+    print("only in bands:", {k: round(v[1], 3) for k, v in t8.items() if k not in t1})
