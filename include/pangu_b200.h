@@ -64,6 +64,10 @@ const char* pangu_last_error(void);
 int pangu_abi_version(void);
 /* 1 if the library was built with tcgen05/TMA kernels for sm_100a (always, for this build). */
 int pangu_has_tcgen05(void);
+/* Programmatic dependent launch between the persistent tensor-core kernels (their set-up overlaps the predecessor's tail).
+ * Process-wide switch, off by default; returns the previous setting.  Turn it on around work that is alone on the device
+ * (a captured inference step); leave it off when NCCL kernels run concurrently on another stream (DDP fine-tune). */
+int pangu_set_pdl(int on);
 
 /* ------------------------------------------------------------------ index kernels (bit-exact) */
 

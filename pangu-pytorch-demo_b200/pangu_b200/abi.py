@@ -38,6 +38,7 @@ _PROTOS = {
     "pangu_window_reverse": (c_int, [c_void_p, c_void_p, POINTER(Geom), c_int, c_int, c_void_p]),
     "pangu_window_source_index": (c_int, [c_void_p, POINTER(Geom), c_int, c_void_p]),
     "pangu_shift_mask": (c_int, [c_void_p, POINTER(Geom), c_void_p]),
+    "pangu_set_pdl": (c_int, [c_int]),
     "pangu_position_index": (c_int, [c_void_p, c_void_p]),
     "pangu_bias_table_expand": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "pangu_bias_table_reduce": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),

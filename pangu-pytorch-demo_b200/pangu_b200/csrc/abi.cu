@@ -64,11 +64,18 @@ int launch_window_attention_bwd(const void* qkv, const float* qkv_bias, const vo
 
 }  // namespace pangu
 
+namespace pangu { namespace tc { int g_pdl_runtime = 0; } }
+
 using namespace pangu;
 
 extern "C" const char* pangu_last_error(void) { return g_err; }
 extern "C" int pangu_abi_version(void) { return 1; }
 extern "C" int pangu_has_tcgen05(void) { return 1; }
+extern "C" int pangu_set_pdl(int on) {
+  const int prev = pangu::tc::g_pdl_runtime;
+  pangu::tc::g_pdl_runtime = on != 0;
+  return prev;
+}
 
 extern "C" int pangu_linear(const void* A, int64_t lda, const void* W, const float* bias, void* out,
                             int64_t ldo, int64_t M, int32_t K, int32_t N, int act, int dtype,

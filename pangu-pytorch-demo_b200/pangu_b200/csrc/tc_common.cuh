@@ -353,12 +353,16 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// Host: launch with the PDL attribute ($PANGU_B200_PDL=0: plain launch).  Only the persistent tensor-core kernels use it --
-// a waiting dependent CTA holds a whole SM's shared memory, which must not be taken from a predecessor that still has
-// CTAs to schedule.
+// Host: launch with the PDL attribute.  Only the persistent tensor-core kernels use it -- a waiting dependent CTA holds a
+// whole SM's shared memory, which must not be taken from a predecessor that still has CTAs to schedule.  OFF by default and
+// switched on by the caller around work that is alone on the device (pangu_set_pdl(1): pangu_b200.graph.GraphedForward
+// captures the inference step with it): next to concurrent NCCL all-reduce kernels of a DDP fine-tune step the early-resident
+// dependents cost 16 % (2 GPUs: 73.4 -> 85.1 ms per step), so the fine-tune path never enables it.
+// $PANGU_B200_PDL=0 / 1 forces it off / on everywhere.
+extern int g_pdl_runtime;                                   // abi.cu
 inline bool pdl_enabled() {
-  static const bool on = []() { const char* e = getenv("PANGU_B200_PDL"); return e == nullptr || atoi(e) != 0; }();
-  return on;
+  static const int forced = []() { const char* e = getenv("PANGU_B200_PDL"); return e == nullptr ? -1 : (atoi(e) != 0 ? 1 : 0); }();
+  return forced >= 0 ? forced != 0 : g_pdl_runtime != 0;
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

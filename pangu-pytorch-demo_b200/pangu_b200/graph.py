@@ -14,7 +14,7 @@ weight caches are refreshed outside the graph).
 """
 import torch
 
-from . import ops
+from . import abi, ops
 from .abi import PanguError
 
 
@@ -42,6 +42,15 @@ class GraphedForward:
         self.recapture()
 
     def recapture(self):
+        # programmatic dependent launch (include/pangu_b200.h: pangu_set_pdl) is baked into the captured kernel nodes: the
+        # replayed step is alone on the device, which is where it pays (emulated 8-band step 23.05 -> 22.44 ms)
+        prev = abi.lib().pangu_set_pdl(1)
+        try:
+            return self._recapture()
+        finally:
+            abi.lib().pangu_set_pdl(prev)
+
+    def _recapture(self):
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
