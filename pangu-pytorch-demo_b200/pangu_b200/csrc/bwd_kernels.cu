@@ -167,15 +167,21 @@ colsum_kernel(const T* __restrict__ x, long long ld, long long M, int C, float* 
   if (col >= C) return;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   float a0 = 0.f, a1 = 0.f;
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += nwarps) {
-    const T* p = x + row * ld + col;
-    if (sizeof(T) == 2) {
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
-      a0 += f.x; a1 += f.y;
-    } else {
-      const float2 f = *reinterpret_cast<const float2*>(p);
-      a0 += f.x; a1 += f.y;
+  constexpr int U = 8;                               // rows in flight per warp (one 4- / 8-byte load per lane each)
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < M; row += nwarps * U) {
+    float2 f[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = row + u * nwarps;
+      f[u] = make_float2(0.f, 0.f);
+      if (r < M) {
+        const T* p = x + r * ld + col;
+        if (sizeof(T) == 2) f[u] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+        else f[u] = *reinterpret_cast<const float2*>(p);
+      }
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { a0 += f[u].x; a1 += f[u].y; }
   }
   atomicAdd(out + col, a0);
   atomicAdd(out + col + 1, a1);
