@@ -97,6 +97,7 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 // all bulk stores of this thread have finished READING their shared-memory source
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // all but the newest group
 
 // ---------------------------------------------------------------- TMEM
 // One full warp allocates `cols` (power of two >= 32) columns; base address lands in *dst_smem.

@@ -38,6 +38,7 @@ struct Gemm2Args {
   __nv_bfloat16* aux;
   float* colsum;
   int aux_mode;
+  int tma_out;                // bf16 output without an aux tensor: the staged [32 x 32] chunks leave through TMA bulk stores
 };
 enum { G2_AUX_NONE = 0, G2_AUX_PRE_OUT = 1, G2_AUX_GELU_BWD = 2 };
 
@@ -79,7 +80,8 @@ __device__ __forceinline__ int g2_stg_b16(int r, int cc) { return r * 64 + ((cc 
 
 template <int KB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kG2Threads, 1)
-gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const Gemm2Args a) {
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmOut, const Gemm2Args a) {
   using Cfg = Gemm2Cfg<KB>;
   constexpr int NSLOT = Cfg::NSLOT;
   extern __shared__ uint8_t smem_raw[];
@@ -105,6 +107,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
+    if (a.tma_out) tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(a_full, 1); mbar_init(a_empty, 1);
@@ -192,6 +195,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t stg = smem_u32(epi_smem) + (warp - 4) * 4096;
     const uint32_t s_bias_u32 = smem_u32(s_bias);
     int acc = 0;
+    int tma_half = 0;
     uint32_t tphase = 0;
     uint32_t v[32];
     // GELU_BWD: the aux (pre-activation) chunk of this warp is fetched ONE CHUNK AHEAD into registers, in the
@@ -255,10 +259,26 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
           }
           if (a.out_dtype == PANGU_BF16) {
+            const uint32_t stg_o = stg + (a.tma_out ? tma_half * 2048 : 0);
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc)
-              sts128(stg + g2_stg_b16(lane, cc), pack_bf16(f[8 * cc], f[8 * cc + 1]), pack_bf16(f[8 * cc + 2], f[8 * cc + 3]),
+              sts128(stg_o + g2_stg_b16(lane, cc), pack_bf16(f[8 * cc], f[8 * cc + 1]), pack_bf16(f[8 * cc + 2], f[8 * cc + 3]),
                      pack_bf16(f[8 * cc + 4], f[8 * cc + 5]), pack_bf16(f[8 * cc + 6], f[8 * cc + 7]));
+            if (a.tma_out) {
+              // The staging tile IS the SWIZZLE_64B image of a [32 rows x 32 bf16] box (g2_stg_b16): one elected lane hands it
+              // to the bulk-copy engine (full 64-byte row segments, rows past M clipped by the tensor map); two 2 KiB staging
+              // halves alternate, so only the store issued two chunks ago has to have been read out before a half is rewritten.
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(&tmOut, reinterpret_cast<const void*>(epi_smem + (warp - 4) * 4096 + tma_half * 2048), n, (int)m_base);
+                tma_store_commit();
+                tma_store_wait_read1();
+              }
+              tma_half ^= 1;
+              __syncwarp();
+              continue;
+            }
             __syncwarp();
             __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
             if (!gelu_bwd) {
@@ -338,6 +358,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         acc ^= 1;
       }
     }
+    if (a.tma_out && lane == 0) tma_store_wait_all();          // the staging tiles must outlive the bulk stores that read them
   }
 
   tcgen05_before_sync();
@@ -355,6 +376,10 @@ static int launch_gemm2_t(const void* A, long long lda, const void* W, Gemm2Args
   if (!encode_tmap_2d_bf16(&tmW, W, K, (uint64_t)a.N, (uint64_t)K * 2, 64, G2_BN / 2)) return PANGU_ERR_CUDA;
   a.n_tiles = a.N / G2_BN;
   a.pair_tiles = (int)((a.M + 255) / 256);
+  static const bool tma_out_on = []() { const char* e = getenv("PANGU_B200_GEMM2_TMA_OUT"); return e == nullptr || atoi(e) != 0; }();
+  a.tma_out = (tma_out_on && a.out_dtype == PANGU_BF16 && a.aux_mode == G2_AUX_NONE && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0) ? 1 : 0;
+  CUtensorMap tmOut = tmA;                                    // placeholder when the store path is off (never dereferenced)
+  if (a.tma_out && !encode_tmap_2d(&tmOut, 1, a.out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldo * 2, 32, 32, 64)) return PANGU_ERR_CUDA;
   auto kern = gemm2_bf16_kernel<KB>;
   static bool configured = false;
   if (!configured) {
@@ -364,7 +389,7 @@ static int launch_gemm2_t(const void* A, long long lda, const void* W, Gemm2Args
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = a.pair_tiles < max_pairs ? a.pair_tiles : max_pairs;
-  cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(kG2Threads), Cfg::SMEM_BYTES, st, tmA, tmW, a);
+  cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(kG2Threads), Cfg::SMEM_BYTES, st, tmA, tmW, tmOut, a);
   if (le != cudaSuccess) { set_error("gemm2_bf16: launch: %s", cudaGetErrorString(le)); return PANGU_ERR_CUDA; }
   return check_launch("gemm2_bf16");
 }
