@@ -64,3 +64,21 @@ def test_position_index(ops, goldens):
 def test_windowed_identity_mode(ops):
     idx = ops.window_source_index(2, 7, 24, 2, "cuda").cpu().numpy()      # nLon=2, T=2
     assert np.array_equal(idx.reshape(-1), np.arange(idx.size))
+
+
+# geometries outside the model's two stages (ragged / minimal grids): the index kernels are closed forms of (Z, H, W), pinned on
+# the CPU against the reference's tensor-op sequence by tests/test_oracle_properties.py
+SMALL = [(2, 1, 12), (4, 7, 24), (8, 13, 36), (6, 19, 12), (8, 25, 48)]
+
+
+@pytest.mark.parametrize("Z,H,W", SMALL)
+@pytest.mark.parametrize("roll", [0, 1])
+def test_index_kernels_on_small_and_minimal_grids(ops, Z, H, W, roll):
+    assert np.array_equal(ops.window_source_index(Z, H, W, roll, "cuda").cpu().numpy(), orc.window_source_index(Z, H, W, bool(roll)))
+    x = torch.randn(Z * H * W, 8, generator=torch.Generator().manual_seed(H))
+    src = torch.from_numpy(orc.window_source_index(Z, H, W, bool(roll)))
+    win = ops.window_partition(x.cuda(), Z, H, W, roll)
+    assert torch.equal(win.cpu(), torch.cat((x, torch.zeros(1, 8)), 0)[src])
+    assert torch.equal(ops.window_reverse(win, Z, H, W, roll).cpu(), x)
+    if H >= 7:
+        assert np.array_equal(ops.shift_mask(Z, H, W, "cuda").cpu().numpy(), orc.shift_mask(Z, H, W))
