@@ -381,6 +381,13 @@ int num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    // $PANGU_B200_SMS=<even count>: grid cap of the persistent kernels -- leaves SMs to NCCL all-reduce CTAs that run next to
+    // a DDP fine-tune step; unset = every SM
+    const char* e = getenv("PANGU_B200_SMS");
+    if (e != nullptr) {
+      const int cap = atoi(e) & ~1;
+      if (cap >= 2 && cap < n) n = cap;
+    }
   }
   return n;
 }
