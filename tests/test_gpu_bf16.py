@@ -134,3 +134,23 @@ def test_full_model_bf16_vs_reference_golden(goldens):
     e1 = check_digest(goldens, "output", out, TOL)
     e2 = check_digest(goldens, "output_surface", out_s, TOL)
     print(f"bf16 full model rel-L2: output {e1:.2e} surface {e2:.2e}")
+
+
+def test_batched_input_is_a_loop_over_samples(L):
+    """The reference is only correct for batch 1 (its window reverse assumes B = 1); the B200 modules take
+    [B, N, C] like the reference's signatures and process the samples one at a time: row b of the batched result is
+    bit-identical to the single-sample call."""
+    pfx = "layers.EarthSpecificLayer0.blocks.EarthSpecificBlock1."
+    Z, H, W, dim, heads = 8, 181, 24, 192, 6
+    blk = load_params(L.EarthSpecificBlock(dim, 0.0, heads, "cpu"), orc.synth_params(seed=0, only_prefix=pfx), pfx)
+    L.set_compute_dtype(blk, "bf16")
+    x = torch.randn(2, Z * H * W, dim, generator=torch.Generator().manual_seed(11)).cuda()
+    with torch.no_grad():
+        y2 = blk(x, Z, H, W, True)
+        y0, y1 = blk(x[0:1], Z, H, W, True), blk(x[1:2], Z, H, W, True)
+    assert y2.shape == x.shape
+    assert torch.equal(y2[0], y0[0]) and torch.equal(y2[1], y1[0])
+    mlp = blk.linear
+    with torch.no_grad():
+        m2 = mlp(x[:, :4096])
+    assert torch.equal(m2[1], mlp(x[1:2, :4096])[0])
