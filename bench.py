@@ -10,10 +10,14 @@ configs[1]).  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for ho
   e2e       the same through the public API (models.pangu_model.PanguModel.forward) starting from pinned
             HOST buffers, H2D of the 287 MB inputs and D2H of the 287 MB outputs inside the timed region
   roofline  the dominant kernel class (tcgen05 GEMM), FLOPs / CUDA-event time vs the measured bf16 peak
-  cpu_baseline  the oracle port (oracle/pangu_oracle.py) timed on the host cores on a bounded sample
+  cpu_baseline  ONE whole forward of the UNMODIFIED reference (baseline/_ref, see baseline/run_reference.py) on all
+            host cores, run in a subprocess
 
---impl reference times the reference algorithm's CPU implementation (the oracle port: the reference is a
-Python project that cannot travel to the GPU box) on all host cores.
+--impl reference runs the unmodified reference PanguModel from the git-ignored baseline/_ref (installed by
+__graft_entry__.build() where /root/reference exists; it travels with the gpurun snapshot) on all host cores:
+1 warm-up + up to 3 timed WHOLE forwards (the cap is stated in config.reference_arm; `steps`/`warmup` in the line
+are what was executed, `steps_requested`/`warmup_requested` what was asked).  Fallback if baseline/_ref is
+absent: the oracle port's full forward, labelled kind "port".  Nothing is extrapolated.
 """
 import argparse
 import json
@@ -34,10 +38,14 @@ FLOPS_TOTAL = 8.421e12            # algorithmic FLOPs of one forwar
 FLOPS_ATTN_MLP = 8.132e12         # attention + MLP blocks
 
 
+TRAFFIC_FILE = "profiles/r2_ncu_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")) \
+    else "profiles/r1_ncu_traffic.json"
+
+
 def ncu_traffic(kernel_tag):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r1_ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
-    p = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    (dram__bytes_read.sum + dram__bytes_write.sum of the un-sharded, full-grid launch), or None."""
+    p = os.path.join(ROOT, TRAFFIC_FILE)
     want = {"mlp_fused_bf16[C=384]": ("tc::mlp_fused_kernel<384>", 148), "mlp_fused_bf16[C=192]": ("tc::mlp_fused_kernel<192>", 148)}
     if kernel_tag not in want or not os.path.exists(p):
         return None
@@ -108,68 +116,67 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port on a bounded sample
+# CPU arm: the UNMODIFIED reference (baseline/_ref, see baseline/run_reference.py), whole forwards, all host cores
 # --------------------------------------------------------------------------------------------
-def cpu_reference_step(orc, torch, params, shrink, cache):
-    """One bounded sample of the forward on the CPU: ONE stage-A block and ONE stage-B block (rolled: the
-    expensive variant with the mask) at 1/shrink of the longitude extent, extrapolated to 4 A + 12 B blocks
-    and the full width; the non-block ops (3.4 % of the FLOPs) are extrapolated by FLOP share.
-    Returns the extrapolated seconds of one full forward."""
-    Wa, Wb = 360 // shrink, 180 // shrink
-    Wa, Wb = max(12, Wa - Wa % 12), max(12, Wb - Wb % 12)
-    if "xa" not in cache:
-        g = torch.Generator().manual_seed(3)
-        cache["xa"] = torch.randn(1, 8 * 181 * Wa, 192, generator=g)
-        cache["xb"] = torch.randn(1, 8 * 91 * Wb, 384, generator=g)
-    pa = "layers.EarthSpecificLayer0.blocks.EarthSpecificBlock1."
-    pb = "layers.EarthSpecificLayer1.blocks.EarthSpecificBlock1."
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        orc.earth_block(cache["xa"], 8, 181, Wa, True, params, pa, 6)
-        t1 = time.perf_counter()
-        orc.earth_block(cache["xb"], 8, 91, Wb, True, params, pb, 12)
-        t2 = time.perf_counter()
-    ta, tb = (t1 - t0) * 360 / Wa, (t2 - t1) * 180 / Wb
-    blocks = 4 * ta + 12 * tb
-    return blocks * FLOPS_TOTAL / FLOPS_ATTN_MLP, {"block_A_s": ta, "block_B_s": tb, "W_A": Wa, "W_B": Wb}
+REF_ARM_MAX_STEPS, REF_ARM_MAX_WARMUP = 3, 1
+# `config` is byte-identical in both arms (the driver compares them); what actually happened is in `launch_used`
+LAUNCH_NOTE = {"on": "b200 arm: cuda-graph replay, 1 graph launch per step (eager ctypes launches if capture fails, see launch_used)",
+               "off": "b200 arm: eager ctypes launches"}
+REF_ARM_NOTE = ("CPU arm = the UNMODIFIED reference PanguModel.eval() (baseline/_ref/models/{layers,pangu_model}.py) under "
+                "torch.no_grad(), fp32, all host cores, WHOLE forwards timed with perf_counter; --impl reference caps the "
+                f"run at {REF_ARM_MAX_WARMUP} warm-up + {REF_ARM_MAX_STEPS} timed forwards whatever --steps/--warmup say "
+                "(a forward takes ~20-60 s); the cpu_baseline leg of the default run times ONE forward without warm-up")
 
 
 def run_cpu_reference(args, as_impl):
+    """Times the reference's own CPU implementation of the path.  Preferred: the unmodified reference files in
+    baseline/_ref (kind "reference"), run in a subprocess (its package is called `models` like ours).  Fallback
+    when baseline/_ref did not travel: the oracle port's full forward (kind "port").  Nothing is extrapolated:
+    every reported time is a whole PanguModel forward that was actually executed."""
+    steps, warm = ((max(1, min(args.steps, REF_ARM_MAX_STEPS)), min(args.warmup, REF_ARM_MAX_WARMUP)) if as_impl else (1, 0))
+    script = os.path.join(ROOT, "baseline", "run_reference.py")
+    r = None
+    if os.path.exists(script):
+        p = subprocess.run([sys.executable, script, "--steps", str(steps), "--warmup", str(warm)],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        try:
+            r = json.loads(p.stdout.strip().splitlines()[-1])
+        except (IndexError, ValueError):
+            sys.stderr.write(f"[bench] reference arm failed (rc {p.returncode}): {p.stderr[-2000:]}\n")
+            r = None
+        if r is not None and "unavailable" in r:
+            sys.stderr.write(f"[bench] {r['unavailable']}; falling back to the oracle port\n")
+            r = None
+    if r is None:
+        r = run_cpu_port(steps, warm)
+    sec = r["seconds_per_forward"]
+    what = ("the UNMODIFIED reference PanguModel.eval() forward (baseline/_ref), " if r["kind"] == "reference" else
+            "the oracle port's pangu_forward (baseline/_ref absent on this box), ")
+    sample = (what + f"{r['warmup']} warm-up + {r['steps']} timed WHOLE forwards at 721x1440 batch 1 fp32 under no_grad, "
+              f"{r['cores']} threads on {r.get('cpu_model', 'unknown CPU')}, torch {r['torch']}; per-forward seconds: "
+              + ", ".join(f"{t:.1f}" for t in r["times_s"]))
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": sample,
+            "seconds_per_forward": sec, "steps": r["steps"], "warmup": r["warmup"], "times": r["times_s"]}
+
+
+def run_cpu_port(steps, warm):
+    """Fallback CPU arm: the oracle's restatement of the whole forward (oracle/pangu_oracle.py pangu_forward)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import pangu_oracle as orc
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    pa = "layers.EarthSpecificLayer0.blocks.EarthSpecificBlock1."
-    pb = "layers.EarthSpecificLayer1.blocks.EarthSpecificBlock1."
-    params = orc.synth_params(0, only_prefix=pa)
-    params.update(orc.synth_params(0, only_prefix=pb))
-    steps, warm = (args.steps, args.warmup) if as_impl else (2, 1)
-    # calibrate the sample size so that the whole run stays within ~150 s (as_impl) / ~25 s (baseline leg)
-    cache = {}
-    t0 = time.perf_counter()
-    est, _ = cpu_reference_step(orc, torch, params, 15, cache)
-    calib = time.perf_counter() - t0                       # seconds for 1/15 of the width
-    budget = (150.0 if as_impl else 25.0) / max(1, steps + warm)
-    shrink = 1
-    for s in (1, 2, 3, 5, 15):
-        shrink = s
-        if calib * 15 / s <= budget:
-            break
-    cache = {}
-    for _ in range(warm):
-        cpu_reference_step(orc, torch, params, shrink, cache)
-    times, detail = [], {}
-    for _ in range(steps):
-        sec, detail = cpu_reference_step(orc, torch, params, shrink, cache)
-        times.append(sec)
-    sec = sum(times) / len(times)
-    sample = (f"1 rolled stage-A block + 1 rolled stage-B block of the oracle at 1/{shrink} of the longitude extent "
-              f"(W={detail['W_A']}/{detail['W_B']}), extrapolated to 4 A + 12 B blocks x full width x "
-              f"{FLOPS_TOTAL / FLOPS_ATTN_MLP:.3f} (non-block FLOP share); torch {torch.__version__} CPU fp32, {cores} threads")
-    return {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-            "seconds_per_forward": sec, "detail": detail, "steps": steps, "warmup": warm, "times": times}
-
+    params = orc.synth_params(0)
+    inp, inp_s, stats, maps, const_h = orc.synth_inputs(1)
+    times = []
+    with torch.no_grad():
+        for i in range(warm + steps):
+            t0 = time.perf_counter()
+            orc.pangu_forward(params, inp, inp_s, stats, maps, const_h)
+            if i >= warm:
+                times.append(time.perf_counter() - t0)
+    return {"kind": "port", "cores": cores, "torch": torch.__version__, "steps": steps, "warmup": warm,
+            "times_s": times, "seconds_per_forward": sum(times) / len(times)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -289,17 +296,104 @@ def run_finetune(args, rank, world, dev, torch, dist, orc, PanguModel, ops):
 
 
 # --------------------------------------------------------------------------------------------
+# iterative rollout (BASELINE configs[2]): the 24 h model chained 7 times, state resident on the device
+# --------------------------------------------------------------------------------------------
+def run_rollout(args, rank, world, dev, torch, dist, orc, PanguModel, ops, chain=7):
+    from pangu_b200.rollout import Rollout
+    model = PanguModel(device="cpu")
+    model.load_state_dict(orc.synth_params(seed=0), strict=True)
+    model = model.to(dev).eval().set_compute_dtype(args.dtype)
+    inp, inp_s, stats, maps, const_h = orc.synth_inputs(seed=1 + rank)
+    sm, ss, um, us = stats                                   # weatherStatistics_output layout, era5_data/utils_data.py:395-421
+    f = lambda t: t.flip(0).permute(1, 3, 0, 2).unsqueeze(-1).contiguous()
+    last = (sm.view(1, 4, 1, 1), ss.view(1, 4, 1, 1), f(um), f(us))
+    ro = Rollout(model, stats, last, maps, const_h, graph=args.graph == "on")
+    h_in = (inp.pin_memory(), inp_s.pin_memory())
+    d_in = (inp.to(dev), inp_s.to(dev))
+    h_out = [(torch.empty((5, 13, 721, 1440)).pin_memory(), torch.empty((4, 721, 1440)).pin_memory()) for _ in range(2)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def chain_resident():
+        for _o, _os in ro.run(d_in[0], d_in[1], steps=chain):
+            pass
+
+    def chain_e2e():
+        a, b = h_in[0].to(dev, non_blocking=True), h_in[1].to(dev, non_blocking=True)
+        for k, (o, os_) in enumerate(ro.run(a, b, steps=chain)):        # every lead time goes back to the host
+            h_out[k % 2][0].copy_(o.reshape(5, 13, 721, 1440), non_blocking=True)
+            h_out[k % 2][1].copy_(os_.reshape(4, 721, 1440), non_blocking=True)
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    chains = max(1, (args.steps + chain - 1) // chain)       # --steps counts forecast steps; whole chains are timed
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(1, (args.warmup + chain - 1) // chain)):
+        chain_resident()
+    ops.LAUNCHES = 0
+    total_ms = timed(chain_resident, chains)
+    launches = ops.LAUNCHES
+    clocks = sampler.stop() if rank == 0 else None
+    steps = chains * chain
+    chain_e2e()
+    e2e_ms = timed(chain_e2e, chains)
+    peaks = load_peaks()
+    if rank == 0:
+        value = world * steps / (total_ms / 1000.0)
+        line = {"metric": "24h forecast steps/s at 721x1440 bf16, 7-step iterative rollout", "value": value, "unit": UNIT, "n_gpus": world,
+                "steps": steps, "warmup": args.warmup, "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic (seeded random-init weights, ERA5-shaped inputs)",
+                "config": {"workload": "Iterative rollout: 24h model chained 7 steps, batch 1, state resident on the device (BASELINE.json configs[2])",
+                           "chain": chain, "chains_timed": chains, "parallelism": f"replicas x{world}",
+                           "launch": LAUNCH_NOTE[args.graph], "de-normalisation": "fused into the patch-recover scatter (normBackData)",
+                           "cache": "activations per step (>= 6 GB) exceed the 126 MB L2; no flush needed"},
+                "e2e": {"value": world * steps / (e2e_ms / 1000.0), "unit": UNIT, "ms_per_step": e2e_ms / steps,
+                        "h2d_bytes_per_step": (inp.numel() + inp_s.numel()) * 4 // chain, "d2h_bytes_per_step": (inp.numel() + inp_s.numel()) * 4,
+                        "api": "pangu_b200.rollout.Rollout.run: initial state from pinned host memory once per chain, every lead time copied back to pinned host memory"},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"bound": "tensor", "achieved": FLOPS_TOTAL * value / world / 1e12, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                             "frac": FLOPS_TOTAL * value / world / 1e12 / peaks["tf_sust"], "traffic": None,
+                             "note": "whole model: 8.421 TFLOP per forecast step / step time (per-kernel figures: default mode)"},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        threading.Timer(15.0, lambda: os._exit(0)).start()
+        dist.destroy_process_group()
+        os._exit(0)
+
+
+# --------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "bands", "finetune"],
+    ap.add_argument("--mode", default="auto", choices=["auto", "replicas", "bands", "finetune", "rollout"],
                     help="multi-GPU partition: replicas = one forecast per GPU (weak scaling); bands = ONE forecast "
                          "sharded over latitude bands with NCCL halo exchange (strong scaling, BASELINE configs[3]); "
                          "finetune = BASELINE configs[4]: fwd + loss + bwd + NCCL gradient all-reduce + Adam, one sample per "
-                         "GPU (data parallel, weak scaling); auto = bands when N > 1")
+                         "GPU (data parallel, weak scaling); rollout = BASELINE configs[2]: the 24 h model chained 7 times on "
+                         "the device; auto = bands when N > 1")
     ap.add_argument("--dp", default="ddp", choices=["buckets", "ddp"],
                     help="--mode finetune gradient all-reduce: pangu_b200.dist.GradientAllReducer or torch DDP (what the "
                          "reference uses, finetune/finetune_fully.py:220)")
@@ -319,8 +413,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     mode = args.mode if args.mode != "auto" else ("bands" if world > 1 else "replicas")
-    if mode == "finetune" and args.impl == "reference":
-        raise SystemExit("--impl reference times the forward (the headline metric); --mode finetune has no CPU arm")
+    if mode in ("finetune", "rollout") and args.impl == "reference":
+        raise SystemExit("--impl reference times the forward (the headline metric); --mode finetune / rollout have no CPU arm")
     if mode == "bands" and world not in (1, 2, 4, 8):
         mode = "replicas"
     par = (f"replicas x{world} (one forecast per GPU, no data-path collective)" if mode == "replicas" else
@@ -330,15 +424,19 @@ def main():
                           + ("" if mode == "replicas" else " sharded as configs[3]") + ")",
               "grid": "13x721x1440 upper-air x5 + 721x1440 surface x4", "tokens": "521280@C192 + 131040@C384",
               "blocks": 16, "params": 276659936, "parallelism": par, "mode": mode,
-              "cache": "inputs+activations per step (>= 6 GB) exceed the 126 MB L2; no flush needed"}
+              "cache": "inputs+activations per step (>= 6 GB) exceed the 126 MB L2; no flush needed",
+              "reference_arm": REF_ARM_NOTE}
 
     if args.impl == "reference":
         if rank != 0:
             return
         r = run_cpu_reference(args, as_impl=True)
+        config["launch"] = LAUNCH_NOTE[args.graph]
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * r["seconds_per_forward"],
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "steps": r["steps"], "warmup": r["warmup"], "steps_requested": args.steps, "warmup_requested": args.warmup,
+                "ms_per_step": 1000.0 * r["seconds_per_forward"],
+                "higher_is_better": True, "scaling": "weak" if mode == "replicas" else "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic (seeded random-init weights, ERA5-shaped inputs)",
                 "config": config, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -361,6 +459,8 @@ def main():
 
     if mode == "finetune":
         return run_finetune(args, rank, world, dev, torch, dist, orc, PanguModel, ops)
+    if mode == "rollout":
+        return run_rollout(args, rank, world, dev, torch, dist, orc, PanguModel, ops)
 
     model = PanguModel(device="cpu")
     model.load_state_dict(orc.synth_params(seed=0), strict=True)
@@ -370,6 +470,7 @@ def main():
         from pangu_b200.dist import BandedPangu, BandPlan
         inp, inp_s, stats, maps, const_h = orc.synth_inputs(seed=1)
         plan = BandPlan(world, rank)
+        full_inputs = (inp, inp_s, maps, const_h) if world > 1 else None       # for the post-timing band check
         inp, inp_s, maps, const_h = plan.slice_inputs(inp[0], inp_s[0], maps, const_h)
         forward = BandedPangu(model, scheme=args.scheme) if world > 1 else model
         config["halo_scheme"] = args.scheme
@@ -404,7 +505,8 @@ def main():
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if int(flag.item()) == 0:
                 graphed = None
-    config["launch"] = "cuda-graph replay (1 graph launch per step)" if graphed is not None else "eager ctypes launches"
+    config["launch"] = LAUNCH_NOTE[args.graph]
+    launch_used = "cuda-graph replay (1 graph launch per step)" if graphed is not None else "eager ctypes launches"
 
     def step_resident():
         if graphed is not None:
@@ -497,13 +599,31 @@ def main():
             calls, tms, fl, _ = gemm[dom]
             ach = fl / (tms / 1000.0) / 1e12
             roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tf_sust"], "traffic": ncu_traffic(dom),
-                        "traffic_source": "profiles/r1_ncu_traffic.json (ncu --set full, full-grid launch)" if ncu_traffic(dom) else None,
+                        "frac": ach / peaks["tf_sust"], "traffic": ncu_traffic(dom) if world == 1 else None,
+                        "traffic_source": (TRAFFIC_FILE + " (ncu --set full capture of this kernel at this shape, committed; "
+                                           "not re-measured by this run)" if world == 1 and ncu_traffic(dom) else
+                                           "null: the committed ncu capture is of the un-sharded launch, not of this band-sized one"
+                                           if world > 1 else None),
                         "algorithmic_bytes_per_launch": gemm[dom][3] / calls, "peak_source": peaks["src"] + " (sustained cuBLAS bf16)",
                         "avg_launch_ms": tms / calls, "flops_per_launch": fl / calls,
                         "all_gemm_tflops": sum(v[2] for v in gemm.values()) / (sum(v[1] for v in gemm.values()) / 1000.0) / 1e12,
                         "model_attn_mlp_frac": FLOPS_ATTN_MLP * value / world / 1e12 / peaks["tf_sust"],
                         "instrumented_ms_per_step": inst_ms / args.steps}
+
+    band_check = None
+    if mode == "bands" and world > 1:
+        # outside the timed regions: every rank also runs the UN-sharded forward and compares its own rows of the
+        # banded result (over real NCCL) with it, bit for bit; the verdict is the minimum over the ranks
+        with torch.no_grad():
+            bo, bos = forward(d_inp, d_inp_s, stats, maps, const_h)
+            fo, fos = model(full_inputs[0].to(dev), full_inputs[1].to(dev), stats, full_inputs[2].to(dev), full_inputs[3].to(dev))
+        p0, p1 = plan.pix
+        same = bool(torch.equal(bo, fo[..., p0:p1, :])) and bool(torch.equal(bos, fos[..., p0:p1, :]))
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        band_check = {"bit_identical_to_unsharded": bool(int(flag.item())), "ranks": world,
+                      "how": "each rank: torch.equal(own rows of the banded forward over NCCL, same rows of its own un-sharded forward)"}
+        del bo, bos, fo, fos
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -519,8 +639,8 @@ def main():
                         "ms_per_step": e2e_ms / args.steps, "api": ("pangu_b200.pipeline.StreamedForecaster(PanguModel / BandedPangu): pinned host in -> pinned host out, "
                                 "transfers of neighbouring samples overlap the forward" if streamer is not None else
                                 "models.pangu_model.PanguModel.forward on pinned host inputs, serial H2D / forward / D2H")},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "kernels": kernels, "tflops_model_per_gpu": FLOPS_TOTAL * value / world / 1e12}
+                "gpu_launches": launches, "launch_used": launch_used, "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "band_check": band_check, "kernels": kernels, "tflops_model_per_gpu": FLOPS_TOTAL * value / world / 1e12}
         print(json.dumps(line))
     if world > 1:
         # NCCL teardown while a captured graph still references the communicator can block: release the graph,

@@ -330,6 +330,23 @@ int pangu_weighted_l1_loss(const float* out, const float* target, const float* m
                            const float* weight, int32_t planes, int32_t planes_per_var, int64_t plane_elems,
                            float scale, float* loss_sum, float* d_out, void* stream);
 
+/* The same with the reference's custom mask (models/pangu_sample.py:120-127,194-199: `use_custom_mask`): every L1 term
+ * is multiplied by mask[h][w] (fp32 [plane_elems], the same for all planes); the caller passes
+ * scale = loss_weight / valid_points (train(), :198-199) or loss_weight / (valid_points * channels) (test(), :467). */
+int pangu_weighted_l1_loss_masked(const float* out, const float* target, const float* mean, const float* stdv,
+                                  const float* weight, const float* mask, int32_t planes, int32_t planes_per_var,
+                                  int64_t plane_elems, float scale, float* loss_sum, float* d_out, void* stream);
+
+/* The reference's wind-speed loss (models/pangu_sample.py:74-93 get_wind_speed, :184-193 `only_use_wind_speed_loss`) and
+ * its gradient in one pass: ws = sqrt(u^2 + v^2) of the output planes and of the (normalised on the fly, mean/std per
+ * plane or NULL) target planes, loss_sum += scale * sum mask * |ws(out) - ws(target)|; d_u / d_v (NULL: no gradient)
+ * = scale * mask * sign(.) * u / ws(out) (0 where ws(out) = 0).  u / v [planes][plane_elems] fp32, plane p of u and of
+ * v being the same level; mask [plane_elems] or NULL. */
+int pangu_wind_speed_l1_loss(const float* out_u, const float* out_v, const float* tgt_u, const float* tgt_v,
+                             const float* mean_u, const float* std_u, const float* mean_v, const float* std_v,
+                             const float* mask, int32_t planes, int64_t plane_elems, float scale, float* loss_sum,
+                             float* d_u, float* d_v, void* stream);
+
 /* Latitude-weighted verification scores in one pass (era5_data/score.py:126-161
  * weighted_rmse_torch_channels with its optional mask, :181-201 weighted_acc_torch_channels).  pred / target fp32
  * [planes][H][W]; mask [H][W] or NULL (= 1); clim [planes] or NULL (= 0): the climatology subtracted from both fields for the

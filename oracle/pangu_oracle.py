@@ -444,6 +444,41 @@ def weighted_acc_channels(pred: torch.Tensor, target: torch.Tensor) -> torch.Ten
         torch.sum(w * pred * pred, dim=(-1, -2)) * torch.sum(w * target * target, dim=(-1, -2)))
 
 
+# ---------------------------------------------------------------------------------------------
+# Training losses (models/pangu_sample.py:163-218), the step after the forward in train(); pinned by
+# tests/golden/reference_loss_goldens.npz = the reference's own train() loop run on a stand-in model
+# (tests/golden/make_loss_golden.py)
+# ---------------------------------------------------------------------------------------------
+def wind_speed(output_surface, target_surface, output, target):
+    """models/pangu_sample.py:74-93 get_wind_speed: sqrt(u^2 + v^2) of surface channels (1, 2) and upper channels (3, 4)."""
+    ws = lambda t, a, b: torch.sqrt(t[:, a] ** 2 + t[:, b] ** 2)
+    return ws(output_surface, 1, 2), ws(target_surface, 1, 2), ws(output, 3, 4), ws(target, 3, 4)
+
+
+def training_loss(output, output_surface, target, target_surface, statistics_last, upper_weights, surface_weights,
+                  upper_loss_weight=1.0, surface_loss_weight=0.25, only_use_wind_speed_loss=False, custom_mask=None):
+    """The loss of one train() iteration, models/pangu_sample.py:168-204 (before the division by accumulation_steps):
+    normData on the targets (era5_data/utils_data.py:531-537), then one of the four branches."""
+    sm, ss, um, us = statistics_last
+    target, target_surface = (target - um) / us, (target_surface - sm) / ss
+    if custom_mask is not None:
+        keep = ~(custom_mask == 0)                                           # :123, (~mask_bool)
+        valid = custom_mask.sum()                                            # :127
+    if only_use_wind_speed_loss:                                             # :184-193
+        wos, wts, wo, wt = wind_speed(output_surface, target_surface, output, target)
+        ls, lu = (wos - wts).abs(), (wo - wt).abs()
+        if custom_mask is not None:
+            return (ls * keep).sum() / valid + (lu * keep).sum() / valid
+        return ls.mean() + lu.mean()
+    ls, lu = (output_surface - target_surface).abs(), (output - target).abs()   # :194-195, L1Loss(reduction='none')
+    if custom_mask is not None:                                              # :196-199
+        wsl = (ls * surface_weights * keep[None, None]).sum() / valid
+        wul = (lu * upper_weights * keep[None]).sum() / valid
+    else:                                                                    # :200-202
+        wsl, wul = torch.mean(ls * surface_weights), torch.mean(lu * upper_weights)
+    return wul * upper_loss_weight + wsl * surface_loss_weight               # :204
+
+
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a = a.double().flatten()
     b = b.double().flatten()

@@ -1,14 +1,20 @@
 """B200-native modules with the API of the reference's models/layers.py.
 
 Every class keeps the reference's constructor signature, forward signature, sub-module names and
-parameter shapes, so `state_dict`s, DDP, deepcopy, pickling and LoRA wrapping (the Linear
-sub-modules are real nn.Linear) behave as with the reference.  The math runs in hand-written CUDA
+parameter shapes, so `state_dict`s, DDP, deepcopy and pickling behave as with the reference (the
+Linear sub-modules are real nn.Linear, so LoRA wrapping finds them; see "LoRA" below for what then happens).  The math runs in hand-written CUDA
 kernels for sm_100a through the C ABI in include/pangu_b200.h (see pangu_b200/functional.py); there is
 no eager-PyTorch or CPU fallback: tensors must live on a CUDA device.
 
-Training: when grad mode is on and a parameter (or the input) requires grad, the forward builds an autograd
-graph out of the Functions in pangu_b200/autograd.py, whose backward runs on the B200 backward kernels
-(bf16 mode; the reference's per-block checkpoint re-computation, models/layers.py:143-149, is kept).
+Training: when grad mode is on and a parameter (or the input) requires grad -- in train() or eval() mode, as
+with any nn.Module -- the forward builds an autograd graph out of the Functions in pangu_b200/autograd.py, whose
+backward runs on the B200 backward kernels (bf16 mode; intermediates are saved, about 35 GB per full-resolution sample;
+$PANGU_B200_TRAIN_RECOMPUTE=1 re-computes per block like models/layers.py:143-149).  Forward-only use: torch.no_grad()
+or `module.set_forward_only()`.
+
+LoRA: peft-wrapped Linear sub-modules are folded (W + scaling * B @ A) into the kernels' operands, with gradients for
+lora_A / lora_B, when the adapter has no active dropout; otherwise, and for any other wrapper or hooked sub-module,
+the forward raises PanguError (pangu_b200.functional.lin_wb) -- adapters are never silently ignored.
 
 Numeric mode: `module.compute_dtype` in {"bf16", "fp32"} (default from $PANGU_B200_COMPUTE, "bf16");
 `set_compute_dtype(module, mode)` switches a whole tree.
@@ -89,6 +95,15 @@ class _B200Module(nn.Module):
 
     def _mode(self):
         return self.compute_dtype
+
+    def set_forward_only(self, flag=True):
+        """Opt this module tree out of autograd-graph building even when grad mode is on and parameters are trainable
+        (pangu_b200.autograd.wants_graph): the call then runs the fused inference kernels and returns tensors without
+        grad_fn -- for grad-enabled evaluation loops like the reference's test() (models/pangu_sample.py:443)."""
+        for m in self.modules():
+            if isinstance(m, _B200Module):
+                m.forward_only = bool(flag)
+        return self
 
 
 def set_compute_dtype(module, mode):

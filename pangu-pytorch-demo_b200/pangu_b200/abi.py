@@ -85,6 +85,8 @@ _PROTOS = {
     "pangu_window_attention_backward": (c_int, [c_void_p] * 9 + [POINTER(Geom), c_int, c_void_p]),
     "pangu_patch_recover_gather_backward": (c_int, [c_void_p] * 4 + [c_int32, c_int32, c_void_p]),
     "pangu_weighted_l1_loss": (c_int, [c_void_p] * 5 + [c_int32, c_int32, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+    "pangu_weighted_l1_loss_masked": (c_int, [c_void_p] * 6 + [c_int32, c_int32, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
+    "pangu_wind_speed_l1_loss": (c_int, [c_void_p] * 9 + [c_int32, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pangu_linear_bf16_aux": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32,
                                       c_int, c_int, c_void_p, c_void_p]),
     "pangu_lat_weighted_score_sums": (c_int, [c_void_p] * 5 + [c_int32, c_int32, c_int32, c_void_p, c_void_p]),

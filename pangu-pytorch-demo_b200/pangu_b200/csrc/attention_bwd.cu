@@ -371,11 +371,10 @@ int launch_window_attention_bwd(const void* qkv, const float* qkv_bias, const vo
                                 const void* dout, const float* lse, void* dqkv, float* dbias, float* dpad,
                                 const WinGeom& g, int roll, cudaStream_t st) {
   using namespace attn_bwd;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  static unsigned long long configured = 0;
+  {
+    cudaError_t e = pangu::set_max_smem_once(configured, window_attention_bwd_kernel, kSmemBytes);
     if (e != cudaSuccess) { set_error("attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    configured = true;
   }
   // longitude windows per CTA: they share the staged bias tile and the fragment-resident dBias accumulators (one
   // reduction of 144 x 144 values per CTA), so chunks are long; still >= ~10 waves of one CTA per SM

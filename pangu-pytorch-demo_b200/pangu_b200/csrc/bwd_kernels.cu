@@ -228,8 +228,8 @@ patch_recover_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* __restri
 // with scale = loss_weight / numel, i.e. loss_weight * mean(L1(out, target) * w) and its gradient for d loss = 1.
 __global__ void __launch_bounds__(256)
 weighted_l1_loss_kernel(const float4* __restrict__ out, const float4* __restrict__ target, const float* __restrict__ mean,
-                        const float* __restrict__ stdv, const float* __restrict__ weight, int planes_per_var,
-                        long long plane_elems4, long long total4, float scale, float* __restrict__ loss_sum,
+                        const float* __restrict__ stdv, const float* __restrict__ weight, const float4* __restrict__ mask,
+                        int planes_per_var, long long plane_elems4, long long total4, float scale, float* __restrict__ loss_sum,
                         float4* __restrict__ d_out) {
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
@@ -238,11 +238,66 @@ weighted_l1_loss_kernel(const float4* __restrict__ out, const float4* __restrict
     float m = 0.f, rs = 1.f;
     if (mean != nullptr) { m = __ldg(mean + plane); rs = 1.0f / __ldg(stdv + plane); }
     const float4 o = __ldg(out + i), t = __ldg(target + i);
+    // custom mask [H][W] (models/pangu_sample.py:196-199): the L1 term of every plane is multiplied by it
+    float4 k = make_float4(w, w, w, w);
+    if (mask != nullptr) { const float4 mk = __ldg(mask + (i - (long long)plane * plane_elems4)); k.x *= mk.x; k.y *= mk.y; k.z *= mk.z; k.w *= mk.w; }
     const float d0 = o.x - (t.x - m) * rs, d1 = o.y - (t.y - m) * rs, d2 = o.z - (t.z - m) * rs, d3 = o.w - (t.w - m) * rs;
-    acc += w * (fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3));
+    acc += k.x * fabsf(d0) + k.y * fabsf(d1) + k.z * fabsf(d2) + k.w * fabsf(d3);
     if (d_out != nullptr)
-      d_out[i] = make_float4(d0 > 0.f ? w : (d0 < 0.f ? -w : 0.f), d1 > 0.f ? w : (d1 < 0.f ? -w : 0.f),
-                             d2 > 0.f ? w : (d2 < 0.f ? -w : 0.f), d3 > 0.f ? w : (d3 < 0.f ? -w : 0.f));
+      d_out[i] = make_float4(d0 > 0.f ? k.x : (d0 < 0.f ? -k.x : 0.f), d1 > 0.f ? k.y : (d1 < 0.f ? -k.y : 0.f),
+                             d2 > 0.f ? k.z : (d2 < 0.f ? -k.z : 0.f), d3 > 0.f ? k.w : (d3 < 0.f ? -k.w : 0.f));
+  }
+  acc = warp_sum(acc);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float v = part[threadIdx.x];
+    v += __shfl_xor_sync(0xffu, v, 4); v += __shfl_xor_sync(0xffu, v, 2); v += __shfl_xor_sync(0xffu, v, 1);
+    if (threadIdx.x == 0) atomicAdd(loss_sum, v);
+  }
+}
+
+// Wind-speed L1 loss and its gradient in one pass (models/pangu_sample.py:74-93 get_wind_speed, :184-193):
+//   ws(u, v) = sqrt(u^2 + v^2);  loss += scale * sum mask * | ws(out_u, out_v) - ws(norm(tgt_u), norm(tgt_v)) |
+//   d_u = scale * mask * sign(.) * out_u / ws(out),  d_v likewise  (0 where ws(out) == 0).
+// u / v are plane-aligned: plane p of u and plane p of v are the same level ([planes][plane_elems] each).
+__global__ void __launch_bounds__(256)
+wind_speed_l1_loss_kernel(const float4* __restrict__ out_u, const float4* __restrict__ out_v, const float4* __restrict__ tgt_u,
+                          const float4* __restrict__ tgt_v, const float* __restrict__ mean_u, const float* __restrict__ std_u,
+                          const float* __restrict__ mean_v, const float* __restrict__ std_v, const float4* __restrict__ mask,
+                          long long plane_elems4, long long total4, float scale, float* __restrict__ loss_sum,
+                          float4* __restrict__ d_u, float4* __restrict__ d_v) {
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int plane = (int)(i / plane_elems4);
+    float mu = 0.f, ru = 1.f, mv = 0.f, rv = 1.f;
+    if (mean_u != nullptr) {
+      mu = __ldg(mean_u + plane); ru = 1.0f / __ldg(std_u + plane);
+      mv = __ldg(mean_v + plane); rv = 1.0f / __ldg(std_v + plane);
+    }
+    const float4 ou = __ldg(out_u + i), ov = __ldg(out_v + i), tu = __ldg(tgt_u + i), tv = __ldg(tgt_v + i);
+    float4 k = make_float4(scale, scale, scale, scale);
+    if (mask != nullptr) { const float4 mk = __ldg(mask + (i - (long long)plane * plane_elems4)); k.x *= mk.x; k.y *= mk.y; k.z *= mk.z; k.w *= mk.w; }
+    const float a[4] = {ou.x, ou.y, ou.z, ou.w}, b[4] = {ov.x, ov.y, ov.z, ov.w};
+    const float c[4] = {(tu.x - mu) * ru, (tu.y - mu) * ru, (tu.z - mu) * ru, (tu.w - mu) * ru};
+    const float d[4] = {(tv.x - mv) * rv, (tv.y - mv) * rv, (tv.z - mv) * rv, (tv.w - mv) * rv};
+    const float kk[4] = {k.x, k.y, k.z, k.w};
+    float gu[4], gv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float wo = sqrtf(a[j] * a[j] + b[j] * b[j]), wt = sqrtf(c[j] * c[j] + d[j] * d[j]);
+      const float diff = wo - wt;
+      acc += kk[j] * fabsf(diff);
+      const float s = diff > 0.f ? kk[j] : (diff < 0.f ? -kk[j] : 0.f);
+      const float inv = wo > 0.f ? 1.0f / wo : 0.f;
+      gu[j] = s * a[j] * inv;
+      gv[j] = s * b[j] * inv;
+    }
+    if (d_u != nullptr) {
+      d_u[i] = make_float4(gu[0], gu[1], gu[2], gu[3]);
+      d_v[i] = make_float4(gv[0], gv[1], gv[2], gv[3]);
+    }
   }
   acc = warp_sum(acc);
   __shared__ float part[8];
@@ -415,17 +470,57 @@ extern "C" int pangu_patch_recover_gather_backward(const float* d_output, const 
   return check_launch("patch_recover_gather_backward");
 }
 
-extern "C" int pangu_weighted_l1_loss(const float* out, const float* target, const float* mean, const float* stdv,
-                                      const float* weight, int32_t planes, int32_t planes_per_var, int64_t plane_elems,
-                                      float scale, float* loss_sum, float* d_out, void* stream) {
+static int launch_weighted_l1(const float* out, const float* target, const float* mean, const float* stdv, const float* weight,
+                              const float* mask, int32_t planes, int32_t planes_per_var, int64_t plane_elems, float scale,
+                              float* loss_sum, float* d_out, void* stream) {
   if (!out || !target || !weight || !loss_sum || planes <= 0 || planes_per_var <= 0 || plane_elems <= 0 || (plane_elems & 3) ||
-      ((mean == nullptr) != (stdv == nullptr))) { set_error("weighted_l1_loss: bad argument"); return PANGU_ERR_BAD_ARG; }
+      ((mean == nullptr) != (stdv == nullptr)) ||
+      ((((uintptr_t)out | (uintptr_t)target | (uintptr_t)mask | (uintptr_t)d_out) & 15) != 0)) {
+    set_error("weighted_l1_loss: bad argument (pointers must be 16-byte aligned, plane_elems a multiple of 4)");
+    return PANGU_ERR_BAD_ARG;
+  }
   const long long total4 = (long long)planes * (plane_elems / 4);
   long long want = (total4 + 255) / 256;
   const unsigned grid = (unsigned)(want < 148LL * 16 ? want : 148LL * 16);
   weighted_l1_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>((const float4*)out, (const float4*)target, mean, stdv, weight,
-                                                              planes_per_var, plane_elems / 4, total4, scale, loss_sum, (float4*)d_out);
+                                                              (const float4*)mask, planes_per_var, plane_elems / 4, total4, scale,
+                                                              loss_sum, (float4*)d_out);
   return check_launch("weighted_l1_loss");
+}
+
+extern "C" int pangu_weighted_l1_loss(const float* out, const float* target, const float* mean, const float* stdv,
+                                      const float* weight, int32_t planes, int32_t planes_per_var, int64_t plane_elems,
+                                      float scale, float* loss_sum, float* d_out, void* stream) {
+  return launch_weighted_l1(out, target, mean, stdv, weight, nullptr, planes, planes_per_var, plane_elems, scale, loss_sum, d_out, stream);
+}
+
+extern "C" int pangu_weighted_l1_loss_masked(const float* out, const float* target, const float* mean, const float* stdv,
+                                             const float* weight, const float* mask, int32_t planes, int32_t planes_per_var,
+                                             int64_t plane_elems, float scale, float* loss_sum, float* d_out, void* stream) {
+  return launch_weighted_l1(out, target, mean, stdv, weight, mask, planes, planes_per_var, plane_elems, scale, loss_sum, d_out, stream);
+}
+
+extern "C" int pangu_wind_speed_l1_loss(const float* out_u, const float* out_v, const float* tgt_u, const float* tgt_v,
+                                        const float* mean_u, const float* std_u, const float* mean_v, const float* std_v,
+                                        const float* mask, int32_t planes, int64_t plane_elems, float scale, float* loss_sum,
+                                        float* d_u, float* d_v, void* stream) {
+  const bool stats = mean_u != nullptr;
+  if (!out_u || !out_v || !tgt_u || !tgt_v || !loss_sum || planes <= 0 || plane_elems <= 0 || (plane_elems & 3) ||
+      (stats != (std_u != nullptr)) || (stats != (mean_v != nullptr)) || (stats != (std_v != nullptr)) ||
+      ((d_u == nullptr) != (d_v == nullptr)) ||
+      ((((uintptr_t)out_u | (uintptr_t)out_v | (uintptr_t)tgt_u | (uintptr_t)tgt_v | (uintptr_t)mask | (uintptr_t)d_u |
+         (uintptr_t)d_v) & 15) != 0)) {
+    set_error("wind_speed_l1_loss: bad argument (pointers must be 16-byte aligned, plane_elems a multiple of 4)");
+    return PANGU_ERR_BAD_ARG;
+  }
+  const long long total4 = (long long)planes * (plane_elems / 4);
+  long long want = (total4 + 255) / 256;
+  const unsigned grid = (unsigned)(want < 148LL * 16 ? want : 148LL * 16);
+  wind_speed_l1_loss_kernel<<<grid, 256, 0, as_stream(stream)>>>((const float4*)out_u, (const float4*)out_v, (const float4*)tgt_u,
+                                                                (const float4*)tgt_v, mean_u, std_u, mean_v, std_v,
+                                                                (const float4*)mask, plane_elems / 4, total4, scale, loss_sum,
+                                                                (float4*)d_u, (float4*)d_v);
+  return check_launch("wind_speed_l1_loss");
 }
 
 extern "C" int pangu_lat_weighted_score_sums(const float* pred, const float* target, const float* mask, const float* clim,

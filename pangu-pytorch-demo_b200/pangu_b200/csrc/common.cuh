@@ -119,4 +119,17 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float a, float b, float c,
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncSetAttribute is per device: `mask` is a function-local static bitset over device ordinals (one process may
+// drive several GPUs: the reference builds torch.device('cuda:' + str(local_rank)) without cudaSetDevice).
+template <typename K>
+inline cudaError_t set_max_smem_once(unsigned long long& mask, K kernel, int bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (mask & bit) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) mask |= bit;
+  return e;
+}
+
 }  // namespace pangu

@@ -256,12 +256,10 @@ int launch_window_attention_f32(const float* qkv, const float* qkv_bias, const f
                                 float* out, const WinGeom& g, int roll, cudaStream_t st) {
   const size_t smem = (size_t)(kWinTokens * (32 + 33 + 32) + ATT_WARPS * kWinTokens) * sizeof(float) +
                       kWinTokens * (sizeof(long long) + sizeof(int));
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_f32_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static unsigned long long configured = 0;
+  {
+    cudaError_t e = pangu::set_max_smem_once(configured, window_attention_f32_kernel, (int)smem);
     if (e != cudaSuccess) { set_error("attention_f32: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    configured = true;
   }
   dim3 grid((unsigned)(g.nLon * g.T), (unsigned)g.heads);
   window_attention_f32_kernel<<<grid, ATT_WARPS * 32, smem, st>>>(qkv, qkv_bias, earth_bias, out, g, roll);

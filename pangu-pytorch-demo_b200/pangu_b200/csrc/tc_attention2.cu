@@ -749,11 +749,10 @@ int launch_window_attention_tc(const void* qkv, const void* halo_qkv, const void
                                int roll, cudaStream_t st, float* lse) {
   using namespace attn2;
   if (bd.nhw <= 0) return PANGU_OK;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  static unsigned long long configured = 0;
+  {
+    cudaError_t e = pangu::set_max_smem_once(configured, window_attention_tc_kernel, kSmemBytes);
     if (e != cudaSuccess) { set_error("attention_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    configured = true;
   }
   // token rows of the three tensors
   const uint64_t own_rows = roll == 2 ? (uint64_t)g.nLon * g.T * kWinTokens : (uint64_t)g.Z * bd.hrows * g.W;

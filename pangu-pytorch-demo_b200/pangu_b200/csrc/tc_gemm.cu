@@ -375,10 +375,11 @@ bool encode_tmap_3d_bf16(CUtensorMap* map, const void* gptr, uint64_t d0, uint64
 }
 
 int num_sms() {
-  static int n = 0;
+  static int per_dev[64] = {0};                      // SM count (after the optional cap) by device ordinal
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = per_dev[dev & 63];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
     // $PANGU_B200_SMS=<even count>: grid cap of the persistent kernels -- leaves SMs to NCCL all-reduce CTAs that run next to
@@ -419,11 +420,10 @@ static int launch_gemm_t(const void* A, long long lda, const void* W, GemmArgs& 
   a.n_tiles = a.N / BN;
   a.k_blocks = (a.K + BK - 1) / BK;
   auto kern = gemm_bf16_kernel<BN, LN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  static unsigned long long configured = 0;
+  {
+    cudaError_t e = pangu::set_max_smem_once(configured, kern, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("gemm_bf16<%d>: cudaFuncSetAttribute(%d B): %s", BN, Cfg::SMEM_BYTES, cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    configured = true;
   }
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();

@@ -381,11 +381,10 @@ static int launch_gemm2_t(const void* A, long long lda, const void* W, Gemm2Args
   CUtensorMap tmOut = tmA;                                    // placeholder when the store path is off (never dereferenced)
   if (a.tma_out && !encode_tmap_2d(&tmOut, 1, a.out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldo * 2, 32, 32, 64)) return PANGU_ERR_CUDA;
   auto kern = gemm2_bf16_kernel<KB>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  static unsigned long long configured = 0;
+  {
+    cudaError_t e = pangu::set_max_smem_once(configured, kern, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("gemm2<%d>: cudaFuncSetAttribute(%d B): %s", K, Cfg::SMEM_BYTES, cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    configured = true;
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = a.pair_tiles < max_pairs ? a.pair_tiles : max_pairs;

@@ -397,11 +397,10 @@ static int launch_mlp_t(const void* x, const void* w1, const void* w2, MlpArgs& 
   if (a.residual == nullptr && Cfg::LN_ASYNC) { set_error("mlp_fused<%d>: a residual tensor is required", C); return PANGU_ERR_BAD_ARG; }
   a.pair_tiles = (int)((a.M + 255) / 256);
   auto kern = mlp_fused_kernel<C>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  static unsigned long long configured = 0;
+  {
+    cudaError_t e = pangu::set_max_smem_once(configured, kern, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("mlp_fused<%d>: cudaFuncSetAttribute(%d B): %s", C, Cfg::SMEM_BYTES, cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    configured = true;
   }
   const int max_pairs = num_sms() / 2;
   const int pairs = a.pair_tiles < max_pairs ? a.pair_tiles : max_pairs;

@@ -144,11 +144,10 @@ template <int NB>
 static int launch_wgrad_t(const CUtensorMap& tmDy, const CUtensorMap& tmX, WgradArgs& a, long long M, cudaStream_t st) {
   using Cfg = WgradCfg<NB>;
   auto kern = wgrad_bf16_kernel<NB>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  static unsigned long long configured = 0;
+  {
+    cudaError_t e = pangu::set_max_smem_once(configured, kern, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("wgrad<%d>: cudaFuncSetAttribute(%d B): %s", NB, Cfg::SMEM_BYTES, cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
-    configured = true;
   }
   const int m_tiles = (a.n_out + WG_BM - 1) / WG_BM;
   a.n_tiles = (a.k_in + Cfg::BN - 1) / Cfg::BN;

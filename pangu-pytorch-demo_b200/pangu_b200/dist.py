@@ -210,11 +210,11 @@ class _Worker:
         if o_first is not None:                          # rows 0..2 of this band were computed by the northern neighbour
             hr, W = self.plan.nrows(stage), TOK_W[stage]
             self.o.view(Z, hr, W, self.o.shape[-1])[:, :3].copy_(o_first.view(Z, 3, W, self.o.shape[-1]))
-        x1, x1b = ops.linear_ln_residual_bf16(self.o, wc.bf16("a2", att.linear2.weight), PF._f(att.linear2.bias),
+        x1, x1b = ops.linear_ln_residual_bf16(self.o, wc.bf16("a2", PF.W(att.linear2)), PF._f(PF.B(att.linear2)),
                                               PF._f(blk.norm1.weight), PF._f(blk.norm1.bias), self.x, eps=blk.norm1.eps)
         self.o = self.halo_o = None
-        self.x, self.xb = ops.mlp_ln_residual_bf16(x1b, wc.bf16("m1", mlp.linear1.weight), PF._f(mlp.linear1.bias),
-                                                   wc.f16("m2h", mlp.linear2.weight), PF._f(mlp.linear2.bias),
+        self.x, self.xb = ops.mlp_ln_residual_bf16(x1b, wc.bf16("m1", PF.W(mlp.linear1)), PF._f(PF.B(mlp.linear1)),
+                                                   wc.f16("m2h", PF.W(mlp.linear2)), PF._f(PF.B(mlp.linear2)),
                                                    PF._f(blk.norm2.weight), PF._f(blk.norm2.bias), x1, eps=blk.norm2.eps)
 
 
@@ -329,7 +329,13 @@ class GradientAllReducer:
     (post-accumulate-grad hooks), on the side stream NCCL uses, so that the reduction of the late blocks overlaps the
     backward kernels of the early ones.  The 16 Earth-specific bias tables are 91 % of the 1.1 GB and get buckets of
     their own.  `finish()` waits for the reductions and copies the means back into `p.grad` (call it before the
-    optimiser step).  Works with any backend (gloo on CPU in the tests)."""
+    optimiser step).  Works with any backend (gloo on CPU in the tests).
+
+    Gradient accumulation (the reference divides the loss by `accumulation_steps` and runs several backward passes per
+    optimiser step): run every micro-step but the last under `with reducer.no_sync():` -- the hooks then leave the
+    gradients to accumulate locally in `p.grad`, exactly like DDP's no_sync -- and the last one normally: its hooks see
+    the accumulated sums, which is what gets reduced.  A second synchronising backward without `finish()` in between
+    raises instead of silently dropping or double-averaging gradients."""
 
     def __init__(self, model, group=None, bucket_mb=64.0):
         import torch.distributed as dist
@@ -355,10 +361,30 @@ class GradientAllReducer:
                 off += p.numel()
         self.pending = [len(b) for b in self.buckets]
         self.works = [None] * len(self.buckets)
+        self.sync = True
         self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
 
+    def no_sync(self):
+        """Context manager: backward passes inside accumulate into `p.grad` without any communication."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            old, self.sync = self.sync, False
+            try:
+                yield self
+            finally:
+                self.sync = old
+        return ctx()
+
     def _on_grad(self, p):
+        if not self.sync:
+            return
         bi, off = self.where[p]
+        if self.pending[bi] <= 0:
+            raise RuntimeError("GradientAllReducer: a second synchronising backward() before finish(); run the earlier "
+                               "micro-steps under `with reducer.no_sync():` (gradient accumulation) or call finish() "
+                               "after every backward()")
         self.flat[bi][off:off + p.numel()].copy_(p.grad.reshape(-1))
         self.pending[bi] -= 1
         if self.pending[bi] == 0:

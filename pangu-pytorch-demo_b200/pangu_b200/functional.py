@@ -36,7 +36,15 @@ class WeightCache:
     def f16(self, key, p):
         return self.bf16(key, p, torch.float16)
 
+    @staticmethod
+    def _transient(p):
+        """Folded (LoRA) weights are fresh tensors every call: their data_ptr may be recycled, so they are never cached."""
+        return not isinstance(p, torch.nn.Parameter)
+
     def bf16(self, key, p, dtype=torch.bfloat16):
+        if self._transient(p):
+            t = p.detach()
+            return (t[:, :, 0] if t.dim() == 3 else t).contiguous().to(dtype)
         ent = self._c.get(key)
         tag = (p.data_ptr(), p._version, p.device)
         if ent is None or ent[0] != tag:
@@ -49,6 +57,9 @@ class WeightCache:
 
     def derived(self, key, params, fn):
         """Cache fn(*params) until one of the parameters is updated in place or replaced."""
+        if any(self._transient(p) for p in params):
+            with torch.no_grad():
+                return fn(*[p.detach() for p in params])
         ent = self._c.get(key)
         tag = tuple((p.data_ptr(), p._version, p.device) for p in params)
         if ent is None or ent[0] != tag:
@@ -59,6 +70,74 @@ class WeightCache:
 
     def clear(self):
         self._c.clear()
+
+
+# ------------------------------------------------------------------------------------------
+# Holders of dense weights.  The kernels read weights straight off the sub-modules (they never call the sub-modules'
+# forward), so anything that changes what `linear(x)` computes must either be folded into the operands or refused:
+# a silently ignored adapter / hook would be a wrong answer (reference: finetune/lora_tune.py:169-186 wraps every
+# nn.Linear with peft LoRA and puts the two output convolutions into `modules_to_save`).
+def _has_hooks(mod):
+    return bool(getattr(mod, "_forward_hooks", None)) or bool(getattr(mod, "_forward_pre_hooks", None))
+
+
+def _dropout_p(d):
+    return float(getattr(d, "p", 0.0)) if isinstance(d, torch.nn.Dropout) else 0.0
+
+
+def lin_wb(mod, who="linear"):
+    """(weight, bias) of a Linear / Conv1d(k=1) holder as the kernels must see them.
+
+    * exactly nn.Linear / nn.Conv1d without forward hooks -> its parameters;
+    * a peft ModulesToSaveWrapper (`modules_to_save`, `original_module`) -> the active copy;
+    * a peft LoRA layer (`base_layer`, `lora_A`, `lora_B`, `scaling`) -> W + sum_a scaling_a * B_a @ A_a as a differentiable
+      expression of (W, A, B), so the backward kernels' weight gradient reaches lora_A / lora_B through autograd;
+      with `lora_dropout` > 0 in train() mode the adapter input differs from the base input and cannot be folded: refused;
+    * anything else (sub-classes, other adapters, hooked modules) -> PanguError.  No silent fallback."""
+    if _has_hooks(mod):
+        raise PanguError(f"{who}: forward hooks on {type(mod).__name__} would be bypassed by the fused kernels; remove them")
+    t = type(mod)
+    if t is torch.nn.Linear or t is torch.nn.Conv1d:
+        return mod.weight, mod.bias
+    if hasattr(mod, "modules_to_save") and hasattr(mod, "original_module"):          # peft ModulesToSaveWrapper
+        act = [a for a in getattr(mod, "active_adapters", []) if a in mod.modules_to_save]
+        if getattr(mod, "disable_adapters", False) or not act:
+            return lin_wb(mod.original_module, who)
+        return lin_wb(mod.modules_to_save[act[0]], who)
+    if hasattr(mod, "base_layer") and hasattr(mod, "lora_A") and hasattr(mod, "lora_B"):   # peft lora.Linear
+        w, b = lin_wb(mod.base_layer, who)
+        if getattr(mod, "merged", False) or getattr(mod, "disable_adapters", False):
+            return w, b
+        dora = getattr(mod, "use_dora", None)
+        for name in getattr(mod, "active_adapters", list(mod.lora_A.keys())):
+            if name not in mod.lora_A:
+                continue
+            drop = mod.lora_dropout[name] if hasattr(mod, "lora_dropout") and name in mod.lora_dropout else None
+            if mod.training and _dropout_p(drop) > 0.0:
+                raise PanguError(f"{who}: LoRA adapter {name!r} has lora_dropout={_dropout_p(drop)} in train() mode; the adapter "
+                                 "then sees a different input than the base layer and cannot be folded into the fused "
+                                 "kernels' weights. Use lora_dropout=0 (or eval()) with the B200 path")
+            if isinstance(dora, dict) and dora.get(name, False):
+                raise PanguError(f"{who}: DoRA adapters are not supported by the B200 path")
+            A, Bm = mod.lora_A[name].weight, mod.lora_B[name].weight
+            w = w + float(mod.scaling[name]) * (Bm @ A).reshape(w.shape)
+        return w, b
+    raise PanguError(f"{who}: expected nn.Linear / nn.Conv1d (or a peft LoRA / modules_to_save wrapper of one), got "
+                     f"{t.__module__}.{t.__name__}; the fused kernels would ignore what it adds to the forward")
+
+
+def norm_wb(mod, who="norm"):
+    if type(mod) is not torch.nn.LayerNorm or _has_hooks(mod):
+        raise PanguError(f"{who}: expected a plain nn.LayerNorm without hooks, got {type(mod).__name__}")
+    return mod.weight, mod.bias
+
+
+def W(mod):
+    return lin_wb(mod)[0]
+
+
+def B(mod):
+    return lin_wb(mod)[1]
 
 
 LOG2E = 1.4426950408889634
@@ -82,7 +161,7 @@ def attention_operands(att, wc):
         b[:C] *= qs
         return b.contiguous()
 
-    return (wc.derived("a1s", (att.linear1.weight,), scaled_w), wc.derived("b1s", (att.linear1.bias,), scaled_b),
+    return (wc.derived("a1s", (W(att.linear1),), scaled_w), wc.derived("b1s", (B(att.linear1),), scaled_b),
             wc.derived("ebs", (att.earth_specific_bias,), lambda e: (e[0].float() * LOG2E).to(torch.bfloat16).contiguous()))
 
 
@@ -101,7 +180,7 @@ def _f(p):
 # ------------------------------------------------------------------------------------------
 def _affine(norm, s):
     """LayerNorm affine parameters with a DropPath factor folded in: s * (LN(y) g + b) = LN(y) (s g) + (s b)."""
-    g, b = _f(norm.weight), _f(norm.bias)
+    g, b = (_f(t) for t in norm_wb(norm))
     return (g, b) if s == 1.0 else (g * s, b * s)
 
 
@@ -115,15 +194,15 @@ def block_forward(blk, x, Z, H, W, roll, mode, xb=None, s1=1.0, s2=1.0):
     if (s1 != 1.0 or s2 != 1.0) and mode != "bf16":
         raise PanguError("stochastic depth (training) runs in compute_dtype='bf16' only")
     if mode == "fp32":
-        qkv = ops.linear(x, _w2d(att.linear1.weight), _f(att.linear1.bias))
-        o = ops.window_attention(qkv, _f(att.linear1.bias), _f(att.earth_specific_bias), Z, H, W, heads, rmode)
+        qkv = ops.linear(x, _w2d(W(att.linear1)), _f(B(att.linear1)))
+        o = ops.window_attention(qkv, _f(B(att.linear1)), _f(att.earth_specific_bias), Z, H, W, heads, rmode)
         del qkv
-        y = ops.linear(o, _w2d(att.linear2.weight), _f(att.linear2.bias))
-        x1, _ = ops.ln_residual(y, _f(blk.norm1.weight), _f(blk.norm1.bias), residual=x, eps=blk.norm1.eps)
-        h = ops.linear(x1, _w2d(mlp.linear1.weight), _f(mlp.linear1.bias), act=ACT_GELU)
-        y = ops.linear(h, _w2d(mlp.linear2.weight), _f(mlp.linear2.bias))
+        y = ops.linear(o, _w2d(W(att.linear2)), _f(B(att.linear2)))
+        x1, _ = ops.ln_residual(y, _f(norm_wb(blk.norm1)[0]), _f(norm_wb(blk.norm1)[1]), residual=x, eps=blk.norm1.eps)
+        h = ops.linear(x1, _w2d(W(mlp.linear1)), _f(B(mlp.linear1)), act=ACT_GELU)
+        y = ops.linear(h, _w2d(W(mlp.linear2)), _f(B(mlp.linear2)))
         del h
-        x2, _ = ops.ln_residual(y, _f(blk.norm2.weight), _f(blk.norm2.bias), residual=x1, eps=blk.norm2.eps)
+        x2, _ = ops.ln_residual(y, _f(norm_wb(blk.norm2)[0]), _f(norm_wb(blk.norm2)[1]), residual=x1, eps=blk.norm2.eps)
         return x2, None
     wc = blk._wcache
     if xb is None:
@@ -135,7 +214,7 @@ def block_forward(blk, x, Z, H, W, roll, mode, xb=None, s1=1.0, s2=1.0):
                                          prescaled=True)
         del qkv
         g1, b1 = _affine(blk.norm1, s1)
-        x1, x1b = ops.linear_ln_residual_bf16(o, wc.bf16("a2", att.linear2.weight), _f(att.linear2.bias), g1, b1, x,
+        x1, x1b = ops.linear_ln_residual_bf16(o, wc.bf16("a2", W(att.linear2)), _f(B(att.linear2)), g1, b1, x,
                                               eps=blk.norm1.eps)
         del o
     else:
@@ -144,12 +223,12 @@ def block_forward(blk, x, Z, H, W, roll, mode, xb=None, s1=1.0, s2=1.0):
         return x1, x1b
     g2, b2 = _affine(blk.norm2, s2)
     if FUSED_MLP:
-        x2, x2b = ops.mlp_ln_residual_bf16(x1b, wc.bf16("m1", mlp.linear1.weight), _f(mlp.linear1.bias),
-                                           wc.f16("m2h", mlp.linear2.weight), _f(mlp.linear2.bias), g2, b2, x1,
+        x2, x2b = ops.mlp_ln_residual_bf16(x1b, wc.bf16("m1", W(mlp.linear1)), _f(B(mlp.linear1)),
+                                           wc.f16("m2h", W(mlp.linear2)), _f(B(mlp.linear2)), g2, b2, x1,
                                            eps=blk.norm2.eps)
         return x2, x2b
-    h = ops.linear(x1b, wc.bf16("m1", mlp.linear1.weight), _f(mlp.linear1.bias), act=ACT_GELU)
-    x2, x2b = ops.linear_ln_residual_bf16(h, wc.bf16("m2", mlp.linear2.weight), _f(mlp.linear2.bias), g2, b2, x1,
+    h = ops.linear(x1b, wc.bf16("m1", W(mlp.linear1)), _f(B(mlp.linear1)), act=ACT_GELU)
+    x2, x2b = ops.linear_ln_residual_bf16(h, wc.bf16("m2", W(mlp.linear2)), _f(B(mlp.linear2)), g2, b2, x1,
                                           eps=blk.norm2.eps)
     return x2, x2b
 
@@ -171,25 +250,25 @@ def attention_windows_forward(att, xw, mask, mode):
     Zf, Hf, Wf = 2, 6 * T - 5, 12 * nLon
     flat = xw.reshape(nLon * T * L, C)
     if mode == "fp32":
-        qkv = ops.linear(flat.contiguous(), _w2d(att.linear1.weight), _f(att.linear1.bias))
-        o = ops.window_attention(qkv, _f(att.linear1.bias), bias, Zf, Hf, Wf, heads, WINDOWED)
-        y = ops.linear(o, _w2d(att.linear2.weight), _f(att.linear2.bias))
+        qkv = ops.linear(flat.contiguous(), _w2d(W(att.linear1)), _f(B(att.linear1)))
+        o = ops.window_attention(qkv, _f(B(att.linear1)), bias, Zf, Hf, Wf, heads, WINDOWED)
+        y = ops.linear(o, _w2d(W(att.linear2)), _f(B(att.linear2)))
     else:
         wc = att._wcache
-        qkv = ops.linear(ops.cast_bf16(flat.contiguous()), wc.bf16("a1", att.linear1.weight), _f(att.linear1.bias))
-        o = ops.window_attention(qkv, _f(att.linear1.bias), bias.to(torch.bfloat16), Zf, Hf, Wf, heads, WINDOWED)
-        y = ops.linear(o, wc.bf16("a2", att.linear2.weight), _f(att.linear2.bias), out_dtype=torch.float32)
+        qkv = ops.linear(ops.cast_bf16(flat.contiguous()), wc.bf16("a1", W(att.linear1)), _f(B(att.linear1)))
+        o = ops.window_attention(qkv, _f(B(att.linear1)), bias.to(torch.bfloat16), Zf, Hf, Wf, heads, WINDOWED)
+        y = ops.linear(o, wc.bf16("a2", W(att.linear2)), _f(B(att.linear2)), out_dtype=torch.float32)
     return y.reshape(nLon, T, L, C)
 
 
 def mlp_forward(mlp, x2d, mode):
     """Mlp.forward (models/layers.py:311-317) on [M, C]."""
     if mode == "fp32":
-        h = ops.linear(x2d, _w2d(mlp.linear1.weight), _f(mlp.linear1.bias), act=ACT_GELU)
-        return ops.linear(h, _w2d(mlp.linear2.weight), _f(mlp.linear2.bias))
+        h = ops.linear(x2d, _w2d(W(mlp.linear1)), _f(B(mlp.linear1)), act=ACT_GELU)
+        return ops.linear(h, _w2d(W(mlp.linear2)), _f(B(mlp.linear2)))
     wc = mlp._wcache
-    h = ops.linear(ops.cast_bf16(x2d), wc.bf16("m1", mlp.linear1.weight), _f(mlp.linear1.bias), act=ACT_GELU)
-    return ops.linear(h, wc.bf16("m2", mlp.linear2.weight), _f(mlp.linear2.bias), out_dtype=torch.float32)
+    h = ops.linear(ops.cast_bf16(x2d), wc.bf16("m1", W(mlp.linear1)), _f(B(mlp.linear1)), act=ACT_GELU)
+    return ops.linear(h, wc.bf16("m2", W(mlp.linear2)), _f(B(mlp.linear2)), out_dtype=torch.float32)
 
 
 def patch_embed_forward(pe, inp, inp_s, statistics, maps, const_h, mode):
@@ -200,37 +279,37 @@ def patch_embed_forward(pe, inp, inp_s, statistics, maps, const_h, mode):
     ns = ps.shape[0]                                     # token rows * 360 (181 * 360 for the full grid)
     x = torch.empty((8 * ns, dim), dtype=torch.float32, device=inp.device)
     if mode == "fp32":
-        ops.linear(ps, _w2d(pe.conv_surface.weight), _f(pe.conv_surface.bias), out=x[:ns])
-        ops.linear(pu, _w2d(pe.conv.weight), _f(pe.conv.bias), out=x[ns:])
+        ops.linear(ps, _w2d(W(pe.conv_surface)), _f(B(pe.conv_surface)), out=x[:ns])
+        ops.linear(pu, _w2d(W(pe.conv)), _f(B(pe.conv)), out=x[ns:])
         return x, None
     wc = pe._wcache
     xb = torch.empty((8 * ns, dim), dtype=torch.bfloat16, device=inp.device)      # bf16 shadow written by the GEMMs
-    ops.linear_ex(ps, wc.bf16("cs", pe.conv_surface.weight), _f(pe.conv_surface.bias), out=x[:ns], shadow=xb[:ns])
-    ops.linear_ex(pu, wc.bf16("c", pe.conv.weight), _f(pe.conv.bias), out=x[ns:], shadow=xb[ns:])
+    ops.linear_ex(ps, wc.bf16("cs", W(pe.conv_surface)), _f(B(pe.conv_surface)), out=x[:ns], shadow=xb[:ns])
+    ops.linear_ex(pu, wc.bf16("c", W(pe.conv)), _f(B(pe.conv)), out=x[ns:], shadow=xb[ns:])
     return x, xb
 
 
 def downsample_forward(ds, x, Z, H, W, mode):
     """DownSample.forward (models/layers.py:497-524) -> ([N/4.., 2C] fp32, bf16|None)."""
     if mode == "fp32":
-        m = ops.downsample_merge_ln(x, _f(ds.norm.weight), _f(ds.norm.bias), Z, H, W, torch.float32, ds.norm.eps)
-        return ops.linear(m, _w2d(ds.linear.weight), None), None
-    m = ops.downsample_merge_ln(x, _f(ds.norm.weight), _f(ds.norm.bias), Z, H, W, torch.bfloat16, ds.norm.eps)
-    return ops.linear_ex(m, ds._wcache.bf16("l", ds.linear.weight), None, want_shadow=True)
+        m = ops.downsample_merge_ln(x, _f(norm_wb(ds.norm)[0]), _f(norm_wb(ds.norm)[1]), Z, H, W, torch.float32, ds.norm.eps)
+        return ops.linear(m, _w2d(W(ds.linear)), None), None
+    m = ops.downsample_merge_ln(x, _f(norm_wb(ds.norm)[0]), _f(norm_wb(ds.norm)[1]), Z, H, W, torch.bfloat16, ds.norm.eps)
+    return ops.linear_ex(m, ds._wcache.bf16("l", W(ds.linear)), None, want_shadow=True)
 
 
 def upsample_forward(us, x, mode, xb=None, Z=8, H2=91, W2=180, H=181):
     """UpSample.forward (models/layers.py:540-567; sizes hard-coded there)."""
     if mode == "fp32":
-        y = ops.linear(x, _w2d(us.linear1.weight), None)
-        n = ops.upsample_shuffle_ln(y, _f(us.norm.weight), _f(us.norm.bias), Z, H2, W2, H, torch.float32, us.norm.eps)
-        return ops.linear(n, _w2d(us.linear2.weight), None), None
+        y = ops.linear(x, _w2d(W(us.linear1)), None)
+        n = ops.upsample_shuffle_ln(y, _f(norm_wb(us.norm)[0]), _f(norm_wb(us.norm)[1]), Z, H2, W2, H, torch.float32, us.norm.eps)
+        return ops.linear(n, _w2d(W(us.linear2)), None), None
     wc = us._wcache
     if xb is None:
         xb = ops.cast_bf16(x)
-    y = ops.linear(xb, wc.bf16("l1", us.linear1.weight), None)
-    n = ops.upsample_shuffle_ln(y, _f(us.norm.weight), _f(us.norm.bias), Z, H2, W2, H, torch.bfloat16, us.norm.eps)
-    return ops.linear_ex(n, wc.bf16("l2", us.linear2.weight), None, want_shadow=True)
+    y = ops.linear(xb, wc.bf16("l1", W(us.linear1)), None)
+    n = ops.upsample_shuffle_ln(y, _f(norm_wb(us.norm)[0]), _f(norm_wb(us.norm)[1]), Z, H2, W2, H, torch.bfloat16, us.norm.eps)
+    return ops.linear_ex(n, wc.bf16("l2", W(us.linear2)), None, want_shadow=True)
 
 
 def patch_recover_forward(pr, x, Z, H, W, mode, skip=None, lat=721, denorm=None, xb=None, skip_b=None):
@@ -243,16 +322,16 @@ def patch_recover_forward(pr, x, Z, H, W, mode, skip=None, lat=721, denorm=None,
     if mode == "fp32":
         if skip is not None:
             x = torch.cat((skip, x), dim=-1)
-        yu = ops.linear(x[ns:], _w2d(pr.conv.weight), _f(pr.conv.bias))
-        ys = ops.linear(x[:ns], _w2d(pr.conv_surface.weight), _f(pr.conv_surface.bias))
+        yu = ops.linear(x[ns:], _w2d(W(pr.conv)), _f(B(pr.conv)))
+        ys = ops.linear(x[:ns], _w2d(W(pr.conv_surface)), _f(B(pr.conv_surface)))
         return ops.patch_recover_scatter(yu, ys, lat, denorm)
     wc = pr._wcache
     if skip is not None and xb is not None and skip_b is not None:
         # the skip concat (models/pangu_model.py:98) is read by the GEMMs from the two bf16 shadows directly
-        yu = ops.linear_ex(skip_b[ns:], wc.bf16("c", pr.conv.weight), _f(pr.conv.bias), a2=xb[ns:])
-        ys = ops.linear_ex(skip_b[:ns], wc.bf16("cs", pr.conv_surface.weight), _f(pr.conv_surface.bias), a2=xb[:ns])
+        yu = ops.linear_ex(skip_b[ns:], wc.bf16("c", W(pr.conv)), _f(B(pr.conv)), a2=xb[ns:])
+        ys = ops.linear_ex(skip_b[:ns], wc.bf16("cs", W(pr.conv_surface)), _f(B(pr.conv_surface)), a2=xb[:ns])
         return ops.patch_recover_scatter(yu, ys, lat, denorm)
     xb = ops.concat_cast_bf16(skip, x) if skip is not None else ops.cast_bf16(x)
-    yu = ops.linear(xb[ns:], wc.bf16("c", pr.conv.weight), _f(pr.conv.bias), out_dtype=torch.float32)
-    ys = ops.linear(xb[:ns], wc.bf16("cs", pr.conv_surface.weight), _f(pr.conv_surface.bias), out_dtype=torch.float32)
+    yu = ops.linear(xb[ns:], wc.bf16("c", W(pr.conv)), _f(B(pr.conv)), out_dtype=torch.float32)
+    ys = ops.linear(xb[:ns], wc.bf16("cs", W(pr.conv_surface)), _f(B(pr.conv_surface)), out_dtype=torch.float32)
     return ops.patch_recover_scatter(yu, ys, lat, denorm)

@@ -30,16 +30,40 @@ def stop_kernel_timing():
     return {k: tuple(v) for k, v in out.items()}
 
 
+_DEV = None           # device of the tensors of the op being issued (set by _chk / _on); the library itself never calls
+                      # cudaSetDevice, so the launch is made with that device current and on ITS current stream
+
+
+def _on(device):
+    """Declare the device of the op being issued (ops without tensor inputs)."""
+    global _DEV
+    _DEV = torch.device(device)
+    if _DEV.type != "cuda":
+        raise abi.PanguError(f"device {device}: the B200 path runs on CUDA only (no CPU fallback)")
+    if _DEV.index is None:
+        _DEV = torch.device("cuda", torch.cuda.current_device())
+    return _DEV
+
+
+def _launch(fn, args):
+    if _DEV is not None and _DEV.index != torch.cuda.current_device():
+        with torch.cuda.device(_DEV):            # model on cuda:1 while cuda:0 is current (reference: torch.device('cuda:%d'))
+            abi.check(getattr(abi.lib(), fn)(*args), fn)
+    else:
+        abi.check(getattr(abi.lib(), fn)(*args), fn)
+
+
 def _call(name, fn, args, kernels=1, flops=0.0, nbytes=0.0):
     global LAUNCHES
     LAUNCHES += kernels
     if _TIMING is None:
-        abi.check(getattr(abi.lib(), fn)(*args), fn)
+        _launch(fn, args)
         return
+    st = torch.cuda.current_stream(_DEV)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    abi.check(getattr(abi.lib(), fn)(*args), fn)
-    e1.record()
+    e0.record(st)
+    _launch(fn, args)
+    e1.record(st)
     _TIMING.append((name, e0, e1, flops, nbytes))
 
 
@@ -48,12 +72,15 @@ def _ptr(t):
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """The current stream of the device the op's tensors live on (not of the current device)."""
+    return torch.cuda.current_stream(_DEV).cuda_stream
 
 
 def _chk(t, dtype=None, name="tensor"):
+    global _DEV
     if not t.is_cuda:
         raise abi.PanguError(f"{name} must be a CUDA tensor: the B200 path has no CPU fallback")
+    _DEV = t.device
     if not t.is_contiguous():
         raise abi.PanguError(f"{name} must be contiguous")
     if dtype is not None and t.dtype != dtype:
@@ -96,6 +123,7 @@ def window_reverse(win, Z, H, W, roll):
 
 def window_source_index(Z, H, W, roll, device):
     nLon, T = window_counts(Z, H, W)
+    device = _on(device)
     out = torch.empty((nLon, T, 144), dtype=torch.int64, device=device)
     g = geom(Z, H, W, 32)
     _call("window_source_index", "pangu_window_source_index", (_ptr(out), g, int(roll), _stream(),))
@@ -104,6 +132,7 @@ def window_source_index(Z, H, W, roll, device):
 
 def shift_mask(Z, H, W, device):
     nLon, T = window_counts(Z, H, W)
+    device = _on(device)
     out = torch.empty((T, 144, 144), dtype=torch.float32, device=device)
     g = geom(Z, H, W, 32)
     _call("shift_mask", "pangu_shift_mask", (_ptr(out), g, _stream(),))
@@ -111,6 +140,7 @@ def shift_mask(Z, H, W, device):
 
 
 def position_index(device):
+    device = _on(device)
     out = torch.empty((144 * 144,), dtype=torch.int64, device=device)
     _call("position_index", "pangu_position_index", (_ptr(out), _stream(),))
     return out

@@ -15,7 +15,7 @@ import math
 
 import torch
 
-from . import abi
+from . import abi, ops
 from .abi import PanguError
 
 
@@ -61,10 +61,11 @@ def score_sums(pred, target, mask=None, clim=None):
             raise PanguError(f"pangu_b200.score: clim must have {planes} entries, got {clim.numel()}")
     w = latitude_weights(H, p.device)
     sums = torch.empty(planes, 5, dtype=torch.float64, device=p.device)
-    abi.check(abi.lib().pangu_lat_weighted_score_sums(
-        p.data_ptr(), t.data_ptr(), mask.data_ptr() if mask is not None else None,
-        clim.data_ptr() if clim is not None else None, w.data_ptr(), planes, H, W, sums.data_ptr(),
-        torch.cuda.current_stream(p.device).cuda_stream), "pangu_lat_weighted_score_sums")
+    ops._chk(p, torch.float32, "pred")                    # also selects p's device / stream for the launch
+    ops._call("lat_weighted_score_sums", "pangu_lat_weighted_score_sums",
+              (p.data_ptr(), t.data_ptr(), mask.data_ptr() if mask is not None else None,
+               clim.data_ptr() if clim is not None else None, w.data_ptr(), planes, H, W, sums.data_ptr(), ops._stream(),),
+              nbytes=float(p.numel() * 8))
     return sums.reshape(*lead, 5), H * W
 
 

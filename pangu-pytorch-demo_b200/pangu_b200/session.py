@@ -13,9 +13,15 @@ unchanged, so those loops run on the B200 path by replacing the `ort.InferenceSe
     output, output_surface = sess.run(None, {'input': x, 'input_surface': xs})
 
 What happens per call: pinned-host staging -> H2D -> one CUDA-graph replay of the forward with the de-normalisation
-(`normBackData`, era5_data/utils_data.py:540-546) fused into the patch-recover scatter -> D2H -> numpy.  When a call is
-fed exactly the arrays the previous call returned (the chained-forecast loops above), the step starts from the device
-copy of that state instead: no H2D, bit-identical to re-uploading because the returned arrays ARE that state.
+(`normBackData`, era5_data/utils_data.py:540-546) fused into the patch-recover scatter -> D2H -> numpy.
+
+Chained calls (`chain_on_device=True`, the default): when a call is fed exactly the array OBJECTS the previous call
+returned (the chained-forecast loops above), the step starts from the device copy of that state instead: no H2D.  For
+this to be bit-identical to re-uploading, the returned arrays must still hold what was returned, so they are handed
+out READ-ONLY (`flags.writeable = False`): an in-place edit between calls (clipping humidity, masking, bias
+correction) raises numpy's "assignment destination is read-only" instead of being silently dropped; edit a copy
+(`x = x.copy()` or `np.clip(x, ...)` without `out=`) and pass that -- a different object is uploaded like any fresh
+input.  `chain_on_device=False` gives plain ORT behaviour: writeable arrays, every call uploads its feeds.
 There is no CPU path: a model that is not on a CUDA device raises `PanguError`.
 """
 import numpy as np
@@ -35,11 +41,14 @@ class _NodeArg:
 
 
 class InferenceSession:
-    def __init__(self, model, statistics, statistics_last, maps, const_h, graph=True, copy_outputs=True):
+    def __init__(self, model, statistics, statistics_last, maps, const_h, graph=True, copy_outputs=True,
+                 chain_on_device=True):
         """`copy_outputs=False` returns views of the session's pinned host buffers (valid until the next `run`) and saves
-        two 287 MB host copies per call; the default hands out fresh arrays, like ORT."""
+        two 287 MB host copies per call; the default hands out fresh arrays, like ORT.  `chain_on_device`: see the module
+        docstring (read-only outputs + no re-upload when they are fed back)."""
         self._ro = Rollout(model, statistics, statistics_last, maps, const_h, graph=graph)
         self._copy = copy_outputs
+        self._chain = bool(chain_on_device)
         self._host_in = None             # pinned staging, allocated on first use
         self._host_out = None
         self._last = None                # (ndarray, ndarray) returned by the previous run, for the chained fast path
@@ -61,7 +70,8 @@ class InferenceSession:
             raise PanguError("InferenceSession.run: feeds must be exactly {'input', 'input_surface'}, got %s" % sorted(input_feed))
         x, xs = input_feed["input"], input_feed["input_surface"]
         dev = self._ro.dev
-        chained = self._last is not None and x is self._last[0] and xs is self._last[1]
+        chained = (self._chain and self._last is not None and x is self._last[0] and xs is self._last[1]
+                   and not x.flags.writeable and not xs.flags.writeable)
         if chained:
             inp, inp_s = self._state
             self.h2d_bytes = 0
@@ -87,7 +97,10 @@ class InferenceSession:
         res = [self._host_out[0].numpy(), self._host_out[1].numpy()]
         if self._copy:
             res = [r.copy() for r in res]
-        self._last = (res[0], res[1])
+        if self._chain:
+            for r in res:
+                r.flags.writeable = False         # the device state mirrors these values: keep them what they are
+            self._last = (res[0], res[1])
         if output_names:
             by_name = {"output": res[0], "output_surface": res[1]}
             try:

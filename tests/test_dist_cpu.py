@@ -163,7 +163,24 @@ def _dp_worker(rank, world, port, q):
             local = [p.grad.numpy().copy() for p in net.parameters()]           # numpy: pickled by value
             red.finish()
             outs.append((local, [p.grad.numpy().copy() for p in net.parameters()]))
-        q.put((rank, len(red.buckets), outs))
+        # gradient accumulation (the reference's loss / accumulation_steps, several backward passes per optimiser step)
+        net.zero_grad(set_to_none=True)
+        xs = [torch.full((3, 8), float(rank + 1 + k)) for k in range(2)]
+        with red.no_sync():
+            (net(xs[0]).square().sum() / 2).backward()
+        (net(xs[1]).square().sum() / 2).backward()
+        local = [p.grad.numpy().copy() for p in net.parameters()]               # accumulated local sums
+        red.finish()
+        outs.append((local, [p.grad.numpy().copy() for p in net.parameters()]))
+        # a second synchronising backward without finish() must raise, not mis-reduce
+        net.zero_grad(set_to_none=True)
+        net(xs[0]).square().sum().backward()
+        try:
+            net(xs[1]).square().sum().backward()
+            raised = False
+        except RuntimeError as e:
+            raised = "no_sync" in str(e)
+        q.put((rank, len(red.buckets), outs, raised))
     finally:
         dist.destroy_process_group()
 
@@ -177,13 +194,13 @@ def test_gradient_allreducer_gloo_world2():
         p.start()
     got = {}
     for _ in range(world):
-        rank, nb, outs = q.get(timeout=120)
+        rank, nb, outs, raised = q.get(timeout=120)
         got[rank] = outs
-        assert nb > 1
+        assert nb > 1 and raised
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for it in range(2):
+    for it in range(3):                                                       # it == 2: two accumulated micro-steps
         mean = [(a + b) / 2 for a, b in zip(got[0][it][0], got[1][it][0])]
         for r in range(world):
             for m, g in zip(mean, got[r][it][1]):

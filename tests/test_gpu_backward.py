@@ -2,8 +2,8 @@
 
 Tolerances (written where they are used): kernel-level checks compare with an fp32 torch evaluation of the SAME
 bf16 operands (only accumulation order differs): rel-L2 <= 2e-3.  Module-level checks compare the bf16 CUDA backward
-with the oracle's fp32 autograd: rel-L2 <= 3e-2 per gradient tensor (north_star's bf16 tolerance is 2e-2 on the
-outputs; gradients go through two bf16 passes)."""
+with the oracle's fp32 autograd: rel-L2 <= 2e-2 per gradient tensor (north_star's bf16 tolerance); the whole model, 16
+blocks deep, <= 3e-2 (measured <= 2.5e-2).  The worst measured values are printed."""
 import numpy as np
 import pytest
 import torch
@@ -13,7 +13,7 @@ import pangu_oracle as orc
 pytestmark = pytest.mark.gpu
 
 KERNEL_TOL = 2e-3
-GRAD_TOL = 3e-2
+GRAD_TOL = 2e-2
 
 
 @pytest.fixture(scope="module")
@@ -245,8 +245,51 @@ def test_block_backward_matches_oracle_autograd(dev, stage, roll):
         assert p.grad is not None and p.grad.shape == p.shape, name
         errs[name] = orc.rel_l2(p.grad, want[pfx + name])
     bad = {k: v for k, v in errs.items() if not v <= GRAD_TOL}
+    print(f"block {stage} roll {roll}: worst gradient rel-L2 {max(errs.values()):.3e} ({max(errs, key=errs.get)})")
     assert not bad, f"gradients off: {bad}\nall: {errs}"
     assert set(n for n, _ in blk.named_parameters()) == set(AG.BLOCK_PARAMS)
+
+
+def test_lora_wrapped_block_folds_adapters_and_trains_them(dev):
+    """finetune/lora_tune.py:169-186 wraps every nn.Linear with peft LoRA.  The kernels never call the sub-modules'
+    forward, so the adapters are folded into the operands (functional.lin_wb): a LoRA-wrapped block must equal the same
+    block with MERGED weights bit for bit, and the gradients reaching lora_A / lora_B must be the chain rule of the
+    merged weight's gradient: dA = s * B^T dW, dB = s * dW A^T.  (peft is not in this image: tests/fake_peft.py has its
+    attribute surface.)  Active lora_dropout cannot be folded and must raise, not be ignored."""
+    import copy
+    from fake_peft import LoraLinear, wrap_linears
+    from pangu_b200.abi import PanguError
+    dim, heads, Z, H, W, pfx = 192, 6, 8, 181, 24, "layers.EarthSpecificLayer0.blocks.EarthSpecificBlock1."
+    plain, _ = _block(dev, dim, heads, pfx)
+    lora = wrap_linears(copy.deepcopy(plain), r=16, lora_alpha=16).to(dev)
+    merged = copy.deepcopy(plain)
+    for (n, m), (_n2, l) in zip([(n, m) for n, m in merged.named_modules() if type(m) is torch.nn.Linear],
+                                [(n, m) for n, m in lora.named_modules() if isinstance(m, LoraLinear)]):
+        with torch.no_grad():
+            m.weight.add_(l.scaling["default"] * (l.lora_B["default"].weight @ l.lora_A["default"].weight))
+    g = _gen(61)
+    x = torch.randn(1, Z * H * W, dim, generator=g).to(dev)
+    gout = torch.randn(1, Z * H * W, dim, generator=g).to(dev)
+    lora.train(); merged.train()
+    y_l = lora(x, Z, H, W, True)
+    y_m = merged(x, Z, H, W, True)
+    assert torch.equal(y_l, y_m) and not torch.equal(y_l, plain.eval()(x, Z, H, W, True).detach())
+    y_l.backward(gout)
+    y_m.backward(gout)
+    lm = {n: m for n, m in lora.named_modules() if isinstance(m, LoraLinear)}
+    mm = {n: m for n, m in merged.named_modules() if type(m) is torch.nn.Linear}
+    assert len(lm) == 4
+    for n, l in lm.items():
+        dW = mm[n].weight.grad
+        A, B, s = l.lora_A["default"].weight, l.lora_B["default"].weight, l.scaling["default"]
+        assert l.base_layer.weight.grad is None                                  # frozen base, as peft leaves it
+        assert orc.rel_l2(A.grad, s * (B.detach().t() @ dW)) <= 1e-3, n           # same kernels; split-K atomics reorder sums
+        assert orc.rel_l2(B.grad, s * (dW @ A.detach().t())) <= 1e-3, n
+    drop = wrap_linears(copy.deepcopy(plain), r=16, lora_alpha=16, lora_dropout=0.1).to(dev).train()
+    with pytest.raises(PanguError, match="lora_dropout"):
+        drop(x, Z, H, W, True)
+    with torch.no_grad():
+        assert torch.isfinite(drop.eval()(x, Z, H, W, True)).all()               # dropout is the identity in eval()
 
 
 def test_block_backward_with_stochastic_depth(dev):
@@ -354,7 +397,7 @@ def test_embed_and_recover_backward(dev):
 
 
 # ------------------------------------------------------------------------------------------ whole model
-FULL_GRAD_TOL = 6e-2      # 16 blocks deep in bf16, every block re-computed in the backward; measured values are printed
+FULL_GRAD_TOL = 3e-2      # 16 blocks deep in bf16 (measured max 2.5e-2 in round 1); measured values are printed
 
 
 def _oracle_full_grads(params, inp, inp_s, stats, maps, const_h, gouts):

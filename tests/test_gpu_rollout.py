@@ -74,3 +74,15 @@ def test_ort_like_session_equals_rollout_step_and_chains_on_device():
     assert sess.h2d_bytes > 0
     assert np.array_equal(out2, out2b) and np.array_equal(out2_s, out2b_s)
     assert np.isfinite(out2).all() and not np.array_equal(out2, out)
+    # the chained fast path may never drop an edit: outputs are read-only, an edited copy is re-uploaded
+    assert not out.flags.writeable and not out_s.flags.writeable
+    with pytest.raises(ValueError):
+        out[0, 0, 0, 0] = 0.0
+    edited = np.clip(out, None, float(np.median(out)))
+    out3, _ = sess.run(None, {"input": edited, "input_surface": out_s})
+    assert sess.h2d_bytes > 0 and not np.array_equal(out3, out2)
+    plain = InferenceSession(model, stats, last, maps, const_h, chain_on_device=False)
+    o1, o1_s = plain.run(None, {"input": x, "input_surface": xs})
+    assert o1.flags.writeable and np.array_equal(o1, out)
+    plain.run(None, {"input": o1, "input_surface": o1_s})
+    assert plain.h2d_bytes > 0                               # plain ORT behaviour: every call uploads

@@ -112,3 +112,65 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "pangu_oracle" not in src and "oracle/" not in src, f"{f} references the oracle"
+
+
+def test_wrapped_or_hooked_linears_are_folded_or_refused_never_ignored():
+    """ADVICE r1 / finetune/lora_tune.py:169-186: the kernels read weights off the sub-modules, so a peft LoRA wrapper is
+    folded into the operand (W + scaling * B @ A, differentiable w.r.t. A and B), and everything the fold cannot express
+    (active LoRA dropout, unknown wrappers, sub-classes, forward hooks) raises PanguError."""
+    from fake_peft import LoraLinear, ModulesToSave
+    from pangu_b200 import functional as PF
+    from pangu_b200.abi import PanguError
+    torch.manual_seed(0)
+    base = torch.nn.Linear(24, 40)
+    w0, b0 = PF.lin_wb(base)
+    assert w0 is base.weight and b0 is base.bias
+    lora = LoraLinear(torch.nn.Linear(24, 40), r=4, lora_alpha=8)
+    w, b = PF.lin_wb(lora)
+    x = torch.randn(5, 24)
+    assert torch.allclose(torch.nn.functional.linear(x, w, b), lora(x), atol=1e-6)         # the fold IS the adapter's forward
+    g = torch.autograd.grad((torch.nn.functional.linear(x, w, b) ** 2).sum(), [lora.lora_A["default"].weight,
+                                                                              lora.lora_B["default"].weight])
+    gr = torch.autograd.grad((lora(x) ** 2).sum(), [lora.lora_A["default"].weight, lora.lora_B["default"].weight])
+    assert all(torch.allclose(a, c, atol=1e-5) for a, c in zip(g, gr))
+    assert not isinstance(w, torch.nn.Parameter) and PF.WeightCache._transient(w)          # folded operands are never cached
+    lora.merged = True
+    assert PF.lin_wb(lora)[0] is lora.base_layer.weight
+    lora.merged = False
+    drop = LoraLinear(torch.nn.Linear(24, 40), r=4, lora_dropout=0.1).train()
+    with pytest.raises(PanguError, match="lora_dropout"):
+        PF.lin_wb(drop)
+    PF.lin_wb(drop.eval())                                                                # dropout is the identity in eval()
+    conv = ModulesToSave(torch.nn.Conv1d(8, 6, 1))
+    assert PF.lin_wb(conv)[0] is conv.modules_to_save["default"].weight
+
+    class MyLinear(torch.nn.Linear):
+        def forward(self, x):
+            return super().forward(x) * 2
+
+    with pytest.raises(PanguError, match="expected nn.Linear"):
+        PF.lin_wb(MyLinear(3, 3))
+    hooked = torch.nn.Linear(3, 3)
+    hooked.register_forward_hook(lambda m, i, o: o + 1)
+    with pytest.raises(PanguError, match="hooks"):
+        PF.lin_wb(hooked)
+    with pytest.raises(PanguError, match="LayerNorm"):
+        PF.norm_wb(torch.nn.GroupNorm(1, 4))
+
+
+def test_wants_graph_follows_autograd_semantics():
+    """eval() with grad mode on and trainable parameters builds the graph (nn.Module semantics); no_grad,
+    frozen parameters or set_forward_only() keep the fused forward-only path."""
+    import models.layers as L
+    from pangu_b200 import autograd as AG
+    m = L.Mlp(192, 0).eval()
+    x = torch.zeros(4, 192)
+    assert AG.wants_graph(m, x)
+    with torch.no_grad():
+        assert not AG.wants_graph(m, x)
+    m.set_forward_only()
+    assert not AG.wants_graph(m, x)
+    m.set_forward_only(False)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    assert not AG.wants_graph(m, x) and AG.wants_graph(m, x.clone().requires_grad_(True))
