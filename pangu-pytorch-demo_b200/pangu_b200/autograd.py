@@ -54,8 +54,8 @@ BLOCK_PARAMS = ("attention.linear1.weight", "attention.linear1.bias", "attention
 
 def block_params(blk):
     a, m = blk.attention, blk.linear
-    return (PF.W(a.linear1), PF.B(a.linear1), a.earth_specific_bias, PF.W(a.linear2), PF.B(a.linear2),
-            blk.norm1.weight, blk.norm1.bias, PF.W(m.linear1), PF.B(m.linear1), PF.W(m.linear2), PF.B(m.linear2),
+    return (PF.lin_w(a.linear1), PF.lin_b(a.linear1), a.earth_specific_bias, PF.lin_w(a.linear2), PF.lin_b(a.linear2),
+            blk.norm1.weight, blk.norm1.bias, PF.lin_w(m.linear1), PF.lin_b(m.linear1), PF.lin_w(m.linear2), PF.lin_b(m.linear2),
             blk.norm2.weight, blk.norm2.bias)
 
 
@@ -74,7 +74,7 @@ def block_forward_train(blk, x0, x0b, Z, H, W, roll, s1, s2):
         w_qkv, b_qkv, eb = PF.attention_operands(att, wc)               # pre-scaled (scale*log2e folded into q)
         qkv = ops.linear(x0b, w_qkv, b_qkv)
         o, lse = ops.window_attention_train(qkv, b_qkv, eb, Z, H, W, att.head_number, 1 if roll else 0)
-        y1 = ops.linear(o, wc.bf16("a2", PF.W(att.linear2)), f(PF.B(att.linear2)), out_dtype=F32)
+        y1 = ops.linear(o, wc.bf16("a2", PF.lin_w(att.linear2)), f(PF.lin_b(att.linear2)), out_dtype=F32)
         gam1, bet1 = PF._affine(blk.norm1, s1)
         x1, x1b = ops.ln_residual(y1, gam1, bet1, residual=x0, want_bf16=True, eps=blk.norm1.eps)
         sv.update(qkv=qkv, o=o, lse=lse, y1=y1)
@@ -82,9 +82,9 @@ def block_forward_train(blk, x0, x0b, Z, H, W, roll, s1, s2):
         x1, x1b = x0, x0b
     sv["x1b"] = x1b
     if s2 != 0.0:
-        w1, b1 = wc.bf16("m1", PF.W(mlp.linear1)), f(PF.B(mlp.linear1))
+        w1, b1 = wc.bf16("m1", PF.lin_w(mlp.linear1)), f(PF.lin_b(mlp.linear1))
         h_pre, h = ops.linear_gelu_pre(x1b, w1, b1)                     # one GEMM pass leaves both (aux epilogue)
-        y2 = ops.linear(h, wc.bf16("m2", PF.W(mlp.linear2)), f(PF.B(mlp.linear2)), out_dtype=F32)
+        y2 = ops.linear(h, wc.bf16("m2", PF.lin_w(mlp.linear2)), f(PF.lin_b(mlp.linear2)), out_dtype=F32)
         gam2, bet2 = PF._affine(blk.norm2, s2)
         x2, x2b = ops.ln_residual(y2, gam2, bet2, residual=x1, want_bf16=True, eps=blk.norm2.eps)
         sv.update(h_pre=h_pre, h=h, y2=y2)
@@ -114,10 +114,10 @@ def block_backward(blk, sv, Z, H, W, roll, s1, s2, g2):
         dy2 = ops.ln_backward(g2, sv["y2"], f(blk.norm2.weight), scale=s2, dgamma=dg2, dbeta=db2n, dcolsum=db2, eps=blk.norm2.eps)
         dw2 = ops.linear_wgrad(dy2, sv["h"])
         db1 = _zeros(4 * C, dev)
-        dh = ops.linear_gelu_backward(dy2, _wT(wc, "m2", PF.W(mlp.linear2)), sv["h_pre"], db1)   # [N, 4C] bf16, * gelu'(h_pre)
+        dh = ops.linear_gelu_backward(dy2, _wT(wc, "m2", PF.lin_w(mlp.linear2)), sv["h_pre"], db1)   # [N, 4C] bf16, * gelu'(h_pre)
         del dy2
         dw1 = ops.linear_wgrad(dh, x1b)
-        g1 = ops.linear_add(dh, _wT(wc, "m1", PF.W(mlp.linear1)), None, addend=g2)
+        g1 = ops.linear_add(dh, _wT(wc, "m1", PF.lin_w(mlp.linear1)), None, addend=g2)
         del dh
         grads[7], grads[8], grads[9], grads[10], grads[11], grads[12] = dw1, db1, dw2, db2, dg2, db2n
     else:
@@ -131,7 +131,7 @@ def block_backward(blk, sv, Z, H, W, roll, s1, s2, g2):
         dg1, db1n, dba2 = _zeros(C, dev), _zeros(C, dev), _zeros(C, dev)
         dy1 = ops.ln_backward(g1, sv["y1"], f(blk.norm1.weight), scale=s1, dgamma=dg1, dbeta=db1n, dcolsum=dba2, eps=blk.norm1.eps)
         dwa2 = ops.linear_wgrad(dy1, sv["o"])
-        do = ops.linear(dy1, _wT(wc, "a2", PF.W(att.linear2)), None)   # [N, C] bf16
+        do = ops.linear(dy1, _wT(wc, "a2", PF.lin_w(att.linear2)), None)   # [N, C] bf16
         del dy1
         d_eb = torch.zeros(att.earth_specific_bias.shape[1:], dtype=F32, device=dev)
         dba1 = _zeros(3 * C, dev)
@@ -139,7 +139,7 @@ def block_backward(blk, sv, Z, H, W, roll, s1, s2, g2):
                                              d_eb, dba1)
         del do
         dwa1 = ops.linear_wgrad(dqkv, x0b)
-        g0 = ops.linear_add(dqkv, _wT(wc, "a1", PF.W(att.linear1)), None, addend=g1)
+        g0 = ops.linear_add(dqkv, _wT(wc, "a1", PF.lin_w(att.linear1)), None, addend=g1)
         del dqkv
         grads[0], grads[1], grads[2], grads[3], grads[4], grads[5], grads[6] = \
             dwa1, dba1, d_eb.unsqueeze(0), dwa2, dba2, dg1, db1n
@@ -218,7 +218,7 @@ class PatchEmbedFn(torch.autograd.Function):
             dws = ops.linear_wgrad(gb[:ns], ps)
             dw = ops.linear_wgrad(gb[ns:], pu)
             dbs, db = ops.colsum(g[:ns]), ops.colsum(g[ns:])
-        return (None, None, None, None, None, None, _like(PF.W(pe.conv), dw), db, _like(PF.W(pe.conv_surface), dws), dbs)
+        return (None, None, None, None, None, None, _like(PF.lin_w(pe.conv), dw), db, _like(PF.lin_w(pe.conv_surface), dws), dbs)
 
 
 # ------------------------------------------------------------------------------------------ DownSample
@@ -246,7 +246,7 @@ class DownSampleFn(torch.autograd.Function):
             gb = ops.cast_bf16(g.contiguous())
             dw = ops.linear_wgrad(gb, m)
             del m
-            dm = ops.linear_add(gb, _wT(ds._wcache, "l", PF.W(ds.linear)), None)
+            dm = ops.linear_add(gb, _wT(ds._wcache, "l", PF.lin_w(ds.linear)), None)
             dgam, dbet = _zeros(C4, x.device), _zeros(C4, x.device)
             dx = ops.downsample_merge_ln_backward(dm, x, f(ds.norm.weight), dgam, dbet, Z, H, W, ds.norm.eps)
         return dx, None, None, None, None, dw, dgam, dbet
@@ -276,17 +276,17 @@ class UpSampleFn(torch.autograd.Function):
         with torch.no_grad():
             f, wc = PF._f, us._wcache
             Co = us.norm.weight.shape[0]
-            y = ops.linear(xb, wc.bf16("l1", PF.W(us.linear1)), None)
+            y = ops.linear(xb, wc.bf16("l1", PF.lin_w(us.linear1)), None)
             n = ops.upsample_shuffle_ln(y, f(us.norm.weight), f(us.norm.bias), Z, H2, W2, H, torch.bfloat16, us.norm.eps)
             gb = ops.cast_bf16(g.contiguous())
             dw2 = ops.linear_wgrad(gb, n)
             del n
-            dn = ops.linear_add(gb, _wT(wc, "l2", PF.W(us.linear2)), None)
+            dn = ops.linear_add(gb, _wT(wc, "l2", PF.lin_w(us.linear2)), None)
             dgam, dbet = _zeros(Co, xb.device), _zeros(Co, xb.device)
             dy = ops.upsample_shuffle_ln_backward(dn, y, f(us.norm.weight), dgam, dbet, Z, H2, W2, H, us.norm.eps)
             del dn, y
             dw1 = ops.linear_wgrad(dy, xb)
-            dx = ops.linear_add(dy, _wT(wc, "l1", PF.W(us.linear1)), None)
+            dx = ops.linear_add(dy, _wT(wc, "l1", PF.lin_w(us.linear1)), None)
         return dx, None, None, None, dw1, dw2, dgam, dbet
 
 
@@ -323,7 +323,7 @@ class PatchRecoverFn(torch.autograd.Function):
                 g_out_s = torch.zeros((1, 4, 721, 1440), dtype=F32, device=dev)
             dyu, dys = ops.patch_recover_gather_backward(g_out.contiguous().float(), g_out_s.contiguous().float(), 721)
             wc = pr._wcache
-            wT, wsT = _wT(wc, "c", PF.W(pr.conv)), _wT(wc, "cs", PF.W(pr.conv_surface))       # [Cin, 160] / [Cin, 64]
+            wT, wsT = _wT(wc, "c", PF.lin_w(pr.conv)), _wT(wc, "cs", PF.lin_w(pr.conv_surface))       # [Cin, 160] / [Cin, 64]
             Cin = wT.shape[0]
             dw = torch.zeros((160, Cin), dtype=F32, device=dev)
             dws = torch.zeros((64, Cin), dtype=F32, device=dev)
@@ -342,7 +342,7 @@ class PatchRecoverFn(torch.autograd.Function):
                 ops.linear_add(dys, wsT[c0:c1].contiguous(), None, out=d[:ns])
                 dins.append(d)
         dskip, dx = (dins[0], dins[1]) if ctx.has_skip else (None, dins[0])
-        return (dskip, None, dx, None, None, None, _like(PF.W(pr.conv), dw), db, _like(PF.W(pr.conv_surface), dws), dbs)
+        return (dskip, None, dx, None, None, None, _like(PF.lin_w(pr.conv), dw), db, _like(PF.lin_w(pr.conv_surface), dws), dbs)
 
 
 # ------------------------------------------------------------------------------------------ module-level helpers
@@ -373,18 +373,18 @@ def block_apply(blk, x, xb, Z, H, W, roll):
 
 
 def embed_apply(pe, inp, inp_s, stats, maps, const_h):
-    return PatchEmbedFn.apply(inp, inp_s, pe, stats, maps, const_h, PF.W(pe.conv), PF.B(pe.conv),
-                              PF.W(pe.conv_surface), PF.B(pe.conv_surface))
+    return PatchEmbedFn.apply(inp, inp_s, pe, stats, maps, const_h, PF.lin_w(pe.conv), PF.lin_b(pe.conv),
+                              PF.lin_w(pe.conv_surface), PF.lin_b(pe.conv_surface))
 
 
 def downsample_apply(ds, x, Z, H, W):
-    return DownSampleFn.apply(x, ds, Z, H, W, PF.W(ds.linear), ds.norm.weight, ds.norm.bias)
+    return DownSampleFn.apply(x, ds, Z, H, W, PF.lin_w(ds.linear), ds.norm.weight, ds.norm.bias)
 
 
 def upsample_apply(us, x, xb, Z=8, H2=91, W2=180, H=181):
-    return UpSampleFn.apply(x, xb, us, (Z, H2, W2, H), PF.W(us.linear1), PF.W(us.linear2), us.norm.weight, us.norm.bias)
+    return UpSampleFn.apply(x, xb, us, (Z, H2, W2, H), PF.lin_w(us.linear1), PF.lin_w(us.linear2), us.norm.weight, us.norm.bias)
 
 
 def recover_apply(pr, x, xb, Z, H, W, skip=None, skip_b=None):
-    return PatchRecoverFn.apply(skip, skip_b, x, xb, pr, (Z, H, W), PF.W(pr.conv), PF.B(pr.conv),
-                                PF.W(pr.conv_surface), PF.B(pr.conv_surface))
+    return PatchRecoverFn.apply(skip, skip_b, x, xb, pr, (Z, H, W), PF.lin_w(pr.conv), PF.lin_b(pr.conv),
+                                PF.lin_w(pr.conv_surface), PF.lin_b(pr.conv_surface))

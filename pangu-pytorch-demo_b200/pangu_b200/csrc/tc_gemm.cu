@@ -46,14 +46,18 @@ constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter,
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kStageEpiBytes = 4096;         // per epilogue warp: 32 rows x 128 B staging tile
 
-// LayerNorm epilogue configuration (tc_ln_epilogue.cuh): 32-column units with 2 residual tiles in flight at
-// C = 192, 16-column units with 3 in flight at C = 384 (shared memory is tighter there).
+// LayerNorm epilogue configuration (tc_ln_epilogue.cuh): residual tiles arrive by TMA (the rows were pulled into L2 one
+// row tile ahead), 2 bf16 staging tiles so that the bulk stores of one unit drain while the next is computed;
+// 32-column units at C = 192, 16-column units at C = 384 (shared memory is tighter there).
 template <int BN> struct LnCfg {
   static constexpr int UW = BN == 192 ? 32 : 16;
-  static constexpr int D = BN == 192 ? 2 : 3;
-  static constexpr int STG = UW * 128 * (D + 1);              // fp32 staging tiles per warp
-  static constexpr int STGB = UW * 64;                        // bf16 staging tile per warp
+  static constexpr int D = BN == 192 ? 1 : 2;                 // residual tiles in flight per warp
+  static constexpr int NB16 = 2;
+  static constexpr int NBUF = D + NB16;
+  static constexpr int STG = UW * 128 * NBUF;                 // fp32 staging tiles per warp
+  static constexpr int STGB = UW * 64 * NB16;                 // bf16 staging tiles per warp
   static constexpr int BYTES = kEpiWarps * (STG + STGB) + 2 * 2 * 128 * 8 + 3 * BN * 4;
+  static_assert(NBUF <= 4, "four load barriers per epilogue warp");
 };
 
 template <int BN, bool LN = false>
@@ -190,7 +194,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t v[32];
-    LnTileEpilogue<LN ? BN : 192, LC::UW, LC::D, true, true> ln;
+    LnTileEpilogue<LN ? BN : 192, LC::UW, LC::D, true, true, LC::NB16, LC::NBUF> ln;
     if constexpr (LN) {
       ln.bias = a.bias; ln.gamma = a.gamma; ln.beta = a.beta; ln.residual = a.residual;
       ln.x_out = a.x_out; ln.xb = a.x_out_bf16; ln.M = a.M; ln.eps = a.eps;
@@ -202,7 +206,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const long long m_base = (long long)(tile / a.n_tiles) * BM + q * 32;
       const int n0 = (tile % a.n_tiles) * BN;
-      if constexpr (LN) { ln.m_base = m_base; ln.prefetch(); }     // residual tiles fly while the MMAs finish
+      if constexpr (LN) {
+        ln.m_base = m_base; ln.prefetch();                           // residual tiles fly while the MMAs finish
+        // the residual rows of this CTA's NEXT row tile -> L2 (16 rows per warp), so that its tile loads are L2 hits
+        const int nxt = tile + gridDim.x;
+        if (nxt < num_tiles && lane == 0) {
+          const long long r0 = (long long)(nxt / a.n_tiles) * BM + q * 32 + hf * 16;
+          long long nrows = a.M - r0;
+          if (nrows > 16) nrows = 16;
+          if (nrows > 0) prefetch_l2_bulk(a.residual + r0 * BN, (uint32_t)(nrows * BN * 4));
+        }
+      }
       if (!LN && a.addend != nullptr && a.out_dtype != PANGU_BF16) {
         // dgrad + residual-gradient add: this tile's addend rows go to L2 while its (long-K) main loop runs, so the
         // loads of the write-out loop below are L2 hits (lane -> row, warp half -> half of the BN columns)

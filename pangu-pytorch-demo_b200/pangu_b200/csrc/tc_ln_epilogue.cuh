@@ -28,11 +28,15 @@ __device__ __forceinline__ int ln_stg16(int r, int cc) { return r * 64 + ((cc ^ 
 // TMASTORE: results leave through TMA bulk stores issued by one lane from the (hardware-swizzle-compatible) staging
 // tiles -- fp32 tile in place, bf16 tile in `stg_b` -- instead of 2 x NV st.global per lane; the affine parameters
 // (bias, gamma, beta) are then read from a shared-memory copy `sparams` [3][C] (broadcast LDS) rather than __ldg.
-template <int C, int UW = 16, int D = 3, bool ASYNC = false, bool TMASTORE = false>
+// NB16 = bf16 staging tiles per warp: unit idx only waits for the bulk stores of unit idx - NB16 to have read their
+// source (cp.async.bulk.wait_group.read NB16-1), so with NB16 = 2 the store of one unit drains while the next unit is
+// computed (r2: the single-tile version serialised every unit behind its predecessor's store, ~2.5 k clocks per unit).
+// The fp32 tile of unit idx + D is the one unit idx + D - NBUF used, whose store must be complete: NBUF >= D + NB16.
+template <int C, int UW = 16, int D = 3, bool ASYNC = false, bool TMASTORE = false, int NB16 = 1, int NBUF_ = 0>
 struct LnTileEpilogue {
   const CUtensorMap* tm_out = nullptr;               // fp32 [M, C], box UW x 32, swizzle UW*4 bytes
   const CUtensorMap* tm_xb = nullptr;                // bf16 [M, C], box UW x 32, swizzle UW*2 bytes (or null)
-  uint8_t* stg_b = nullptr;                          // per warp: 32 rows x UW bf16
+  uint8_t* stg_b = nullptr;                          // per warp: NB16 tiles of 32 rows x UW bf16
   const float* sparams = nullptr;                    // smem [3][C]: bias, gamma, beta
   const CUtensorMap* tm_res = nullptr;               // ASYNC: fp32 residual [M, C], same box / swizzle as tm_out
   uint64_t* ld_bar = nullptr;                        // ASYNC: this warp's NBUF mbarriers (count 1) for the tile loads
@@ -41,7 +45,10 @@ struct LnTileEpilogue {
     return UW == 32 ? r * 64 + ((cc ^ ((r >> 1) & 3)) << 4) : r * 32 + ((cc ^ ((r >> 2) & 1)) << 4);
   }
   static constexpr int UNIT_BYTES = UW * 128;        // one staging tile: 32 rows x UW fp32
-  static constexpr int NBUF = ASYNC ? D + 1 : 1;     // staging tiles per warp (ASYNC: D landing tiles + the one being consumed)
+  static constexpr int NBUF = ASYNC ? (NBUF_ > 0 ? NBUF_ : D + NB16) : 1;   // fp32 staging tiles per warp (ASYNC: D landing + NB16 draining)
+  static constexpr int STGB_TILE = UW * 64;          // one bf16 staging tile: 32 rows x UW bf16
+  static_assert(!ASYNC || NBUF >= D + NB16, "a refilled fp32 tile must belong to a unit whose store has been waited for");
+  static_assert(ASYNC || NB16 == 1, "register-prefetch mode stages through one tile");
   static constexpr int NU = C / (2 * UW);            // units per warp
   static constexpr int NV = UW / 4;                  // float4 per lane per unit
   static constexpr int RPI = 128 / UW;               // rows covered by one warp-wide 16-byte access (8 or 4)
@@ -86,7 +93,7 @@ struct LnTileEpilogue {
   }
   __device__ __forceinline__ void prefetch() {
     if constexpr (ASYNC) {
-      if constexpr (TMASTORE) {                        // the previous tile's bulk stores still read the staging tiles
+      if constexpr (TMASTORE) {                        // the previous row tile's bulk stores still read the staging tiles
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
       }
@@ -130,8 +137,9 @@ struct LnTileEpilogue {
     const int u = hf + 2 * idx, rcc = lane & (NV - 1), rr0 = lane / NV;
     uint8_t* stg_u = stg;
     if (dbg) dbg[0] = clock64();
-    if constexpr (TMASTORE) {                          // the previous unit's bulk stores must have drained the tiles
-      if (lane == 0) tma_store_wait_read();
+    uint8_t* stg_bu = stg_b + (NB16 > 1 ? (idx % NB16) * STGB_TILE : 0);
+    if constexpr (TMASTORE) {                          // the bulk stores of unit idx - NB16 must have drained their tiles
+      if (lane == 0) tma_store_wait_read_n<NB16 - 1>();
       __syncwarp();
     }
     if constexpr (ASYNC) {
@@ -183,7 +191,7 @@ struct LnTileEpilogue {
       *reinterpret_cast<float4*>(stg_u + stg_off(lane, cc)) = rr[cc];
       if constexpr (TMASTORE) {
         if (tm_xb != nullptr) {                        // 4 bf16 = 8 bytes: half of 16-byte chunk cc >> 1
-          uint8_t* pb = stg_b + stg_b_off(lane, cc >> 1) + (cc & 1) * 8;
+          uint8_t* pb = stg_bu + stg_b_off(lane, cc >> 1) + (cc & 1) * 8;
           *reinterpret_cast<uint2*>(pb) = make_uint2(pack_bf16(rr[cc].x, rr[cc].y), pack_bf16(rr[cc].z, rr[cc].w));
         }
       }
@@ -195,7 +203,7 @@ struct LnTileEpilogue {
       if (dbg) dbg[4] = clock64();
       if (lane == 0 && store) {
         tma_store_2d(tm_out, stg_u, u * UW, (int)m_base);
-        if (tm_xb != nullptr) tma_store_2d(tm_xb, stg_b, u * UW, (int)m_base);
+        if (tm_xb != nullptr) tma_store_2d(tm_xb, stg_bu, u * UW, (int)m_base);
         tma_store_commit();
       }
       __syncwarp();

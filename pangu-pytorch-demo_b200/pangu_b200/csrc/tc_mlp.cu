@@ -11,16 +11,22 @@
 // 128 tokens -- that halves the L2->SM operand traffic (the measured limiter of the un-fused GEMMs) and
 // the shared-memory footprint (the 96 KiB x tile + a 4-deep weight ring fit at C = 384).
 //
-// Warp roles (per CTA, 384 threads):
-//   warp 0      TMA producer (own x rows, own halves of the W1/W2 chunks; signals the LEADER's barriers)
-//   warp 1      MMA issuer   (leader CTA only; one thread)
-//   warp 2      TMEM allocator (cta_group::2, both CTAs)
-//   warps 4..11 epilogue: per hidden chunk  H(TMEM) -> +b1, GELU -> bf16 P(TMEM);
-//               per row tile  Y(TMEM) -> +b2, LayerNorm, +residual -> fp32 + bf16, row-contiguous stores
+// Warp roles (per CTA, 640 threads; r2: the LayerNorm epilogue has warps of its own):
+//   warp 0        TMA producer (own x rows, own halves of the W1/W2 chunks; signals the LEADER's barriers); also pulls the
+//                 row tile's fp32 residual rows into L2 while the MMAs run (cp.async.bulk.prefetch.L2)
+//   warp 1        MMA issuer   (leader CTA only; one thread)
+//   warp 2        TMEM allocator (cta_group::2, both CTAs)
+//   warps 4..11   GELU: per hidden chunk  H(TMEM) -> +b1, GELU -> fp16 P(TMEM)
+//   warps 12..19  LayerNorm: per row tile  Y(TMEM) -> +b2, LayerNorm, +residual -> fp32 + bf16 through TMA bulk stores
+// setmaxnreg moves registers from the control warpgroup (56) to the GELU warpgroups (112); the LayerNorm groups keep 96.
 //
 // TMEM columns: Y [0,384) (one accumulator at C = 384, TWO at C = 192) | HP0 [384,448) | HP1 [448,512).  With two
-// Y accumulators the LayerNorm/store phase of row tile i is spread, one 16-column unit at a time, between the
-// hidden chunks of row tile i+1, so its HBM traffic overlaps the MMAs instead of bursting.  HP_b holds the fp32
+// Y accumulators the LayerNorm warps work on row tile i while the MMA / GELU warps are on row tile i+1, so the
+// epilogue's HBM traffic overlaps the MMAs.  At C = 384 TMEM is full (Y 384 + H/P 128): the epilogue is a phase of its own,
+// and it is made short instead: the residual rows are already in L2, the units are staged through 4 fp32 + 2 bf16 tiles
+// per warp so that loads, arithmetic and bulk stores of neighbouring units overlap (tc_ln_epilogue.cuh), and that
+// staging lives in the x tile's shared memory, which is dead once the last GEMM1 of the row tile has completed.
+// HP_b holds the fp32
 // hidden chunk H_j (j & 1 == b); each epilogue warp overwrites the first half of ITS OWN 32 columns with
 // the packed bf16 P_j, which GEMM2 then reads as its A operand.  Because the tensor pipe executes MMAs in
 // issue order, G1(j+2) (which overwrites HP_b) needs no barrier against G2(j) (which reads it).
@@ -33,8 +39,9 @@
 namespace pangu {
 namespace tc {
 
-constexpr int kMlpThreads = 384;
-constexpr int kMlpEpiWarps = 8;
+constexpr int kMlpThreads = 640;
+constexpr int kMlpEpiWarps = 8;                  // GELU warps 4..11; and as many LayerNorm warps, 12..19
+constexpr int kMlpLnWarp0 = 12;
 constexpr int NH = 64;                           // hidden columns per chunk (per CTA pair)
 
 struct MlpArgs {
@@ -65,18 +72,23 @@ struct MlpCfg {
   static constexpr int X_BYTES = 128 * C * 2;    // this CTA's rows of the x tile
   static constexpr int SLOT_BYTES = C * 64;      // half W1 chunk [32 x C] == half W2 chunk [C/2 x 64] (bf16)
   static constexpr int LN_UW = C == 192 ? 32 : 16;   // LayerNorm unit width (columns): 32 where smem allows
-  static constexpr int LN_D = C == 192 ? 1 : 3;      // residual prefetch depth: the interleaved schedule at C = 192
-                                                     // leaves thousands of cycles between a fetch and its use
-  static constexpr bool LN_ASYNC = C == 192;         // cp.async residual prefetch (two staging tiles per warp)
-  static constexpr int STG_BYTES = LN_UW * 128 * (LN_ASYNC ? 2 : 1);   // per epilogue warp: fp32 staging tile(s)
-  static constexpr int STGB_BYTES = LN_UW * 64;      // per epilogue warp: bf16 staging tile of the TMA store
+  static constexpr int LN_D = C == 192 ? 1 : 2;      // residual tiles in flight per LayerNorm warp (TMA loads)
+  static constexpr int LN_NB16 = C == 192 ? 1 : 2;   // bf16 staging tiles: 2 = the store of unit i drains while unit i+1 is computed
+  static constexpr int LN_NBUF = LN_D + LN_NB16;      // fp32 staging tiles: LN_D landing + LN_NB16 draining
+  static constexpr int STG_BYTES = LN_UW * 128 * LN_NBUF;     // per LayerNorm warp: fp32 staging tiles
+  static constexpr int STGB_BYTES = LN_UW * 64 * LN_NB16;     // per LayerNorm warp: bf16 staging tiles of the TMA stores
+  // C = 384: the staging tiles alias the x tile (dead after the last GEMM1 of the row tile; the producer waits for the
+  // LayerNorm warps before it loads the next one).  C = 192: the LayerNorm of tile i runs next to the MMAs of tile i+1,
+  // which read x -- dedicated staging.
+  static constexpr bool LN_ALIAS_X = C == 384;
   static constexpr int PART_BYTES = 2 * 2 * 128 * 8; // LayerNorm partial sums
   static constexpr int PARAM_BYTES = 3 * C * 4;      // b2, gamma, beta
-  static constexpr int EPI_BYTES = kMlpEpiWarps * (STG_BYTES + STGB_BYTES) + PART_BYTES + PARAM_BYTES;
-  static constexpr int BAR_BYTES = 512;
+  static constexpr int EPI_BYTES = (LN_ALIAS_X ? 0 : kMlpEpiWarps * (STG_BYTES + STGB_BYTES)) + PART_BYTES + PARAM_BYTES;
+  static constexpr int BAR_BYTES = 1024;
   static constexpr int AVAIL = 227 * 1024 - 1024 - BAR_BYTES - X_BYTES - EPI_BYTES;
   static constexpr int NSLOT = AVAIL / SLOT_BYTES > 8 ? 8 : AVAIL / SLOT_BYTES;
   static constexpr int SMEM_BYTES = 1024 + X_BYTES + NSLOT * SLOT_BYTES + EPI_BYTES + BAR_BYTES;
+  static_assert(!LN_ALIAS_X || kMlpEpiWarps * (STG_BYTES + STGB_BYTES) <= X_BYTES, "staging must fit in the x tile");
   static constexpr int NY = C == 192 ? 2 : 1;    // output accumulators: double-buffered when TMEM has room
   static constexpr int COL_HP = 384;             // two 64-column H/P buffers behind the Y accumulator(s)
   static_assert(C % 192 == 0 && C + 128 <= 512, "C must be 192 or 384");
@@ -96,21 +108,25 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sX = smem;                                         // [KB1][128 rows x 128 B]   (SW128 K-major)
   uint8_t* sW = smem + Cfg::X_BYTES;                          // [NSLOT][SLOT_BYTES]
-  uint8_t* epi_smem = sW + NSLOT * Cfg::SLOT_BYTES;           // 8 x 2 KiB staging + LN partial sums
-  uint8_t* stgb_smem = epi_smem + kMlpEpiWarps * Cfg::STG_BYTES;
-  float2* ln_part = reinterpret_cast<float2*>(stgb_smem + kMlpEpiWarps * Cfg::STGB_BYTES);
+  uint8_t* epi_smem = sW + NSLOT * Cfg::SLOT_BYTES;
+  // LayerNorm staging: fp32 tiles of all warps, then bf16 tiles of all warps (inside the x tile at C = 384)
+  uint8_t* stg_smem = Cfg::LN_ALIAS_X ? sX : epi_smem;
+  uint8_t* stgb_smem = stg_smem + kMlpEpiWarps * Cfg::STG_BYTES;
+  float2* ln_part = reinterpret_cast<float2*>(epi_smem + (Cfg::LN_ALIAS_X ? 0 : kMlpEpiWarps * (Cfg::STG_BYTES + Cfg::STGB_BYTES)));
   float* sparams = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ln_part) + Cfg::PART_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
   uint64_t* x_full = bars + 0;
-  uint64_t* x_empty = bars + 1;
-  uint64_t* h_full = bars + 2;       // [2]  MMA -> epilogue: H_j complete in HP[j&1]   (both CTAs)
-  uint64_t* p_full = bars + 4;       // [2]  epilogue -> MMA: P_j written to HP[j&1]    (leader's copy)
-  uint64_t* y_full = bars + 6;       // [2]  MMA -> epilogue: Y accumulator complete    (both CTAs)
-  uint64_t* y_empty = bars + 8;      // [2]  epilogue -> MMA: Y accumulator drained     (leader's copy)
-  uint64_t* w_full = bars + 10;      // [NSLOT]
-  uint64_t* w_empty = bars + 10 + NSLOT;
-  uint64_t* ln_bar = bars + 10 + 2 * NSLOT;      // [8 warps][2] barriers of the residual tile loads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26 + 2 * NSLOT);
+  uint64_t* x_empty = bars + 1;      // MMA -> producer (and LayerNorm warps): every GEMM1 of the row tile has read x  (both CTAs)
+  uint64_t* h_full = bars + 2;       // [2]  MMA -> GELU: H_j complete in HP[j&1]            (both CTAs)
+  uint64_t* p_full = bars + 4;       // [2]  GELU -> MMA: P_j written to HP[j&1]             (leader's copy)
+  uint64_t* y_full = bars + 6;       // [2]  MMA -> LayerNorm: Y accumulator complete        (both CTAs)
+  uint64_t* y_empty = bars + 8;      // [2]  LayerNorm -> MMA: Y accumulator drained         (leader's copy)
+  uint64_t* xs_free = bars + 10;     // LayerNorm -> producer: the staging tiles inside the x tile are free (local)
+  uint64_t* w_full = bars + 11;      // [NSLOT]
+  uint64_t* w_empty = bars + 11 + NSLOT;
+  uint64_t* ln_bar = bars + 11 + 2 * NSLOT;      // [8 warps][4] barriers of the residual tile loads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11 + 2 * NSLOT + 4 * kMlpEpiWarps);
+  static_assert((11 + 2 * 8 + 4 * kMlpEpiWarps) * 8 + 8 <= Cfg::BAR_BYTES, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                    // 0 = leader of the pair
@@ -121,6 +137,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmOut);
+    tma_prefetch_desc(&tmRes);
     if (a.x_out_bf16 != nullptr) tma_prefetch_desc(&tmXb);
   }
   for (int i = threadIdx.x; i < 3 * C; i += kMlpThreads)      // affine parameters of the row-tile epilogue -> smem
@@ -130,8 +147,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     mbar_init(&h_full[0], 1); mbar_init(&h_full[1], 1);
     mbar_init(&p_full[0], 2 * kMlpEpiWarps); mbar_init(&p_full[1], 2 * kMlpEpiWarps);
     for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 2 * kMlpEpiWarps); }
+    mbar_init(xs_free, kMlpEpiWarps);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int i = 0; i < 2 * kMlpEpiWarps; ++i) mbar_init(&ln_bar[i], 1);
+    for (int i = 0; i < 4 * kMlpEpiWarps; ++i) mbar_init(&ln_bar[i], 1);
     fence_barrier_init();
   }
   cluster_sync_all();                                         // barrier inits visible to the peer CTA
@@ -148,9 +166,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     while (clock64() - t0 < a.stagger) __nanosleep(200);
   }
 
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (both CTAs)
-    {
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");      // the control warpgroup gives registers to the GELU warps
+    if (warp == 0) {
+      // ------------------------------------------------------------ TMA producer (both CTAs)
       const uint32_t x_full_L = mapa_u32(smem_u32(x_full), 0);
       int slot = 0;
       uint32_t wphase = 0, xphase = 0;
@@ -178,12 +197,20 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       };
       for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
         const int m0 = pt * 256 + (int)rank * 128;
-        mbar_wait(x_empty, xphase ^ 1);
+        mbar_wait(x_empty, xphase ^ 1);                       // every GEMM1 of the previous row tile has read x
+        if (Cfg::LN_ALIAS_X) mbar_wait(xs_free, xphase ^ 1);  // ... and its LayerNorm no longer stages through it
         xphase ^= 1;
         if (rank == 0 && elect_one()) mbar_expect_tx(x_full, 2 * Cfg::X_BYTES);
 #pragma unroll
         for (int kb = 0; kb < KB1; ++kb)
           if (elect_one()) tma_load_2d_cg2(sX + kb * 16384, &tmX, x_full_L, kb * 64, m0);
+        // this row tile's residual rows -> L2, long before the LayerNorm warps ask for them (16 rows per lane 0..7)
+        if (lane < 8) {
+          const long long r0 = (long long)m0 + lane * 16;
+          long long nrows = a.M - r0;
+          if (nrows > 16) nrows = 16;
+          if (nrows > 0) prefetch_l2_bulk(a.residual + r0 * C, (uint32_t)(nrows * C * 4));
+        }
         load_w1(0);
         load_w1(1);
         for (int j = 0; j < NCH; ++j) {                       // same order as the MMA issuer consumes
@@ -191,182 +218,158 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (j + 2 < NCH) load_w1(j + 2);
         }
       }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (leader CTA; warp-uniform
-    // control flow, one elected lane issues)
-    if (rank == 0) {
-      constexpr uint32_t idesc1 = make_idesc_bf16(256, NH, 0, 0);
-      constexpr uint32_t idesc2 = make_idesc_f16(256, 192);       // P (TMEM) and W2 (smem) are fp16
-      const uint32_t tHP = tmem_base + Cfg::COL_HP;
-      int yb = 0;                                             // Y accumulator of the current row tile
-      int slot = 0;
-      uint32_t wphase = 0, xphase = 0, yphase = 0, pphase = 0;   // pphase: bit b = phase of p_full[b]
-      auto advance = [&]() { if (++slot == NSLOT) { slot = 0; wphase ^= 1; } };
-      auto issue_g1 = [&](int b) {                            // HP_b = X . W1chunk^T   (K = C)
-        mbar_wait(&w_full[slot], wphase);
-        tcgen05_after_sync();
-        const uint32_t sw = smem_u32(sW + slot * Cfg::SLOT_BYTES);
-#pragma unroll
-        for (int kb = 0; kb < KB1; ++kb) {
-          const uint64_t da = make_desc_k_sw128(smem_u32(sX) + kb * 16384);
-          const uint64_t db = make_desc_k_sw128(sw + kb * 4096);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if ((a.dbg & 4) && k) break;
-            if (elect_one()) umma2_bf16(tHP + b * 64, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
-          }
-        }
-        if (elect_one()) { umma2_commit_mc(&w_empty[slot]); umma2_commit_mc(&h_full[b]); }
-        advance();
-      };
-      for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
-        mbar_wait(x_full, xphase);
-        xphase ^= 1;
-        tcgen05_after_sync();
-        issue_g1(0);
-        issue_g1(1);
-        for (int j = 0; j < NCH; ++j) {
-          const int b = j & 1;
-          mbar_wait(&p_full[b], (pphase >> b) & 1);           // GELU(H_j) written to TMEM by both CTAs
-          pphase ^= 1u << b;
-          const bool tr = (a.dbg & 16) && blockIdx.x == 0 && pt == pair0 + npairs && j < 64 && lane == 0;
-          if (tr) g_mlp_trace[j * 8 + 0] = clock64();
-          if (j == 0) { mbar_wait(&y_empty[yb], ((yphase >> yb) & 1) ^ 1); yphase ^= 1u << yb; }   // this Y buffer drained
+      __syncwarp();
+    } else if (warp == 1) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA; warp-uniform
+      // control flow, one elected lane issues)
+      if (rank == 0) {
+        constexpr uint32_t idesc1 = make_idesc_bf16(256, NH, 0, 0);
+        constexpr uint32_t idesc2 = make_idesc_f16(256, 192);     // P (TMEM) and W2 (smem) are fp16
+        const uint32_t tHP = tmem_base + Cfg::COL_HP;
+        int yb = 0;                                             // Y accumulator of the current row tile
+        int slot = 0;
+        uint32_t wphase = 0, xphase = 0, yphase = 0, pphase = 0;   // pphase: bit b = phase of p_full[b]
+        auto advance = [&]() { if (++slot == NSLOT) { slot = 0; wphase ^= 1; } };
+        auto issue_g1 = [&](int b) {                            // HP_b = X . W1chunk^T   (K = C)
           mbar_wait(&w_full[slot], wphase);
           tcgen05_after_sync();
           const uint32_t sw = smem_u32(sW + slot * Cfg::SLOT_BYTES);
 #pragma unroll
-          for (int h = 0; h < NSPLIT; ++h) {
-            const uint64_t db = make_desc_k_sw128(sw + h * 12288);
+          for (int kb = 0; kb < KB1; ++kb) {
+            const uint64_t da = make_desc_k_sw128(smem_u32(sX) + kb * 16384);
+            const uint64_t db = make_desc_k_sw128(sw + kb * 4096);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)                        // Y += P_j . W2chunk^T ; K-step k lives at columns (k>>1)*32 + (k&1)*8
-              if (!((a.dbg & 8) && k) && elect_one()) umma2_bf16_ts(tmem_base + yb * 192 + h * 192, tHP + b * 64 + (k >> 1) * 32 + (k & 1) * 8, db + 2 * k, idesc2, (j | k) != 0);
+            for (int k = 0; k < 4; ++k) {
+              if ((a.dbg & 4) && k) break;
+              if (elect_one()) umma2_bf16(tHP + b * 64, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+            }
           }
-          if (elect_one()) umma2_commit_mc(&w_empty[slot]);
+          if (elect_one()) { umma2_commit_mc(&w_empty[slot]); umma2_commit_mc(&h_full[b]); }
           advance();
-          if (tr) g_mlp_trace[j * 8 + 1] = clock64();
-          if (j + 2 < NCH) {
-            issue_g1(b);
-            if (tr) g_mlp_trace[j * 8 + 2] = clock64();                                      // H_{j+2} overwrites HP_b after G2(j) (pipe order)
-            if (j + 2 == NCH - 1 && elect_one()) umma2_commit_mc(x_empty);   // last read of the x tile
+        };
+        for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
+          mbar_wait(x_full, xphase);
+          xphase ^= 1;
+          tcgen05_after_sync();
+          issue_g1(0);
+          issue_g1(1);
+          for (int j = 0; j < NCH; ++j) {
+            const int b = j & 1;
+            mbar_wait(&p_full[b], (pphase >> b) & 1);           // GELU(H_j) written to TMEM by both CTAs
+            pphase ^= 1u << b;
+            const bool tr = (a.dbg & 16) && blockIdx.x == 0 && pt == pair0 + npairs && j < 64 && lane == 0;
+            if (tr) g_mlp_trace[j * 8 + 0] = clock64();
+            if (j == 0) { mbar_wait(&y_empty[yb], ((yphase >> yb) & 1) ^ 1); yphase ^= 1u << yb; }   // this Y buffer drained
+            mbar_wait(&w_full[slot], wphase);
+            tcgen05_after_sync();
+            const uint32_t sw = smem_u32(sW + slot * Cfg::SLOT_BYTES);
+#pragma unroll
+            for (int h = 0; h < NSPLIT; ++h) {
+              const uint64_t db = make_desc_k_sw128(sw + h * 12288);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)                        // Y += P_j . W2chunk^T ; K-step k lives at columns (k>>1)*32 + (k&1)*8
+                if (!((a.dbg & 8) && k) && elect_one()) umma2_bf16_ts(tmem_base + yb * 192 + h * 192, tHP + b * 64 + (k >> 1) * 32 + (k & 1) * 8, db + 2 * k, idesc2, (j | k) != 0);
+            }
+            if (elect_one()) umma2_commit_mc(&w_empty[slot]);
+            advance();
+            if (tr) g_mlp_trace[j * 8 + 1] = clock64();
+            if (j + 2 < NCH) {
+              issue_g1(b);
+              if (tr) g_mlp_trace[j * 8 + 2] = clock64();                                      // H_{j+2} overwrites HP_b after G2(j) (pipe order)
+              if (j + 2 == NCH - 1 && elect_one()) umma2_commit_mc(x_empty);   // last read of the x tile
+            }
           }
+          if (elect_one()) umma2_commit_mc(&y_full[yb]);
+          __syncwarp();
+          if (Cfg::NY == 2) yb ^= 1;
         }
-        if (elect_one()) umma2_commit_mc(&y_full[yb]);
-        __syncwarp();
-        if (Cfg::NY == 2) yb ^= 1;
       }
+      __syncwarp();
     }
-    __syncwarp();
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue warps (both CTAs)
+  } else if (warp < kMlpLnWarp0) {
+    // ------------------------------------------------------------ GELU warps (both CTAs): per hidden chunk
+    // H_j (TMEM) -> +b1, GELU (packed fp16) -> P_j (TMEM, over the warp's own columns)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int q = warp & 3, hf = (warp - 4) >> 2;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t y_empty_L0 = mapa_u32(smem_u32(&y_empty[0]), 0), y_empty_L1 = mapa_u32(smem_u32(&y_empty[1]), 0);
     const uint32_t p_full_L0 = mapa_u32(smem_u32(&p_full[0]), 0), p_full_L1 = mapa_u32(smem_u32(&p_full[1]), 0);
-    uint32_t hphase = 0, yphase = 0;                          // bit b = phase of h_full[b] / y_full[b]
+    uint32_t hphase = 0;                                      // bit b = phase of h_full[b]
     uint32_t v[32];
-    using Ln = LnTileEpilogue<C, Cfg::LN_UW, Cfg::LN_D, Cfg::LN_ASYNC, true>;
+    for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
+#pragma unroll 1
+      for (int j = 0; j < NCH; ++j) {
+        const int b = j & 1;
+        float4 bb[8];                                          // b1 of this warp's 32 hidden units: fetched before the wait
+        {
+          const float4* b1 = reinterpret_cast<const float4*>(a.b1 + j * NH + hf * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bb[i] = __ldg(b1 + i);
+        }
+        mbar_wait(&h_full[b], (hphase >> b) & 1);
+        hphase ^= 1u << b;
+        tcgen05_after_sync();
+        const bool tr = (a.dbg & 16) && blockIdx.x == 0 && warp == 4 && lane == 0 && pt == pair0 + npairs && j < 64;
+        if (tr) g_mlp_trace[j * 8 + 4] = clock64();
+        const uint32_t t_own = lane_base + Cfg::COL_HP + b * 64 + hf * 32;   // this warp's 32 columns of H_j
+        tmem_ld_32x32(t_own, v);
+        tmem_ld_wait();
+        if (tr) g_mlp_trace[j * 8 + 5] = clock64();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          pk[2 * i] = gelu_fast_h2(__uint_as_float(v[4 * i]) + bb[i].x, __uint_as_float(v[4 * i + 1]) + bb[i].y);
+          pk[2 * i + 1] = gelu_fast_h2(__uint_as_float(v[4 * i + 2]) + bb[i].z, __uint_as_float(v[4 * i + 3]) + bb[i].w);
+        }
+        if (tr) g_mlp_trace[j * 8 + 6] = clock64();
+        tmem_st_32x16(t_own, pk);                               // P_j over the first 16 of the warp's own columns
+        tmem_st_wait();
+        if (tr) g_mlp_trace[j * 8 + 7] = clock64();
+        tcgen05_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(b ? p_full_L1 : p_full_L0);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ LayerNorm warps (both CTAs): per row tile
+    // Y (TMEM) -> +b2, LayerNorm, + residual -> fp32 + bf16 (tc_ln_epilogue.cuh)
+    const int lw = warp - kMlpLnWarp0;                        // 0..7
+    const int q = warp & 3, hf = lw >> 2;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t y_empty_L0 = mapa_u32(smem_u32(&y_empty[0]), 0), y_empty_L1 = mapa_u32(smem_u32(&y_empty[1]), 0);
+    uint32_t yphase = 0;                                      // bit b = phase of y_full[b]
+    using Ln = LnTileEpilogue<C, Cfg::LN_UW, Cfg::LN_D, true, true, Cfg::LN_NB16, Cfg::LN_NBUF>;
+    static_assert(Ln::NBUF <= 4, "four load barriers per LayerNorm warp");
     Ln ln;
     ln.bias = a.b2; ln.gamma = a.gamma; ln.beta = a.beta; ln.residual = a.residual;
     ln.x_out = a.x_out; ln.xb = a.x_out_bf16; ln.M = a.M; ln.eps = a.eps;
     ln.tm_out = &tmOut; ln.tm_xb = a.x_out_bf16 != nullptr ? &tmXb : nullptr;
-    ln.stg_b = stgb_smem + (warp - 4) * Cfg::STGB_BYTES; ln.sparams = sparams;
-    ln.tm_res = &tmRes; ln.ld_bar = &ln_bar[(warp - 4) * 2];
-    static_assert(Ln::NBUF <= 2, "two load barriers per epilogue warp");
-    ln.stg = epi_smem + (warp - 4) * Cfg::STG_BYTES; ln.ln_part = ln_part; ln.q = q; ln.hf = hf; ln.lane = lane; ln.tile_par = 0;
+    ln.stg = stg_smem + lw * Cfg::STG_BYTES; ln.stg_b = stgb_smem + lw * Cfg::STGB_BYTES; ln.sparams = sparams;
+    ln.tm_res = &tmRes; ln.ld_bar = &ln_bar[lw * 4];
+    ln.ln_part = ln_part; ln.q = q; ln.hf = hf; ln.lane = lane; ln.tile_par = 0;
     const bool ln_store = !(a.dbg & 32);
-
-    // one hidden chunk: H_j (TMEM) -> +b1, GELU (packed fp16) -> P_j (TMEM, over the warp's own columns)
-    auto gelu_chunk = [&](int pt, int j) {
-      const int b = j & 1;
-      float4 bb[8];                                            // b1 of this warp's 32 hidden units: fetched before the wait
-      {
-        const float4* b1 = reinterpret_cast<const float4*>(a.b1 + j * NH + hf * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) bb[i] = __ldg(b1 + i);
+    int yb = 0;
+    uint32_t xe_phase = 0;
+    for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
+      ln.m_base = (long long)pt * 256 + rank * 128 + q * 32;
+      if (Cfg::LN_ALIAS_X) {                                  // the staging tiles are the x tile: wait until every GEMM1 has read it
+        mbar_wait(x_empty, xe_phase);
+        xe_phase ^= 1;
       }
-      mbar_wait(&h_full[b], (hphase >> b) & 1);
-      hphase ^= 1u << b;
-      tcgen05_after_sync();
-      const bool tr = (a.dbg & 16) && blockIdx.x == 0 && warp == 4 && lane == 0 && pt == pair0 + npairs && j < 64;
-      if (tr) g_mlp_trace[j * 8 + 4] = clock64();
-      const uint32_t t_own = lane_base + Cfg::COL_HP + b * 64 + hf * 32;   // this warp's 32 columns of H_j
-      tmem_ld_32x32(t_own, v);
-      tmem_ld_wait();
-      if (tr) g_mlp_trace[j * 8 + 5] = clock64();
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        pk[2 * i] = gelu_fast_h2(__uint_as_float(v[4 * i]) + bb[i].x, __uint_as_float(v[4 * i + 1]) + bb[i].y);
-        pk[2 * i + 1] = gelu_fast_h2(__uint_as_float(v[4 * i + 2]) + bb[i].z, __uint_as_float(v[4 * i + 3]) + bb[i].w);
-      }
-      if (tr) g_mlp_trace[j * 8 + 6] = clock64();
-      tmem_st_32x16(t_own, pk);                               // P_j over the first 16 of the warp's own columns
-      tmem_st_wait();
-      if (tr) g_mlp_trace[j * 8 + 7] = clock64();
-      tcgen05_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(b ? p_full_L1 : p_full_L0);
-    };
-    auto y_wait = [&](int yb) {                               // accumulator yb complete
-      mbar_wait(&y_full[yb], (yphase >> yb) & 1);
+      ln.prefetch();                                          // first residual tiles (L2 hits: pulled in by the producer warp)
+      mbar_wait(&y_full[yb], (yphase >> yb) & 1);             // accumulator yb complete
       yphase ^= 1u << yb;
       tcgen05_after_sync();
-    };
-    auto y_release = [&](int yb) {                            // all TMEM reads of accumulator yb done
-      tcgen05_before_sync();
+      const uint32_t y = lane_base + yb * 192 * (Cfg::NY - 1);
+      ln.stats(y);
+      if (!(a.dbg & 2)) ln.all_units(y, ln_store);
+      tcgen05_before_sync();                                  // all TMEM reads of accumulator yb are done
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(yb ? y_empty_L1 : y_empty_L0);
-    };
-
-    if constexpr (Cfg::NY == 1) {
-      for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
-#pragma unroll 1
-        for (int j = 0; j < NCH; ++j) gelu_chunk(pt, j);
-        // row-tile epilogue: the first residual fetches are issued before the accumulator is even complete
-        ln.m_base = (long long)pt * 256 + rank * 128 + q * 32;
-        ln.prefetch();
-        y_wait(0);
-        ln.stats(lane_base);
-        if (!(a.dbg & 2)) ln.all_units(lane_base, ln_store);
-        y_release(0);
+      if (Cfg::LN_ALIAS_X) {                                  // hand the x tile back once the bulk stores have read the staging tiles
+        if (lane == 0) { tma_store_wait_read(); mbar_arrive(xs_free); }
+        __syncwarp();
       }
-    } else {
-      // two accumulators: the LayerNorm units of the PREVIOUS row tile run between the hidden chunks of the
-      // current one (NCH = 12 chunks, NU = 3 units of 32 columns per warp: one unit after every fourth chunk)
-      static_assert(Cfg::NY == 1 || (NCH == 12 && Ln::NU == 3 && Cfg::LN_D == 1), "interleave schedule assumes C = 192");
-      int yb = 0;
-      bool pending = false;                                   // ln.* describes a finished tile in accumulator yb ^ 1
-      for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
-        const uint32_t y_prev = lane_base + (yb ^ 1) * 192;
-        gelu_chunk(pt, 0);
-        if (pending) { y_wait(yb ^ 1); ln.stats(y_prev); }
-#pragma unroll 1
-        for (int jb = 0; jb < NCH; jb += 4) {
-          if (jb) gelu_chunk(pt, jb);
-          gelu_chunk(pt, jb + 1);
-          gelu_chunk(pt, jb + 2);
-          gelu_chunk(pt, jb + 3);
-          if (pending) {
-            ln.dbg = ((a.dbg & 16) && blockIdx.x == 0 && warp == 4 && lane == 0 && pt == pair0 + npairs) ? g_mlp_trace + 400 + (jb / 4) * 8 : nullptr;
-            ln.template unit<0>(y_prev, jb / 4, ln_store);
-          }
-        }
-        if (pending) y_release(yb ^ 1);
-        ln.m_base = (long long)pt * 256 + rank * 128 + q * 32;   // this tile becomes the pending one
-        ln.prefetch();
-        pending = true;
-        yb ^= 1;
-      }
-      if (pending) {                                          // drain the last row tile
-        const uint32_t y_prev = lane_base + (yb ^ 1) * 192;
-        y_wait(yb ^ 1);
-        ln.stats(y_prev);
-        ln.all_units(y_prev, ln_store);
-        y_release(yb ^ 1);
-      }
+      if (Cfg::NY == 2) yb ^= 1;
     }
     ln.drain_stores();
   }
@@ -394,7 +397,7 @@ static int launch_mlp_t(const void* x, const void* w1, const void* w2, MlpArgs& 
   }
   CUtensorMap tmRes = tmOut;
   if (a.residual != nullptr && !encode_tmap_2d(&tmRes, 0, a.residual, C, (uint64_t)a.M, (uint64_t)C * 4, UW, 32, UW * 4)) return PANGU_ERR_CUDA;
-  if (a.residual == nullptr && Cfg::LN_ASYNC) { set_error("mlp_fused<%d>: a residual tensor is required", C); return PANGU_ERR_BAD_ARG; }
+  if (a.residual == nullptr) { set_error("mlp_fused<%d>: a residual tensor is required", C); return PANGU_ERR_BAD_ARG; }
   a.pair_tiles = (int)((a.M + 255) / 256);
   auto kern = mlp_fused_kernel<C>;
   static unsigned long long configured = 0;

@@ -210,11 +210,11 @@ class _Worker:
         if o_first is not None:                          # rows 0..2 of this band were computed by the northern neighbour
             hr, W = self.plan.nrows(stage), TOK_W[stage]
             self.o.view(Z, hr, W, self.o.shape[-1])[:, :3].copy_(o_first.view(Z, 3, W, self.o.shape[-1]))
-        x1, x1b = ops.linear_ln_residual_bf16(self.o, wc.bf16("a2", PF.W(att.linear2)), PF._f(PF.B(att.linear2)),
+        x1, x1b = ops.linear_ln_residual_bf16(self.o, wc.bf16("a2", PF.lin_w(att.linear2)), PF._f(PF.lin_b(att.linear2)),
                                               PF._f(blk.norm1.weight), PF._f(blk.norm1.bias), self.x, eps=blk.norm1.eps)
         self.o = self.halo_o = None
-        self.x, self.xb = ops.mlp_ln_residual_bf16(x1b, wc.bf16("m1", PF.W(mlp.linear1)), PF._f(PF.B(mlp.linear1)),
-                                                   wc.f16("m2h", PF.W(mlp.linear2)), PF._f(PF.B(mlp.linear2)),
+        self.x, self.xb = ops.mlp_ln_residual_bf16(x1b, wc.bf16("m1", PF.lin_w(mlp.linear1)), PF._f(PF.lin_b(mlp.linear1)),
+                                                   wc.f16("m2h", PF.lin_w(mlp.linear2)), PF._f(PF.lin_b(mlp.linear2)),
                                                    PF._f(blk.norm2.weight), PF._f(blk.norm2.bias), x1, eps=blk.norm2.eps)
 
 

@@ -132,11 +132,11 @@ def norm_wb(mod, who="norm"):
     return mod.weight, mod.bias
 
 
-def W(mod):
+def lin_w(mod):
     return lin_wb(mod)[0]
 
 
-def B(mod):
+def lin_b(mod):
     return lin_wb(mod)[1]
 
 
@@ -161,7 +161,7 @@ def attention_operands(att, wc):
         b[:C] *= qs
         return b.contiguous()
 
-    return (wc.derived("a1s", (W(att.linear1),), scaled_w), wc.derived("b1s", (B(att.linear1),), scaled_b),
+    return (wc.derived("a1s", (lin_w(att.linear1),), scaled_w), wc.derived("b1s", (lin_b(att.linear1),), scaled_b),
             wc.derived("ebs", (att.earth_specific_bias,), lambda e: (e[0].float() * LOG2E).to(torch.bfloat16).contiguous()))
 
 
@@ -194,13 +194,13 @@ def block_forward(blk, x, Z, H, W, roll, mode, xb=None, s1=1.0, s2=1.0):
     if (s1 != 1.0 or s2 != 1.0) and mode != "bf16":
         raise PanguError("stochastic depth (training) runs in compute_dtype='bf16' only")
     if mode == "fp32":
-        qkv = ops.linear(x, _w2d(W(att.linear1)), _f(B(att.linear1)))
-        o = ops.window_attention(qkv, _f(B(att.linear1)), _f(att.earth_specific_bias), Z, H, W, heads, rmode)
+        qkv = ops.linear(x, _w2d(lin_w(att.linear1)), _f(lin_b(att.linear1)))
+        o = ops.window_attention(qkv, _f(lin_b(att.linear1)), _f(att.earth_specific_bias), Z, H, W, heads, rmode)
         del qkv
-        y = ops.linear(o, _w2d(W(att.linear2)), _f(B(att.linear2)))
+        y = ops.linear(o, _w2d(lin_w(att.linear2)), _f(lin_b(att.linear2)))
         x1, _ = ops.ln_residual(y, _f(norm_wb(blk.norm1)[0]), _f(norm_wb(blk.norm1)[1]), residual=x, eps=blk.norm1.eps)
-        h = ops.linear(x1, _w2d(W(mlp.linear1)), _f(B(mlp.linear1)), act=ACT_GELU)
-        y = ops.linear(h, _w2d(W(mlp.linear2)), _f(B(mlp.linear2)))
+        h = ops.linear(x1, _w2d(lin_w(mlp.linear1)), _f(lin_b(mlp.linear1)), act=ACT_GELU)
+        y = ops.linear(h, _w2d(lin_w(mlp.linear2)), _f(lin_b(mlp.linear2)))
         del h
         x2, _ = ops.ln_residual(y, _f(norm_wb(blk.norm2)[0]), _f(norm_wb(blk.norm2)[1]), residual=x1, eps=blk.norm2.eps)
         return x2, None
@@ -214,7 +214,7 @@ def block_forward(blk, x, Z, H, W, roll, mode, xb=None, s1=1.0, s2=1.0):
                                          prescaled=True)
         del qkv
         g1, b1 = _affine(blk.norm1, s1)
-        x1, x1b = ops.linear_ln_residual_bf16(o, wc.bf16("a2", W(att.linear2)), _f(B(att.linear2)), g1, b1, x,
+        x1, x1b = ops.linear_ln_residual_bf16(o, wc.bf16("a2", lin_w(att.linear2)), _f(lin_b(att.linear2)), g1, b1, x,
                                               eps=blk.norm1.eps)
         del o
     else:
@@ -223,12 +223,12 @@ def block_forward(blk, x, Z, H, W, roll, mode, xb=None, s1=1.0, s2=1.0):
         return x1, x1b
     g2, b2 = _affine(blk.norm2, s2)
     if FUSED_MLP:
-        x2, x2b = ops.mlp_ln_residual_bf16(x1b, wc.bf16("m1", W(mlp.linear1)), _f(B(mlp.linear1)),
-                                           wc.f16("m2h", W(mlp.linear2)), _f(B(mlp.linear2)), g2, b2, x1,
+        x2, x2b = ops.mlp_ln_residual_bf16(x1b, wc.bf16("m1", lin_w(mlp.linear1)), _f(lin_b(mlp.linear1)),
+                                           wc.f16("m2h", lin_w(mlp.linear2)), _f(lin_b(mlp.linear2)), g2, b2, x1,
                                            eps=blk.norm2.eps)
         return x2, x2b
-    h = ops.linear(x1b, wc.bf16("m1", W(mlp.linear1)), _f(B(mlp.linear1)), act=ACT_GELU)
-    x2, x2b = ops.linear_ln_residual_bf16(h, wc.bf16("m2", W(mlp.linear2)), _f(B(mlp.linear2)), g2, b2, x1,
+    h = ops.linear(x1b, wc.bf16("m1", lin_w(mlp.linear1)), _f(lin_b(mlp.linear1)), act=ACT_GELU)
+    x2, x2b = ops.linear_ln_residual_bf16(h, wc.bf16("m2", lin_w(mlp.linear2)), _f(lin_b(mlp.linear2)), g2, b2, x1,
                                           eps=blk.norm2.eps)
     return x2, x2b
 
@@ -250,25 +250,25 @@ def attention_windows_forward(att, xw, mask, mode):
     Zf, Hf, Wf = 2, 6 * T - 5, 12 * nLon
     flat = xw.reshape(nLon * T * L, C)
     if mode == "fp32":
-        qkv = ops.linear(flat.contiguous(), _w2d(W(att.linear1)), _f(B(att.linear1)))
-        o = ops.window_attention(qkv, _f(B(att.linear1)), bias, Zf, Hf, Wf, heads, WINDOWED)
-        y = ops.linear(o, _w2d(W(att.linear2)), _f(B(att.linear2)))
+        qkv = ops.linear(flat.contiguous(), _w2d(lin_w(att.linear1)), _f(lin_b(att.linear1)))
+        o = ops.window_attention(qkv, _f(lin_b(att.linear1)), bias, Zf, Hf, Wf, heads, WINDOWED)
+        y = ops.linear(o, _w2d(lin_w(att.linear2)), _f(lin_b(att.linear2)))
     else:
         wc = att._wcache
-        qkv = ops.linear(ops.cast_bf16(flat.contiguous()), wc.bf16("a1", W(att.linear1)), _f(B(att.linear1)))
-        o = ops.window_attention(qkv, _f(B(att.linear1)), bias.to(torch.bfloat16), Zf, Hf, Wf, heads, WINDOWED)
-        y = ops.linear(o, wc.bf16("a2", W(att.linear2)), _f(B(att.linear2)), out_dtype=torch.float32)
+        qkv = ops.linear(ops.cast_bf16(flat.contiguous()), wc.bf16("a1", lin_w(att.linear1)), _f(lin_b(att.linear1)))
+        o = ops.window_attention(qkv, _f(lin_b(att.linear1)), bias.to(torch.bfloat16), Zf, Hf, Wf, heads, WINDOWED)
+        y = ops.linear(o, wc.bf16("a2", lin_w(att.linear2)), _f(lin_b(att.linear2)), out_dtype=torch.float32)
     return y.reshape(nLon, T, L, C)
 
 
 def mlp_forward(mlp, x2d, mode):
     """Mlp.forward (models/layers.py:311-317) on [M, C]."""
     if mode == "fp32":
-        h = ops.linear(x2d, _w2d(W(mlp.linear1)), _f(B(mlp.linear1)), act=ACT_GELU)
-        return ops.linear(h, _w2d(W(mlp.linear2)), _f(B(mlp.linear2)))
+        h = ops.linear(x2d, _w2d(lin_w(mlp.linear1)), _f(lin_b(mlp.linear1)), act=ACT_GELU)
+        return ops.linear(h, _w2d(lin_w(mlp.linear2)), _f(lin_b(mlp.linear2)))
     wc = mlp._wcache
-    h = ops.linear(ops.cast_bf16(x2d), wc.bf16("m1", W(mlp.linear1)), _f(B(mlp.linear1)), act=ACT_GELU)
-    return ops.linear(h, wc.bf16("m2", W(mlp.linear2)), _f(B(mlp.linear2)), out_dtype=torch.float32)
+    h = ops.linear(ops.cast_bf16(x2d), wc.bf16("m1", lin_w(mlp.linear1)), _f(lin_b(mlp.linear1)), act=ACT_GELU)
+    return ops.linear(h, wc.bf16("m2", lin_w(mlp.linear2)), _f(lin_b(mlp.linear2)), out_dtype=torch.float32)
 
 
 def patch_embed_forward(pe, inp, inp_s, statistics, maps, const_h, mode):
@@ -279,13 +279,13 @@ def patch_embed_forward(pe, inp, inp_s, statistics, maps, const_h, mode):
     ns = ps.shape[0]                                     # token rows * 360 (181 * 360 for the full grid)
     x = torch.empty((8 * ns, dim), dtype=torch.float32, device=inp.device)
     if mode == "fp32":
-        ops.linear(ps, _w2d(W(pe.conv_surface)), _f(B(pe.conv_surface)), out=x[:ns])
-        ops.linear(pu, _w2d(W(pe.conv)), _f(B(pe.conv)), out=x[ns:])
+        ops.linear(ps, _w2d(lin_w(pe.conv_surface)), _f(lin_b(pe.conv_surface)), out=x[:ns])
+        ops.linear(pu, _w2d(lin_w(pe.conv)), _f(lin_b(pe.conv)), out=x[ns:])
         return x, None
     wc = pe._wcache
     xb = torch.empty((8 * ns, dim), dtype=torch.bfloat16, device=inp.device)      # bf16 shadow written by the GEMMs
-    ops.linear_ex(ps, wc.bf16("cs", W(pe.conv_surface)), _f(B(pe.conv_surface)), out=x[:ns], shadow=xb[:ns])
-    ops.linear_ex(pu, wc.bf16("c", W(pe.conv)), _f(B(pe.conv)), out=x[ns:], shadow=xb[ns:])
+    ops.linear_ex(ps, wc.bf16("cs", lin_w(pe.conv_surface)), _f(lin_b(pe.conv_surface)), out=x[:ns], shadow=xb[:ns])
+    ops.linear_ex(pu, wc.bf16("c", lin_w(pe.conv)), _f(lin_b(pe.conv)), out=x[ns:], shadow=xb[ns:])
     return x, xb
 
 
@@ -293,23 +293,23 @@ def downsample_forward(ds, x, Z, H, W, mode):
     """DownSample.forward (models/layers.py:497-524) -> ([N/4.., 2C] fp32, bf16|None)."""
     if mode == "fp32":
         m = ops.downsample_merge_ln(x, _f(norm_wb(ds.norm)[0]), _f(norm_wb(ds.norm)[1]), Z, H, W, torch.float32, ds.norm.eps)
-        return ops.linear(m, _w2d(W(ds.linear)), None), None
+        return ops.linear(m, _w2d(lin_w(ds.linear)), None), None
     m = ops.downsample_merge_ln(x, _f(norm_wb(ds.norm)[0]), _f(norm_wb(ds.norm)[1]), Z, H, W, torch.bfloat16, ds.norm.eps)
-    return ops.linear_ex(m, ds._wcache.bf16("l", W(ds.linear)), None, want_shadow=True)
+    return ops.linear_ex(m, ds._wcache.bf16("l", lin_w(ds.linear)), None, want_shadow=True)
 
 
 def upsample_forward(us, x, mode, xb=None, Z=8, H2=91, W2=180, H=181):
     """UpSample.forward (models/layers.py:540-567; sizes hard-coded there)."""
     if mode == "fp32":
-        y = ops.linear(x, _w2d(W(us.linear1)), None)
+        y = ops.linear(x, _w2d(lin_w(us.linear1)), None)
         n = ops.upsample_shuffle_ln(y, _f(norm_wb(us.norm)[0]), _f(norm_wb(us.norm)[1]), Z, H2, W2, H, torch.float32, us.norm.eps)
-        return ops.linear(n, _w2d(W(us.linear2)), None), None
+        return ops.linear(n, _w2d(lin_w(us.linear2)), None), None
     wc = us._wcache
     if xb is None:
         xb = ops.cast_bf16(x)
-    y = ops.linear(xb, wc.bf16("l1", W(us.linear1)), None)
+    y = ops.linear(xb, wc.bf16("l1", lin_w(us.linear1)), None)
     n = ops.upsample_shuffle_ln(y, _f(norm_wb(us.norm)[0]), _f(norm_wb(us.norm)[1]), Z, H2, W2, H, torch.bfloat16, us.norm.eps)
-    return ops.linear_ex(n, wc.bf16("l2", W(us.linear2)), None, want_shadow=True)
+    return ops.linear_ex(n, wc.bf16("l2", lin_w(us.linear2)), None, want_shadow=True)
 
 
 def patch_recover_forward(pr, x, Z, H, W, mode, skip=None, lat=721, denorm=None, xb=None, skip_b=None):
@@ -322,16 +322,16 @@ def patch_recover_forward(pr, x, Z, H, W, mode, skip=None, lat=721, denorm=None,
     if mode == "fp32":
         if skip is not None:
             x = torch.cat((skip, x), dim=-1)
-        yu = ops.linear(x[ns:], _w2d(W(pr.conv)), _f(B(pr.conv)))
-        ys = ops.linear(x[:ns], _w2d(W(pr.conv_surface)), _f(B(pr.conv_surface)))
+        yu = ops.linear(x[ns:], _w2d(lin_w(pr.conv)), _f(lin_b(pr.conv)))
+        ys = ops.linear(x[:ns], _w2d(lin_w(pr.conv_surface)), _f(lin_b(pr.conv_surface)))
         return ops.patch_recover_scatter(yu, ys, lat, denorm)
     wc = pr._wcache
     if skip is not None and xb is not None and skip_b is not None:
         # the skip concat (models/pangu_model.py:98) is read by the GEMMs from the two bf16 shadows directly
-        yu = ops.linear_ex(skip_b[ns:], wc.bf16("c", W(pr.conv)), _f(B(pr.conv)), a2=xb[ns:])
-        ys = ops.linear_ex(skip_b[:ns], wc.bf16("cs", W(pr.conv_surface)), _f(B(pr.conv_surface)), a2=xb[:ns])
+        yu = ops.linear_ex(skip_b[ns:], wc.bf16("c", lin_w(pr.conv)), _f(lin_b(pr.conv)), a2=xb[ns:])
+        ys = ops.linear_ex(skip_b[:ns], wc.bf16("cs", lin_w(pr.conv_surface)), _f(lin_b(pr.conv_surface)), a2=xb[:ns])
         return ops.patch_recover_scatter(yu, ys, lat, denorm)
     xb = ops.concat_cast_bf16(skip, x) if skip is not None else ops.cast_bf16(x)
-    yu = ops.linear(xb[ns:], wc.bf16("c", W(pr.conv)), _f(B(pr.conv)), out_dtype=torch.float32)
-    ys = ops.linear(xb[:ns], wc.bf16("cs", W(pr.conv_surface)), _f(B(pr.conv_surface)), out_dtype=torch.float32)
+    yu = ops.linear(xb[ns:], wc.bf16("c", lin_w(pr.conv)), _f(lin_b(pr.conv)), out_dtype=torch.float32)
+    ys = ops.linear(xb[:ns], wc.bf16("cs", lin_w(pr.conv_surface)), _f(lin_b(pr.conv_surface)), out_dtype=torch.float32)
     return ops.patch_recover_scatter(yu, ys, lat, denorm)

@@ -151,6 +151,8 @@ def test_batched_input_is_a_loop_over_samples(L):
     assert y2.shape == x.shape
     assert torch.equal(y2[0], y0[0]) and torch.equal(y2[1], y1[0])
     mlp = blk.linear
-    with torch.no_grad():
+    with torch.no_grad():                                      # stand-alone Mlp is forward-only (it raises when a graph is wanted)
         m2 = mlp(x[:, :4096])
-    assert torch.equal(m2[1], mlp(x[1:2, :4096])[0])
+        assert torch.equal(m2[1], mlp(x[1:2, :4096])[0])
+    with pytest.raises(L.PanguError):
+        mlp(x[1:2, :4096])

@@ -2,8 +2,8 @@
 UNMODIFIED reference chained 7 times on the CPU (tests/golden/reference_rollout_goldens.npz, written by
 make_rollout_golden.py: best_model(...) then normBackData fed back, inference/inference_mix_multiOutput.py:201-238).
 
-fp32 mode must stay within 1e-4 rel-L2 at every one of the 7 steps; bf16 mode must start inside north_star's 2e-2 and its
-growth curve is printed and bounded (the chain feeds each step's rounding back through a random-init network)."""
+fp32 mode must stay within 1e-4 rel-L2 at every one of the 7 steps (measured 4.9e-7 ... 5.9e-7); bf16 mode within
+north_star's 2e-2 at every step; the growth curve is printed (measured: flat, 3.0e-3 -> 3.7e-3)."""
 import os
 
 import numpy as np
@@ -16,7 +16,7 @@ from util_gpu import check_digest
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-BF16_STEP_TOL = (2e-2, 3e-2, 4e-2, 5e-2, 6e-2, 7e-2, 8e-2)       # step 1 is north_star's bound; later steps: bounded growth
+BF16_STEP_TOL = (2e-2,) * 7       # north_star's bf16 bound at EVERY lead time (measured 3.0e-3 at step 1 -> 3.7e-3 / 4.1e-3 at step 7)
 
 
 @pytest.fixture(scope="module")
