@@ -507,7 +507,12 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       if (trc && warp == 0) g_attn_trace[13] = clock64();
     }
     const int i_end = min(nwin, (u0 + ts + 1) * g.nLon - p0);    // windows [.., i_end) lie in tile u0 + ts
-    float bmax = -INFINITY;                                   // maximum of my part of this tile's bias row (incl. mask)
+    bool masked_tile = false;                                 // this tile's window type carries the shift mask (layers.py:187-216)
+    if (roll == 1) {
+      const int tt = tile_type(g, bd, u0 + ts), tzw = tt / g.nH;
+      masked_tile = tzw == g.nZ - 1 || tt - tzw * g.nH == g.nH - 1;
+    }
+    float bmax = -INFINITY;                                   // maximum of my part of this tile's bias row
     if (i < i_end) {
 #pragma unroll
       for (int c = 0; c < 10; ++c) {
@@ -538,9 +543,32 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
         // ---- pass 1: an UPPER BOUND of the row maximum of S + bias over my keys: max(S) + max(bias).  Softmax is
         // invariant under the shift, and bf16 P / fp32 sums keep their relative precision over the whole exponent range,
         // so any bound within ~100 (log2 units) of the true maximum gives the same result; this one is off by at most
-        // the spread of the bias row (the -100 of a masked key only makes the bound looser by the spread of S).  It
-        // saves the bias reads and adds of a full pass.
+        // the spread of the bias row.  It saves the bias reads and adds of a full pass.
+        // NOT on masked window types (r2, found by tests/test_gpu_stress.py): there the folded -100 makes the "spread"
+        // 144 log2 units -- when a MASKED key carries the largest score of the row by more than ~126, every exponent
+        // underflows, the row sum is 0 and the output NaN (the reference, with the true maximum, lets the masked key win
+        // because -100 is finite).  Those tiles (28 % of them) take the exact maximum of S + bias below.
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        if (masked_tile) {
+#pragma unroll
+          for (int c = 0; c < 5; ++c) {
+            if (c < nchunk) {
+              uint32_t v[16];
+              tc::tmem_ld_32x16(tS + 16 * c, v);
+              const uint4 b0 = lds128(brow + 32 * c), b1 = lds128(brow + 32 * c + 16);
+              const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              tmem_ld_wait16(v);
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) {
+                float s0 = __uint_as_float(v[2 * e]), s1 = __uint_as_float(v[2 * e + 1]);
+                float s2 = __uint_as_float(v[2 * e + 2]), s3 = __uint_as_float(v[2 * e + 3]);
+                add_bias2(bw[e], s0, s1);
+                add_bias2(bw[e + 1], s2, s3);
+                mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1); mx2 = fmaxf(mx2, s2); mx3 = fmaxf(mx3, s3);
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
@@ -566,7 +594,8 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
             mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
           }
         }
-        mx0 = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) + bmax;
+        }
+        mx0 = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) + (masked_tile ? 0.f : bmax);
         m = mx0;
         sts_f32(exm + (hf * 128 + row) * 4, m);
       }

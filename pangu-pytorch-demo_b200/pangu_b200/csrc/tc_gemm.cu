@@ -40,19 +40,21 @@ struct GemmArgs {
   float* x_out;
   __nv_bfloat16* x_out_bf16;
   float eps;
+  int ln_prefetch;              // $PANGU_GEMM_LN_PREFETCH=1 (experiment): pull the next row tile's residual rows into L2
 };
 
 constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter, interleaved 32-column chunks
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int kStageEpiBytes = 4096;         // per epilogue warp: 32 rows x 128 B staging tile
 
-// LayerNorm epilogue configuration (tc_ln_epilogue.cuh): residual tiles arrive by TMA (the rows were pulled into L2 one
-// row tile ahead), 2 bf16 staging tiles so that the bulk stores of one unit drain while the next is computed;
-// 32-column units at C = 192, 16-column units at C = 384 (shared memory is tighter there).
+// LayerNorm epilogue configuration (tc_ln_epilogue.cuh): 32-column units with 2 residual tiles in flight at
+// C = 192, 16-column units with 3 in flight at C = 384 (shared memory is tighter there).  (r2 experiment: 2 bf16 staging
+// tiles + fewer tiles in flight + the next row tile's residual prefetched into L2 was SLOWER, 1.54 -> 1.77 ms per step at
+// C = 384: this kernel is HBM-bound and wants bytes in flight, not shorter store waits.)
 template <int BN> struct LnCfg {
   static constexpr int UW = BN == 192 ? 32 : 16;
-  static constexpr int D = BN == 192 ? 1 : 2;                 // residual tiles in flight per warp
-  static constexpr int NB16 = 2;
+  static constexpr int D = BN == 192 ? 2 : 3;                 // residual tiles in flight per warp
+  static constexpr int NB16 = 1;
   static constexpr int NBUF = D + NB16;
   static constexpr int STG = UW * 128 * NBUF;                 // fp32 staging tiles per warp
   static constexpr int STGB = UW * 64 * NB16;                 // bf16 staging tiles per warp
@@ -210,7 +212,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ln.m_base = m_base; ln.prefetch();                           // residual tiles fly while the MMAs finish
         // the residual rows of this CTA's NEXT row tile -> L2 (16 rows per warp), so that its tile loads are L2 hits
         const int nxt = tile + gridDim.x;
-        if (nxt < num_tiles && lane == 0) {
+        if (a.ln_prefetch && nxt < num_tiles && lane == 0) {
           const long long r0 = (long long)(nxt / a.n_tiles) * BM + q * 32 + hf * 16;
           long long nrows = a.M - r0;
           if (nrows > 16) nrows = 16;
@@ -491,6 +493,8 @@ int launch_tc_linear_ln(const void* A, long long lda, const void* W, const float
   tc::GemmArgs a{};
   a.M = M; a.K = K; a.N = C; a.bias = bias; a.gamma = gamma; a.beta = beta; a.residual = residual;
   a.x_out = x_out; a.x_out_bf16 = reinterpret_cast<__nv_bfloat16*>(x_out_bf16); a.eps = eps;
+  static const int ln_pf = []() { const char* e = getenv("PANGU_GEMM_LN_PREFETCH"); return e ? atoi(e) : 0; }();
+  a.ln_prefetch = ln_pf;
   if (C == 192) return tc::launch_gemm_t<192, true>(A, lda, W, a, st);
   if (C == 384) return tc::launch_gemm_t<384, true>(A, lda, W, a, st);
   set_error("linear_ln(bf16): C=%d unsupported (192/384)", C);

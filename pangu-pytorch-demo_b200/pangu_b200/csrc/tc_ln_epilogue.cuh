@@ -237,7 +237,10 @@ struct LnTileEpilogue {
   __device__ __forceinline__ void all_units(uint32_t y, bool store = true) {
     if constexpr (ASYNC) {
 #pragma unroll 1
-      for (int idx = 0; idx < NU; ++idx) unit<0>(y, idx, store);
+      for (int idx = 0; idx < NU; ++idx) {
+        unit<0>(y, idx, store);
+        if (dbg) dbg += 8;                             // bring-up: 8 stamps per unit
+      }
       return;
     }
 #pragma unroll 1

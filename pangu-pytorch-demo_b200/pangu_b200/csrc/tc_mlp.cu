@@ -200,12 +200,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         mbar_wait(x_empty, xphase ^ 1);                       // every GEMM1 of the previous row tile has read x
         if (Cfg::LN_ALIAS_X) mbar_wait(xs_free, xphase ^ 1);  // ... and its LayerNorm no longer stages through it
         xphase ^= 1;
+        if ((a.dbg & 16) && blockIdx.x == 0 && lane == 0) { const int n = (pt - pair0) / npairs; if (n >= 1 && n <= 2) g_mlp_trace[256 + n * 16 + 0] = clock64(); }
         if (rank == 0 && elect_one()) mbar_expect_tx(x_full, 2 * Cfg::X_BYTES);
 #pragma unroll
         for (int kb = 0; kb < KB1; ++kb)
           if (elect_one()) tma_load_2d_cg2(sX + kb * 16384, &tmX, x_full_L, kb * 64, m0);
         // this row tile's residual rows -> L2, long before the LayerNorm warps ask for them (16 rows per lane 0..7)
-        if (lane < 8) {
+        if (lane < 8 && !(a.dbg & 64)) {
           const long long r0 = (long long)m0 + lane * 16;
           long long nrows = a.M - r0;
           if (nrows > 16) nrows = 16;
@@ -251,6 +252,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_wait(x_full, xphase);
           xphase ^= 1;
           tcgen05_after_sync();
+          const int tn = (pt - pair0) / npairs;
+          const bool trt = (a.dbg & 16) && blockIdx.x == 0 && lane == 0 && tn >= 1 && tn <= 2;
+          if (trt) g_mlp_trace[256 + tn * 16 + 1] = clock64();
           issue_g1(0);
           issue_g1(1);
           for (int j = 0; j < NCH; ++j) {
@@ -259,7 +263,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             pphase ^= 1u << b;
             const bool tr = (a.dbg & 16) && blockIdx.x == 0 && pt == pair0 + npairs && j < 64 && lane == 0;
             if (tr) g_mlp_trace[j * 8 + 0] = clock64();
-            if (j == 0) { mbar_wait(&y_empty[yb], ((yphase >> yb) & 1) ^ 1); yphase ^= 1u << yb; }   // this Y buffer drained
+            if (j == 0) { mbar_wait(&y_empty[yb], ((yphase >> yb) & 1) ^ 1); yphase ^= 1u << yb; if (trt) g_mlp_trace[256 + tn * 16 + 2] = clock64(); }   // this Y buffer drained
             mbar_wait(&w_full[slot], wphase);
             tcgen05_after_sync();
             const uint32_t sw = smem_u32(sW + slot * Cfg::SLOT_BYTES);
@@ -280,6 +284,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             }
           }
           if (elect_one()) umma2_commit_mc(&y_full[yb]);
+          if (trt) g_mlp_trace[256 + tn * 16 + 3] = clock64();
           __syncwarp();
           if (Cfg::NY == 2) yb ^= 1;
         }
@@ -309,6 +314,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         hphase ^= 1u << b;
         tcgen05_after_sync();
         const bool tr = (a.dbg & 16) && blockIdx.x == 0 && warp == 4 && lane == 0 && pt == pair0 + npairs && j < 64;
+        if ((a.dbg & 16) && blockIdx.x == 0 && warp == 4 && lane == 0 && (j == 0 || j == NCH - 1)) {
+          const int tn = (pt - pair0) / npairs;
+          if (tn >= 1 && tn <= 2) g_mlp_trace[256 + tn * 16 + (j == 0 ? 9 : 10)] = clock64();
+        }
         if (tr) g_mlp_trace[j * 8 + 4] = clock64();
         const uint32_t t_own = lane_base + Cfg::COL_HP + b * 64 + hf * 32;   // this warp's 32 columns of H_j
         tmem_ld_32x32(t_own, v);
@@ -351,22 +360,31 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint32_t xe_phase = 0;
     for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
       ln.m_base = (long long)pt * 256 + rank * 128 + q * 32;
+      const int tn = (pt - pair0) / npairs;
+      const bool trl = (a.dbg & 16) && blockIdx.x == 0 && lw == 0 && lane == 0 && tn >= 1 && tn <= 2;
       if (Cfg::LN_ALIAS_X) {                                  // the staging tiles are the x tile: wait until every GEMM1 has read it
         mbar_wait(x_empty, xe_phase);
         xe_phase ^= 1;
       }
+      if (trl) g_mlp_trace[256 + tn * 16 + 4] = clock64();
       ln.prefetch();                                          // first residual tiles (L2 hits: pulled in by the producer warp)
       mbar_wait(&y_full[yb], (yphase >> yb) & 1);             // accumulator yb complete
       yphase ^= 1u << yb;
       tcgen05_after_sync();
+      if (trl) g_mlp_trace[256 + tn * 16 + 5] = clock64();
       const uint32_t y = lane_base + yb * 192 * (Cfg::NY - 1);
       ln.stats(y);
+      if (trl) g_mlp_trace[256 + tn * 16 + 6] = clock64();
+      ln.dbg = (trl && tn == 1) ? g_mlp_trace + 400 : nullptr;            // per-unit stamps of LN warp 0, row tile 1
       if (!(a.dbg & 2)) ln.all_units(y, ln_store);
+      ln.dbg = nullptr;
+      if (trl) g_mlp_trace[256 + tn * 16 + 7] = clock64();
       tcgen05_before_sync();                                  // all TMEM reads of accumulator yb are done
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(yb ? y_empty_L1 : y_empty_L0);
       if (Cfg::LN_ALIAS_X) {                                  // hand the x tile back once the bulk stores have read the staging tiles
         if (lane == 0) { tma_store_wait_read(); mbar_arrive(xs_free); }
+        if (trl) g_mlp_trace[256 + tn * 16 + 8] = clock64();
         __syncwarp();
       }
       if (Cfg::NY == 2) yb ^= 1;

@@ -11,7 +11,7 @@ os.environ["PANGU_MLP_DBG"] = str(16 | int(os.environ.get("PANGU_MLP_DBG", "0"))
 from pangu_b200 import abi, ops  # noqa: E402
 
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 384
-M = 148 * 128 * 2
+M = 148 * 128 * 4
 g = torch.Generator(device="cuda").manual_seed(0)
 xb = torch.randn(M, C, device="cuda", generator=g).bfloat16()
 x = torch.randn(M, C, device="cuda", generator=g)
@@ -31,8 +31,19 @@ for j in range(nch):
     r = [buf[j * 8 + k] - t0 if buf[j * 8 + k] else -1 for k in range(8)]
     print(f"{j:3d}   | {r[0]:8d} {r[1]:8d} {r[2]:8d} | {r[4]:8d} {r[5]:8d} {r[6]:8d} {r[7]:8d}")
 
-if C == 192:
-    print("LN units (interleaved): stamps = start, tile landed, prefetch issued, tmem loaded, math done, staged, fenced, stores issued")
-    for u in range(3):
-        r = [buf[400 + u * 8 + k] - t0 for k in (0, 1, 2, 3, 6, 7, 4, 5)]
-        print(f"  unit {u}: " + " ".join(f"{x:8d}" for x in r))
+print("tile-level events of CTA 0, row tiles 1 and 2 (cycles since tile 1's x load was issued):")
+names = ["x load issued", "x_full passed (MMA)", "y_empty passed (MMA)", "y_full committed (MMA issue)", "LN: x_empty passed", "LN: y_full passed",
+         "LN: stats done", "LN: units done", "LN: stores read, xs_free", "GELU: first h_full", "GELU: last h_full"]
+base = buf[256 + 16]
+for n in (1, 2):
+    for k, nm in enumerate(names):
+        v = buf[256 + n * 16 + k]
+        print(f"  tile {n}  {nm:32s} {v - base if v else -1:9d}")
+nu = 3 if C == 192 else 12
+print("LN units of warp 12, row tile 1: start, tile landed, prefetch issued, tmem loaded, math done, staged, fenced, stores issued (cycles since unit 0 start)")
+b0 = buf[400]
+for u in range(nu):
+    if 400 + u * 8 + 7 >= 512:
+        break
+    r = [buf[400 + u * 8 + k] - b0 for k in (0, 1, 2, 3, 6, 7, 4, 5)]
+    print(f"  unit {u:2d}: " + " ".join(f"{x:8d}" for x in r))
