@@ -32,7 +32,8 @@ __device__ __forceinline__ int ln_stg16(int r, int cc) { return r * 64 + ((cc ^ 
 // source (cp.async.bulk.wait_group.read NB16-1), so with NB16 = 2 the store of one unit drains while the next unit is
 // computed (r2: the single-tile version serialised every unit behind its predecessor's store, ~2.5 k clocks per unit).
 // The fp32 tile of unit idx + D is the one unit idx + D - NBUF used, whose store must be complete: NBUF >= D + NB16.
-template <int C, int UW = 16, int D = 3, bool ASYNC = false, bool TMASTORE = false, int NB16 = 1, int NBUF_ = 0>
+// NPART = warps per TMEM lane quarter (2: eight epilogue warps; 4: sixteen): warp (q, hf) takes the units hf, hf + NPART, ...
+template <int C, int UW = 16, int D = 3, bool ASYNC = false, bool TMASTORE = false, int NB16 = 1, int NBUF_ = 0, int NPART = 2>
 struct LnTileEpilogue {
   const CUtensorMap* tm_out = nullptr;               // fp32 [M, C], box UW x 32, swizzle UW*4 bytes
   const CUtensorMap* tm_xb = nullptr;                // bf16 [M, C], box UW x 32, swizzle UW*2 bytes (or null)
@@ -49,7 +50,8 @@ struct LnTileEpilogue {
   static constexpr int STGB_TILE = UW * 64;          // one bf16 staging tile: 32 rows x UW bf16
   static_assert(!ASYNC || NBUF >= D + NB16, "a refilled fp32 tile must belong to a unit whose store has been waited for");
   static_assert(ASYNC || NB16 == 1, "register-prefetch mode stages through one tile");
-  static constexpr int NU = C / (2 * UW);            // units per warp
+  static constexpr int NU = C / (NPART * UW);        // units per warp
+  static_assert(C % (NPART * UW) == 0 && (C / 32) % NPART == 0, "columns must split evenly over the warps of a lane quarter");
   static constexpr int NV = UW / 4;                  // float4 per lane per unit
   static constexpr int RPI = 128 / UW;               // rows covered by one warp-wide 16-byte access (8 or 4)
   static_assert(UW == 16 || UW == 32, "unit width");
@@ -66,7 +68,7 @@ struct LnTileEpilogue {
   long long M, m_base;                               // m_base: global row of this warp's first row
   float eps, mean, rstd;
   uint8_t* stg;                                      // per warp: UNIT_BYTES (x2 with ASYNC)
-  float2* ln_part;                                   // [2 parity][2 hf][128]
+  float2* ln_part;                                   // [2 parity][NPART][128]
   int q, hf, lane;
   uint32_t tile_par;
   long long* dbg = nullptr;                          // bring-up: 6 clock64 stamps per unit when non-null
@@ -74,7 +76,7 @@ struct LnTileEpilogue {
 
   template <int S>
   __device__ __forceinline__ void load_residual(int idx) {
-    const int u = hf + 2 * idx, rcc = lane & (NV - 1), rr0 = lane / NV;
+    const int u = hf + NPART * idx, rcc = lane & (NV - 1), rr0 = lane / NV;
     if constexpr (ASYNC) {                             // one TMA tile load per warp (rows >= M are zero-filled)
       const int b = idx % NBUF;
       if (lane == 0) {
@@ -111,7 +113,7 @@ struct LnTileEpilogue {
     uint32_t v[32];
     float s = 0.f, ss = 0.f;
 #pragma unroll 1
-    for (int c = hf; c < C / 32; c += 2) {
+    for (int c = hf; c < C / 32; c += NPART) {
       tmem_ld_32x32(y + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
@@ -123,18 +125,23 @@ struct LnTileEpilogue {
         ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
       }
     }
-    float2* part = ln_part + tile_par * 256;
+    float2* part = ln_part + tile_par * (NPART * 128);
     part[hf * 128 + q * 32 + lane] = make_float2(s, ss);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float2 p0 = part[q * 32 + lane], p1 = part[128 + q * 32 + lane];
-    mean = (p0.x + p1.x) * (1.0f / C);
-    const float var = fmaxf((p0.y + p1.y) * (1.0f / C) - mean * mean, 0.f);
+    asm volatile("bar.sync 1, %0;" ::"n"(NPART * 128) : "memory");
+    float sx = 0.f, sxx = 0.f;
+#pragma unroll
+    for (int k = 0; k < NPART; ++k) {
+      const float2 pk = part[k * 128 + q * 32 + lane];
+      sx += pk.x; sxx += pk.y;
+    }
+    mean = sx * (1.0f / C);
+    const float var = fmaxf(sxx * (1.0f / C) - mean * mean, 0.f);
     rstd = rsqrtf(var + eps);
     tile_par ^= 1;
   }
   template <int S>
   __device__ __forceinline__ void unit(uint32_t y, int idx, bool store = true) {
-    const int u = hf + 2 * idx, rcc = lane & (NV - 1), rr0 = lane / NV;
+    const int u = hf + NPART * idx, rcc = lane & (NV - 1), rr0 = lane / NV;
     uint8_t* stg_u = stg;
     if (dbg) dbg[0] = clock64();
     uint8_t* stg_bu = stg_b + (NB16 > 1 ? (idx % NB16) * STGB_TILE : 0);

@@ -42,6 +42,11 @@ namespace tc {
 constexpr int kMlpThreads = 640;
 constexpr int kMlpEpiWarps = 8;                  // GELU warps 4..11; and as many LayerNorm warps, 12..19
 constexpr int kMlpLnWarp0 = 12;
+#ifndef PANGU_MLP_LN_JOIN
+#define PANGU_MLP_LN_JOIN 1          // 1: at C = 384 the 8 GELU warps join the 8 LayerNorm warps for the LayerNorm phase (0.373 -> 0.360 ms per launch;
+                                     // 8 warps with 32-column units: 0.373; the phase stays ~15 k clocks either way: half of the SMs burst 490 KB each
+                                     // at the same time, i.e. it is bound by HBM, profiles/r2_mlp_trace.md)
+#endif
 constexpr int NH = 64;                           // hidden columns per chunk (per CTA pair)
 
 struct MlpArgs {
@@ -71,24 +76,30 @@ struct MlpCfg {
   static constexpr int NSPLIT = C / 192;         // GEMM2: N = C issued as NSPLIT MMAs of N = 192
   static constexpr int X_BYTES = 128 * C * 2;    // this CTA's rows of the x tile
   static constexpr int SLOT_BYTES = C * 64;      // half W1 chunk [32 x C] == half W2 chunk [C/2 x 64] (bf16)
-  static constexpr int LN_UW = C == 192 ? 32 : 16;   // LayerNorm unit width (columns): 32 where smem allows
+  static constexpr int LN_UW = C == 192 ? 32 : 16;   // LayerNorm unit width (columns)
   static constexpr int LN_D = C == 192 ? 1 : 2;      // residual tiles in flight per LayerNorm warp (TMA loads)
   static constexpr int LN_NB16 = C == 192 ? 1 : 2;   // bf16 staging tiles: 2 = the store of unit i drains while unit i+1 is computed
   static constexpr int LN_NBUF = LN_D + LN_NB16;      // fp32 staging tiles: LN_D landing + LN_NB16 draining
+  // C = 384: TMEM is full, the LayerNorm is a phase of its own during which the x tile AND the weight ring are dead, and
+  // the per-unit chain (tile wait, TMEM load, arithmetic, staging, proxy fence, bulk stores) is latency-bound (~1.5 k clocks
+  // per 16-column unit and warp, profiles/r2_mlp_trace.md): the 8 GELU warps JOIN the 8 LayerNorm warps (4 warps per TMEM
+  // lane quarter), and all staging tiles alias x + ring (the producer waits for them before it loads the next row tile).
+  // C = 192: the LayerNorm of tile i runs next to the MMAs of tile i+1 (two Y accumulators) on its own 8 warps with
+  // dedicated staging.
+  static constexpr bool LN_JOIN = C == 384 && PANGU_MLP_LN_JOIN;   // GELU warps join the LayerNorm phase
+  static constexpr bool LN_ALIAS = C == 384;          // staging tiles alias x tile + weight ring
+  static constexpr int LN_NPART = LN_JOIN ? 4 : 2;    // LayerNorm warps per TMEM lane quarter
+  static constexpr int LN_WARPS = 4 * LN_NPART;
   static constexpr int STG_BYTES = LN_UW * 128 * LN_NBUF;     // per LayerNorm warp: fp32 staging tiles
   static constexpr int STGB_BYTES = LN_UW * 64 * LN_NB16;     // per LayerNorm warp: bf16 staging tiles of the TMA stores
-  // C = 384: the staging tiles alias the x tile (dead after the last GEMM1 of the row tile; the producer waits for the
-  // LayerNorm warps before it loads the next one).  C = 192: the LayerNorm of tile i runs next to the MMAs of tile i+1,
-  // which read x -- dedicated staging.
-  static constexpr bool LN_ALIAS_X = C == 384;
-  static constexpr int PART_BYTES = 2 * 2 * 128 * 8; // LayerNorm partial sums
+  static constexpr int PART_BYTES = 2 * LN_NPART * 128 * 8;   // LayerNorm partial sums
   static constexpr int PARAM_BYTES = 3 * C * 4;      // b2, gamma, beta
-  static constexpr int EPI_BYTES = (LN_ALIAS_X ? 0 : kMlpEpiWarps * (STG_BYTES + STGB_BYTES)) + PART_BYTES + PARAM_BYTES;
+  static constexpr int EPI_BYTES = (LN_ALIAS ? 0 : LN_WARPS * (STG_BYTES + STGB_BYTES)) + PART_BYTES + PARAM_BYTES;
   static constexpr int BAR_BYTES = 1024;
   static constexpr int AVAIL = 227 * 1024 - 1024 - BAR_BYTES - X_BYTES - EPI_BYTES;
   static constexpr int NSLOT = AVAIL / SLOT_BYTES > 8 ? 8 : AVAIL / SLOT_BYTES;
   static constexpr int SMEM_BYTES = 1024 + X_BYTES + NSLOT * SLOT_BYTES + EPI_BYTES + BAR_BYTES;
-  static_assert(!LN_ALIAS_X || kMlpEpiWarps * (STG_BYTES + STGB_BYTES) <= X_BYTES, "staging must fit in the x tile");
+  static_assert(!LN_ALIAS || LN_WARPS * (STG_BYTES + STGB_BYTES) <= X_BYTES + NSLOT * SLOT_BYTES, "staging must fit in x tile + weight ring");
   static constexpr int NY = C == 192 ? 2 : 1;    // output accumulators: double-buffered when TMEM has room
   static constexpr int COL_HP = 384;             // two 64-column H/P buffers behind the Y accumulator(s)
   static_assert(C % 192 == 0 && C + 128 <= 512, "C must be 192 or 384");
@@ -110,9 +121,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* sW = smem + Cfg::X_BYTES;                          // [NSLOT][SLOT_BYTES]
   uint8_t* epi_smem = sW + NSLOT * Cfg::SLOT_BYTES;
   // LayerNorm staging: fp32 tiles of all warps, then bf16 tiles of all warps (inside the x tile at C = 384)
-  uint8_t* stg_smem = Cfg::LN_ALIAS_X ? sX : epi_smem;
-  uint8_t* stgb_smem = stg_smem + kMlpEpiWarps * Cfg::STG_BYTES;
-  float2* ln_part = reinterpret_cast<float2*>(epi_smem + (Cfg::LN_ALIAS_X ? 0 : kMlpEpiWarps * (Cfg::STG_BYTES + Cfg::STGB_BYTES)));
+  uint8_t* stg_smem = Cfg::LN_ALIAS ? sX : epi_smem;
+  uint8_t* stgb_smem = stg_smem + Cfg::LN_WARPS * Cfg::STG_BYTES;
+  float2* ln_part = reinterpret_cast<float2*>(epi_smem + (Cfg::LN_ALIAS ? 0 : Cfg::LN_WARPS * (Cfg::STG_BYTES + Cfg::STGB_BYTES)));
   float* sparams = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ln_part) + Cfg::PART_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
   uint64_t* x_full = bars + 0;
@@ -124,9 +135,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* xs_free = bars + 10;     // LayerNorm -> producer: the staging tiles inside the x tile are free (local)
   uint64_t* w_full = bars + 11;      // [NSLOT]
   uint64_t* w_empty = bars + 11 + NSLOT;
-  uint64_t* ln_bar = bars + 11 + 2 * NSLOT;      // [8 warps][4] barriers of the residual tile loads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11 + 2 * NSLOT + 4 * kMlpEpiWarps);
-  static_assert((11 + 2 * 8 + 4 * kMlpEpiWarps) * 8 + 8 <= Cfg::BAR_BYTES, "barrier area");
+  uint64_t* ln_bar = bars + 11 + 2 * NSLOT;      // [LN warps][4] barriers of the residual tile loads
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11 + 2 * NSLOT + 4 * Cfg::LN_WARPS);
+  static_assert((11 + 2 * 8 + 4 * Cfg::LN_WARPS) * 8 + 8 <= Cfg::BAR_BYTES, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                    // 0 = leader of the pair
@@ -146,10 +157,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     mbar_init(x_full, 1); mbar_init(x_empty, 1);
     mbar_init(&h_full[0], 1); mbar_init(&h_full[1], 1);
     mbar_init(&p_full[0], 2 * kMlpEpiWarps); mbar_init(&p_full[1], 2 * kMlpEpiWarps);
-    for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 2 * kMlpEpiWarps); }
-    mbar_init(xs_free, kMlpEpiWarps);
+    for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 2 * Cfg::LN_WARPS); }
+    mbar_init(xs_free, Cfg::LN_WARPS);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int i = 0; i < 4 * kMlpEpiWarps; ++i) mbar_init(&ln_bar[i], 1);
+    for (int i = 0; i < 4 * Cfg::LN_WARPS; ++i) mbar_init(&ln_bar[i], 1);
     fence_barrier_init();
   }
   cluster_sync_all();                                         // barrier inits visible to the peer CTA
@@ -198,7 +209,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
         const int m0 = pt * 256 + (int)rank * 128;
         mbar_wait(x_empty, xphase ^ 1);                       // every GEMM1 of the previous row tile has read x
-        if (Cfg::LN_ALIAS_X) mbar_wait(xs_free, xphase ^ 1);  // ... and its LayerNorm no longer stages through it
+        if (Cfg::LN_ALIAS) mbar_wait(xs_free, xphase ^ 1);    // ... and its LayerNorm no longer stages through x tile + ring
         xphase ^= 1;
         if ((a.dbg & 16) && blockIdx.x == 0 && lane == 0) { const int n = (pt - pair0) / npairs; if (n >= 1 && n <= 2) g_mlp_trace[256 + n * 16 + 0] = clock64(); }
         if (rank == 0 && elect_one()) mbar_expect_tx(x_full, 2 * Cfg::X_BYTES);
@@ -291,35 +302,52 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       __syncwarp();
     }
-  } else if (warp < kMlpLnWarp0) {
-    // ------------------------------------------------------------ GELU warps (both CTAs): per hidden chunk
-    // H_j (TMEM) -> +b1, GELU (packed fp16) -> P_j (TMEM, over the warp's own columns)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    const int q = warp & 3, hf = (warp - 4) >> 2;
+  } else {
+    // ------------------------------------------------------------ warps 4..11 GELU, warps 12..19 LayerNorm (both CTAs);
+    // at C = 384 the GELU warps join the LayerNorm phase of their row tile
+    const bool is_gelu = warp < kMlpLnWarp0;
+    if (is_gelu) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int q = warp & 3;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int ghf = (warp - 4) >> 2;                          // GELU: which 32 of the chunk's 64 hidden units
     const uint32_t p_full_L0 = mapa_u32(smem_u32(&p_full[0]), 0), p_full_L1 = mapa_u32(smem_u32(&p_full[1]), 0);
     uint32_t hphase = 0;                                      // bit b = phase of h_full[b]
-    uint32_t v[32];
-    for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
+    // LayerNorm participant?  C = 384: all 16 warps, lw = 0..15; C = 192: warps 12..19, lw = 0..7
+    const bool is_ln = Cfg::LN_JOIN || !is_gelu;
+    const int lw = Cfg::LN_JOIN ? warp - 4 : warp - kMlpLnWarp0;
+    const uint32_t y_empty_L0 = mapa_u32(smem_u32(&y_empty[0]), 0), y_empty_L1 = mapa_u32(smem_u32(&y_empty[1]), 0);
+    uint32_t yphase = 0;                                      // bit b = phase of y_full[b]
+    using Ln = LnTileEpilogue<C, Cfg::LN_UW, Cfg::LN_D, true, true, Cfg::LN_NB16, Cfg::LN_NBUF, Cfg::LN_NPART>;
+    static_assert(Ln::NBUF <= 4, "four load barriers per LayerNorm warp");
+    Ln ln;
+    ln.bias = a.b2; ln.gamma = a.gamma; ln.beta = a.beta; ln.residual = a.residual;
+    ln.x_out = a.x_out; ln.xb = a.x_out_bf16; ln.M = a.M; ln.eps = a.eps;
+    ln.tm_out = &tmOut; ln.tm_xb = a.x_out_bf16 != nullptr ? &tmXb : nullptr;
+    ln.stg = stg_smem + (is_ln ? lw : 0) * Cfg::STG_BYTES; ln.stg_b = stgb_smem + (is_ln ? lw : 0) * Cfg::STGB_BYTES; ln.sparams = sparams;
+    ln.tm_res = &tmRes; ln.ld_bar = &ln_bar[(is_ln ? lw : 0) * 4];
+    ln.ln_part = ln_part; ln.q = q; ln.hf = lw >> 2; ln.lane = lane; ln.tile_par = 0;
+    const bool ln_store = !(a.dbg & 32);
+    int yb = 0;
+    // one row tile of GELU work: per hidden chunk  H_j (TMEM) -> +b1, GELU (packed fp16) -> P_j (TMEM, over the warp's own columns)
+    auto gelu_tile = [&](int tn) {
+      uint32_t v[32];
 #pragma unroll 1
       for (int j = 0; j < NCH; ++j) {
         const int b = j & 1;
         float4 bb[8];                                          // b1 of this warp's 32 hidden units: fetched before the wait
         {
-          const float4* b1 = reinterpret_cast<const float4*>(a.b1 + j * NH + hf * 32);
+          const float4* b1 = reinterpret_cast<const float4*>(a.b1 + j * NH + ghf * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) bb[i] = __ldg(b1 + i);
         }
         mbar_wait(&h_full[b], (hphase >> b) & 1);
         hphase ^= 1u << b;
         tcgen05_after_sync();
-        const bool tr = (a.dbg & 16) && blockIdx.x == 0 && warp == 4 && lane == 0 && pt == pair0 + npairs && j < 64;
-        if ((a.dbg & 16) && blockIdx.x == 0 && warp == 4 && lane == 0 && (j == 0 || j == NCH - 1)) {
-          const int tn = (pt - pair0) / npairs;
-          if (tn >= 1 && tn <= 2) g_mlp_trace[256 + tn * 16 + (j == 0 ? 9 : 10)] = clock64();
-        }
+        const bool tr = (a.dbg & 16) && blockIdx.x == 0 && warp == 4 && lane == 0 && tn == 1 && j < 64;
+        if ((a.dbg & 16) && blockIdx.x == 0 && warp == 4 && lane == 0 && (j == 0 || j == NCH - 1) && tn >= 1 && tn <= 2)
+          g_mlp_trace[256 + tn * 16 + (j == 0 ? 9 : 10)] = clock64();
         if (tr) g_mlp_trace[j * 8 + 4] = clock64();
-        const uint32_t t_own = lane_base + Cfg::COL_HP + b * 64 + hf * 32;   // this warp's 32 columns of H_j
+        const uint32_t t_own = lane_base + Cfg::COL_HP + b * 64 + ghf * 32;   // this warp's 32 columns of H_j
         tmem_ld_32x32(t_own, v);
         tmem_ld_wait();
         if (tr) g_mlp_trace[j * 8 + 5] = clock64();
@@ -337,59 +365,47 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(b ? p_full_L1 : p_full_L0);
       }
-    }
-  } else {
-    // ------------------------------------------------------------ LayerNorm warps (both CTAs): per row tile
-    // Y (TMEM) -> +b2, LayerNorm, + residual -> fp32 + bf16 (tc_ln_epilogue.cuh)
-    const int lw = warp - kMlpLnWarp0;                        // 0..7
-    const int q = warp & 3, hf = lw >> 2;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t y_empty_L0 = mapa_u32(smem_u32(&y_empty[0]), 0), y_empty_L1 = mapa_u32(smem_u32(&y_empty[1]), 0);
-    uint32_t yphase = 0;                                      // bit b = phase of y_full[b]
-    using Ln = LnTileEpilogue<C, Cfg::LN_UW, Cfg::LN_D, true, true, Cfg::LN_NB16, Cfg::LN_NBUF>;
-    static_assert(Ln::NBUF <= 4, "four load barriers per LayerNorm warp");
-    Ln ln;
-    ln.bias = a.b2; ln.gamma = a.gamma; ln.beta = a.beta; ln.residual = a.residual;
-    ln.x_out = a.x_out; ln.xb = a.x_out_bf16; ln.M = a.M; ln.eps = a.eps;
-    ln.tm_out = &tmOut; ln.tm_xb = a.x_out_bf16 != nullptr ? &tmXb : nullptr;
-    ln.stg = stg_smem + lw * Cfg::STG_BYTES; ln.stg_b = stgb_smem + lw * Cfg::STGB_BYTES; ln.sparams = sparams;
-    ln.tm_res = &tmRes; ln.ld_bar = &ln_bar[lw * 4];
-    ln.ln_part = ln_part; ln.q = q; ln.hf = hf; ln.lane = lane; ln.tile_par = 0;
-    const bool ln_store = !(a.dbg & 32);
-    int yb = 0;
-    uint32_t xe_phase = 0;
-    for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
+    };
+    // one row tile of LayerNorm work:  Y (TMEM) -> +b2, LayerNorm, + residual -> fp32 + bf16 (tc_ln_epilogue.cuh)
+    auto ln_tile = [&](int pt, int tn) {
       ln.m_base = (long long)pt * 256 + rank * 128 + q * 32;
-      const int tn = (pt - pair0) / npairs;
-      const bool trl = (a.dbg & 16) && blockIdx.x == 0 && lw == 0 && lane == 0 && tn >= 1 && tn <= 2;
-      if (Cfg::LN_ALIAS_X) {                                  // the staging tiles are the x tile: wait until every GEMM1 has read it
-        mbar_wait(x_empty, xe_phase);
-        xe_phase ^= 1;
-      }
+      const bool trl = (a.dbg & 16) && blockIdx.x == 0 && warp == kMlpLnWarp0 && lane == 0 && tn >= 1 && tn <= 2;
+      if (!Cfg::LN_ALIAS) ln.prefetch();                      // dedicated staging: the first residual tiles can fly already
       if (trl) g_mlp_trace[256 + tn * 16 + 4] = clock64();
-      ln.prefetch();                                          // first residual tiles (L2 hits: pulled in by the producer warp)
-      mbar_wait(&y_full[yb], (yphase >> yb) & 1);             // accumulator yb complete
-      yphase ^= 1u << yb;
+      mbar_wait(&y_full[yb], (yphase >> yb) & 1);             // accumulator yb complete: every MMA of the row tile has retired,
+      yphase ^= 1u << yb;                                     // so at C = 384 the x tile and the weight ring are dead
       tcgen05_after_sync();
       if (trl) g_mlp_trace[256 + tn * 16 + 5] = clock64();
+      if (Cfg::LN_ALIAS) ln.prefetch();                       // staging aliases x + ring (L2 hits: rows pulled in by the producer)
       const uint32_t y = lane_base + yb * 192 * (Cfg::NY - 1);
       ln.stats(y);
       if (trl) g_mlp_trace[256 + tn * 16 + 6] = clock64();
-      ln.dbg = (trl && tn == 1) ? g_mlp_trace + 400 : nullptr;            // per-unit stamps of LN warp 0, row tile 1
+      ln.dbg = (trl && tn == 1) ? g_mlp_trace + 400 : nullptr;            // per-unit stamps of warp 12, row tile 1
       if (!(a.dbg & 2)) ln.all_units(y, ln_store);
       ln.dbg = nullptr;
       if (trl) g_mlp_trace[256 + tn * 16 + 7] = clock64();
       tcgen05_before_sync();                                  // all TMEM reads of accumulator yb are done
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(yb ? y_empty_L1 : y_empty_L0);
-      if (Cfg::LN_ALIAS_X) {                                  // hand the x tile back once the bulk stores have read the staging tiles
+      if (Cfg::LN_ALIAS) {                                    // hand x tile + ring back once the bulk stores have read the staging tiles
         if (lane == 0) { tma_store_wait_read(); mbar_arrive(xs_free); }
         if (trl) g_mlp_trace[256 + tn * 16 + 8] = clock64();
         __syncwarp();
       }
       if (Cfg::NY == 2) yb ^= 1;
+    };
+    if constexpr (Cfg::LN_JOIN) {
+      for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
+        const int tn = (pt - pair0) / npairs;
+        if (is_gelu) gelu_tile(tn);
+        ln_tile(pt, tn);
+      }
+    } else if (is_gelu) {
+      for (int pt = pair0; pt < a.pair_tiles; pt += npairs) gelu_tile((pt - pair0) / npairs);
+    } else {
+      for (int pt = pair0; pt < a.pair_tiles; pt += npairs) ln_tile(pt, (pt - pair0) / npairs);
     }
-    ln.drain_stores();
+    if (is_ln) ln.drain_stores();
   }
 
   tcgen05_before_sync();
