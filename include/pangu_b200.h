@@ -171,7 +171,11 @@ int pangu_window_attention(const void* qkv, const float* qkv_bias, const void* e
  * bias/mask types are global.  roll in {0,1}.
  * prescaled != 0: the caller folded scale*log2(e) = 32^-0.5 * 1.442695 into the q rows of linear1 (weights AND
  * the qkv_bias given here) and log2(e) into earth_bias, i.e. q k^T + bias is already the exponent in log2 units
- * (the host mirror does this once per weight update); 0 = plain reference semantics (models/layers.py:431-453). */
+ * (the host mirror does this once per weight update); 0 = plain reference semantics (models/layers.py:431-453).
+ * Bit 1 of `prescaled` (PANGU_ATTN_EXACT_MAX = 2, pre-scaled bf16 path): take the exact row maximum of S + bias in every
+ * window type instead of the bound max(S) + max(bias row) -- for bias tables whose rows spread over more than ~100 log2
+ * units (the bound would underflow every exponent); shift-masked window types always take the exact maximum. */
+#define PANGU_ATTN_EXACT_MAX 2
 int pangu_window_attention_band(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv,
                                 const float* qkv_bias, const void* earth_bias, int bias_dtype, void* out,
                                 void* halo_out, const pangu_geom* g, const pangu_band* band, int roll,
@@ -301,7 +305,9 @@ int pangu_gelu_backward_bf16(const void* dh, const void* h_pre, void* dh_pre, fl
                              void* stream);
 
 /* pangu_window_attention_band on the whole grid with pre-scaled operands (see there), additionally writing
- * lse [nLon, T, heads, 144] fp32 = log2-sum-exp of every score row, which the backward kernel consumes. */
+ * lse [nLon, T, heads, 144] fp32 = log2-sum-exp of every score row, which the backward kernel consumes.
+ * roll | PANGU_ROLL_EXACT_MAX: exact row maximum everywhere (see PANGU_ATTN_EXACT_MAX). */
+#define PANGU_ROLL_EXACT_MAX 0x100
 int pangu_window_attention_train(const void* qkv, const float* qkv_bias, const void* earth_bias, void* out,
                                  float* lse, const pangu_geom* g, int roll, void* stream);
 

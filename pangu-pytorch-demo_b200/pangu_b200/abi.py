@@ -8,7 +8,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpangu_b200.so")
+# $PANGU_B200_LIB: another build of the same C ABI (A/B measurements of kernel versions on one box, tools/ab_build.sh)
+LIB_PATH = os.environ.get("PANGU_B200_LIB") or os.path.join(HERE, "libpangu_b200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU = 0, 1

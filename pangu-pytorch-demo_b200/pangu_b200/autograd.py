@@ -73,7 +73,8 @@ def block_forward_train(blk, x0, x0b, Z, H, W, roll, s1, s2):
     if s1 != 0.0:
         w_qkv, b_qkv, eb = PF.attention_operands(att, wc)               # pre-scaled (scale*log2e folded into q)
         qkv = ops.linear(x0b, w_qkv, b_qkv)
-        o, lse = ops.window_attention_train(qkv, b_qkv, eb, Z, H, W, att.head_number, 1 if roll else 0)
+        o, lse = ops.window_attention_train(qkv, b_qkv, eb, Z, H, W, att.head_number, 1 if roll else 0,
+                                            exact_max=True)   # parameters change every step: no per-step host read of the bias spread
         y1 = ops.linear(o, wc.bf16("a2", PF.lin_w(att.linear2)), f(PF.lin_b(att.linear2)), out_dtype=F32)
         gam1, bet1 = PF._affine(blk.norm1, s1)
         x1, x1b = ops.ln_residual(y1, gam1, bet1, residual=x0, want_bf16=True, eps=blk.norm1.eps)

@@ -185,7 +185,7 @@ extern "C" int pangu_window_attention_band(const void* qkv, const void* halo_qkv
       return PANGU_ERR_BAD_ARG;
     }
   }
-  return launch_window_attention_bf16(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, bias_dtype, out, halo_out, g, bd, roll, prescaled != 0, as_stream(stream));
+  return launch_window_attention_bf16(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, bias_dtype, out, halo_out, g, bd, roll, prescaled & 3, as_stream(stream));
 }
 
 extern "C" int pangu_linear_bf16_add(const void* A, int64_t lda, const void* W, const float* bias, const float* addend,
@@ -199,9 +199,11 @@ extern "C" int pangu_window_attention_train(const void* qkv, const float* qkv_bi
   WinGeom g;
   if (!make_geom(gg, g) || !qkv || !qkv_bias || !earth_bias || !out || !lse) { set_error("window_attention_train: bad argument"); return PANGU_ERR_BAD_ARG; }
   if (g.C != g.heads * kHeadDim) { set_error("window_attention_train: C=%d must equal heads*32", g.C); return PANGU_ERR_BAD_ARG; }
+  const int exact = (roll >> 8) & 1;                              // PANGU_ROLL_EXACT_MAX
+  roll &= 0xff;
   if (roll < 0 || roll > 2) { set_error("window_attention_train: roll must be 0, 1 or 2"); return PANGU_ERR_BAD_ARG; }
   const BandGeom full{0, g.H, 0, g.nH, 0, 0, 0};
-  return launch_window_attention_bf16(qkv, nullptr, nullptr, qkv_bias, earth_bias, PANGU_BF16, out, nullptr, g, full, roll, 1, as_stream(stream), lse);
+  return launch_window_attention_bf16(qkv, nullptr, nullptr, qkv_bias, earth_bias, PANGU_BF16, out, nullptr, g, full, roll, 1 | (exact << 1), as_stream(stream), lse);
 }
 
 extern "C" int pangu_window_attention_backward(const void* qkv, const float* qkv_bias, const void* earth_bias,

@@ -290,7 +290,7 @@ static int launch_attn_t(const void* qkv, const void* halo_qkv, const void* halo
 // tc_attention2.cu: tcgen05 / TMEM formulation (bf16 pre-scaled operands)
 int launch_window_attention_tc(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias,
                                const void* earth_bias, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
-                               int roll, cudaStream_t st, float* lse);
+                               int roll, cudaStream_t st, float* lse, int exact_max);
 
 int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias, const void* earth_bias,
                                  int bias_dtype, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
@@ -299,8 +299,9 @@ int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const vo
   if (bd.nhw <= 0) return PANGU_OK;
   {   // pre-scaled bf16 operands: the tcgen05 kernel; $PANGU_B200_ATTN_TC=0 keeps the mma.sync kernel below
     static const bool use_tc = []() { const char* e = getenv("PANGU_B200_ATTN_TC"); return e == nullptr || atoi(e) != 0; }();
-    if (use_tc && prescaled && bias_dtype == PANGU_BF16)
-      return launch_window_attention_tc(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, st, lse);
+    if (use_tc && (prescaled & 1) && bias_dtype == PANGU_BF16)
+      return launch_window_attention_tc(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, st, lse, (prescaled >> 1) & 1);
+    prescaled &= 1;
   }
   // longitude windows per CTA (they share the staged bias tile): as many as possible (<= 5) while the grid
   // still fills the GPU for at least ~4 waves of 2 CTAs/SM -- small latitude bands get finer CTAs

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __restrict__ qkv_bias,
                            const __nv_bfloat16* __restrict__ earth_bias, __nv_bfloat16* __restrict__ out,
                            __nv_bfloat16* __restrict__ halo_out, WinGeom g, BandGeom bd, int roll,
-                           float* __restrict__ lse, int dbg) {
+                           float* __restrict__ lse, int dbg, int exact_all) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(smem);                       // [144][152]
@@ -507,10 +507,10 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       if (trc && warp == 0) g_attn_trace[13] = clock64();
     }
     const int i_end = min(nwin, (u0 + ts + 1) * g.nLon - p0);    // windows [.., i_end) lie in tile u0 + ts
-    bool masked_tile = false;                                 // this tile's window type carries the shift mask (layers.py:187-216)
-    if (roll == 1) {
+    bool masked_tile = exact_all != 0;                        // this tile's window type carries the shift mask (layers.py:187-216),
+    if (roll == 1) {                                          // or the caller asked for the exact maximum everywhere (wide bias tables)
       const int tt = tile_type(g, bd, u0 + ts), tzw = tt / g.nH;
-      masked_tile = tzw == g.nZ - 1 || tt - tzw * g.nH == g.nH - 1;
+      masked_tile = masked_tile || tzw == g.nZ - 1 || tt - tzw * g.nH == g.nH - 1;
     }
     float bmax = -INFINITY;                                   // maximum of my part of this tile's bias row
     if (i < i_end) {
@@ -775,7 +775,7 @@ namespace tc { int num_sms(); }
 
 int launch_window_attention_tc(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv, const float* qkv_bias,
                                const void* earth_bias, void* out, void* halo_out, const WinGeom& g, const BandGeom& bd,
-                               int roll, cudaStream_t st, float* lse) {
+                               int roll, cudaStream_t st, float* lse, int exact_max) {
   using namespace attn2;
   if (bd.nhw <= 0) return PANGU_OK;
   static unsigned long long configured = 0;
@@ -809,7 +809,7 @@ int launch_window_attention_tc(const void* qkv, const void* halo_qkv, const void
   static const int dbg = []() { const char* e = getenv("PANGU_ATTN_DBG"); return e ? atoi(e) : 0; }();
   cudaError_t le = tc::launch_pdl(window_attention_tc_kernel, dim3((unsigned)(nteams * g.heads)), dim3(kThreads), kSmemBytes, st,
                                   maps, qkv_bias, (const __nv_bfloat16*)earth_bias, (__nv_bfloat16*)out, (__nv_bfloat16*)halo_out, g, bd,
-                                  roll, lse, dbg);
+                                  roll, lse, dbg, exact_max);
   if (le != cudaSuccess) { set_error("window_attention_tc: launch: %s", cudaGetErrorString(le)); return PANGU_ERR_CUDA; }
   return check_launch("window_attention_tc");
 }

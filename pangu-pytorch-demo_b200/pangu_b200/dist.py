@@ -202,7 +202,8 @@ class _Worker:
         _, b_qkv, eb = PF.attention_operands(att, wc)
         self.o, self.halo_o = ops.window_attention_band(
             self.qkv, self.halo_qkv, b_qkv, eb, Z, TOK_H[stage], TOK_W[stage], att.head_number, band, roll,
-            halo_lo_qkv=self.halo_lo_qkv, return_halo=(scheme == "sendback"), prescaled=True)
+            halo_lo_qkv=self.halo_lo_qkv, return_halo=(scheme == "sendback"), prescaled=True,
+            exact_max=PF.attention_exact_max(att, wc))
         self.qkv = self.halo_qkv = self.halo_lo_qkv = None
 
     def block_finish(self, blk, stage, o_first):

@@ -165,6 +165,22 @@ def attention_operands(att, wc):
             wc.derived("ebs", (att.earth_specific_bias,), lambda e: (e[0].float() * LOG2E).to(torch.bfloat16).contiguous()))
 
 
+# The tcgen05 attention kernel shifts each score row by the BOUND max(S) + max(bias row) (no bias traffic in its max pass);
+# the bound is loose by at most the spread of the bias row, and bf16 P / fp32 sums absorb ~100 log2 units of looseness.
+# A bias table with wider rows (not seen at init or in the stress tests, but nothing forbids it) gets the exact maximum.
+BIAS_SPREAD_LIMIT = 80.0          # log2 units
+
+
+def attention_exact_max(att, wc):
+    """True when some row of the (log2-scaled) Earth-specific bias spreads over more than BIAS_SPREAD_LIMIT: the caller then
+    asks the kernel for the exact row maximum (PANGU_ATTN_EXACT_MAX).  One device reduction + host read per weight update,
+    made while the operand caches are (re)built, i.e. outside CUDA-graph capture."""
+    def spread(e):
+        t = e[0].float()
+        return float(((t.amax(-1) - t.amin(-1)).max() * LOG2E).item()) > BIAS_SPREAD_LIMIT
+    return wc.derived("ebx", (att.earth_specific_bias,), spread)
+
+
 def _w2d(p):
     """Linear [out,in] or Conv1d(k=1) [out,in,1] weight as a contiguous fp32 matrix."""
     t = p.detach()
@@ -211,7 +227,7 @@ def block_forward(blk, x, Z, H, W, roll, mode, xb=None, s1=1.0, s2=1.0):
         w_qkv, b_qkv, eb = attention_operands(att, wc)
         qkv = ops.linear(xb, w_qkv, b_qkv)
         o, _ = ops.window_attention_band(qkv, None, b_qkv, eb, Z, H, W, heads, ops.full_band(H), 1 if roll else 0,
-                                         prescaled=True)
+                                         prescaled=True, exact_max=attention_exact_max(att, wc))
         del qkv
         g1, b1 = _affine(blk.norm1, s1)
         x1, x1b = ops.linear_ln_residual_bf16(o, wc.bf16("a2", lin_w(att.linear2)), _f(lin_b(att.linear2)), g1, b1, x,

@@ -262,7 +262,7 @@ def full_band(H):
 
 
 def window_attention_band(qkv, halo_qkv, qkv_bias, earth_bias, Z, H, W, heads, band, roll, halo_lo_qkv=None,
-                          return_halo=True, prescaled=False):
+                          return_halo=True, prescaled=False, exact_max=False):
     """Band-sharded window attention (bf16): qkv [Z*hrows*W, 3C] holds the band's own rows of the GLOBAL
     (Z, H, W) grid, halo_qkv [Z*halo*W, 3C] the southern neighbour's first rows, halo_lo_qkv the northern
     neighbour's last rows.  -> (out, halo_out): halo_out (attention output of the southern halo rows, to be sent
@@ -286,7 +286,8 @@ def window_attention_band(qkv, halo_qkv, qkv_bias, earth_bias, Z, H, W, heads, b
     nwin = (W // 12) * (Z // 2) * band.nhw
     _call("attention_bf16[C=%d]" % C, "pangu_window_attention_band",
           (_ptr(qkv), _ptr(halo_qkv) if band.halo else None, _ptr(halo_lo_qkv) if band.halo_lo else None, _ptr(qkv_bias),
-           _ptr(earth_bias), _DT[earth_bias.dtype], _ptr(out), _ptr(halo_out), g, band, int(roll), int(prescaled),
+           _ptr(earth_bias), _DT[earth_bias.dtype], _ptr(out), _ptr(halo_out), g, band, int(roll),
+           int(bool(prescaled)) | (2 if exact_max else 0),
            _stream(),),
           flops=nwin * heads * 4.0 * 144 * 144 * 32,
           nbytes=float(qkv.numel() * 2 + out.numel() * 2 + earth_bias.numel() * earth_bias.element_size() * band.nhw / ((H + 5) // 6)))
@@ -525,7 +526,7 @@ def linear_gelu_backward(dy, w_t, h_pre, dcolsum=None):
     return dh
 
 
-def window_attention_train(qkv, qkv_bias, earth_bias, Z, H, W, heads, roll):
+def window_attention_train(qkv, qkv_bias, earth_bias, Z, H, W, heads, roll, exact_max=False):
     """Pre-scaled bf16 window attention that also returns the log2-sum-exp rows for the backward kernel."""
     _chk(qkv, torch.bfloat16, "qkv")
     _chk(qkv_bias, torch.float32, "qkv_bias")
@@ -537,7 +538,7 @@ def window_attention_train(qkv, qkv_bias, earth_bias, Z, H, W, heads, roll):
     lse = torch.empty((nLon, T, heads, 144), dtype=torch.float32, device=qkv.device)
     g = geom(Z, H, W, C, heads)
     _call("attention_bf16[C=%d]" % C, "pangu_window_attention_train",
-          (_ptr(qkv), _ptr(qkv_bias), _ptr(earth_bias), _ptr(out), _ptr(lse), g, int(roll), _stream(),),
+          (_ptr(qkv), _ptr(qkv_bias), _ptr(earth_bias), _ptr(out), _ptr(lse), g, int(roll) | (0x100 if exact_max else 0), _stream(),),
           flops=nLon * T * heads * 4.0 * 144 * 144 * 32, nbytes=float(qkv.numel() * 2 + out.numel() * 2 + earth_bias.numel() * 2))
     return out, lse
 

@@ -121,3 +121,17 @@ def test_inputs_times_100_and_trained_scale_weights(stage, roll):
     print(f"inputs x100, stage {stage} roll {roll}: output {e_out:.2e}, branch vs fp32 {e_branch:.2e}, "
           f"branch vs fp32-on-bf16-operands {e_emul:.2e}")
     assert e_out <= TOL and e_emul <= TOL
+
+
+def test_bias_rows_wider_than_the_softmax_bound_take_the_exact_maximum():
+    """A bias table whose rows spread over more than functional.BIAS_SPREAD_LIMIT log2 units (here +-150 outliers): the
+    host mirror detects it once per weight version and asks the kernel for the exact row maximum (PANGU_ATTN_EXACT_MAX);
+    with the bound max(S) + max(bias row) every exponent of such a row would underflow (sum 0 -> NaN)."""
+    def mutate(p, pfx, g):
+        b = p[pfx + "attention.earth_specific_bias"]
+        idx = torch.randint(0, b.numel(), (b.numel() // 300,), generator=g)
+        b.view(-1)[idx] = (torch.randint(0, 2, idx.shape, generator=g).float() * 2 - 1) * 150.0
+    for roll in (False, True):
+        e_out, e_branch = _run("A", roll, mutate)
+        print(f"bias +-150 outliers, roll {roll}: output {e_out:.2e}, branch {e_branch:.2e}")
+        assert e_out <= TOL and e_branch <= TOL
