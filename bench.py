@@ -201,7 +201,10 @@ def run_finetune(args, rank, world, dev, torch, dist, orc, PanguModel, ops):
     if world > 1:
         if args.dp == "ddp":
             from torch.nn.parallel import DistributedDataParallel as DDP
-            fwd = DDP(model, device_ids=[dev.index], bucket_cap_mb=64, gradient_as_bucket_view=True)
+            # --bucket-mb: DDP's bucket size.  64 MB overlaps the all-reduce with the backward, but the persistent kernels
+            # (one CTA per SM, ~220 KB of shared memory each) then queue behind resident NCCL CTAs; a bucket larger than the
+            # 1.1 GB of gradients defers the (2-3 ms over NVLink) all-reduce to the end of the backward: no contention.
+            fwd = DDP(model, device_ids=[dev.index], bucket_cap_mb=args.bucket_mb, gradient_as_bucket_view=True)
         else:
             from pangu_b200.dist import GradientAllReducer
             reducer = GradientAllReducer(model)
@@ -273,7 +276,7 @@ def run_finetune(args, rank, world, dev, torch, dist, orc, PanguModel, ops):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic (seeded random-init weights, ERA5-shaped inputs and targets)",
                 "config": {"workload": "finetune_fully.py fwd+bwd bf16, batch 1 per GPU, data-parallel NCCL all-reduce (BASELINE.json configs[4])",
-                           "parallelism": f"dp{world} ({'torch DDP' if args.dp == 'ddp' else 'GradientAllReducer: flat fp32 buckets, NCCL all-reduce overlapped with the backward'})",
+                           "parallelism": f"dp{world} ({f'torch DDP, bucket_cap_mb={args.bucket_mb}' if args.dp == 'ddp' else 'GradientAllReducer: flat fp32 buckets, NCCL all-reduce overlapped with the backward'})",
                            "params": 276659936, "grad_bytes": 276659936 * 4, "optimizer": "Adam lr 2e-5 wd 3e-6 (torch fused)",
                            "activations": "saved (no re-computation)" if os.environ.get("PANGU_B200_TRAIN_RECOMPUTE", "0") == "0" else "re-computed per block",
                            "peak_mem_gb": peak_gb, "cache": "activations per step (>= 35 GB) exceed the 126 MB L2; no flush needed"},
@@ -397,6 +400,8 @@ def main():
     ap.add_argument("--dp", default="ddp", choices=["buckets", "ddp"],
                     help="--mode finetune gradient all-reduce: pangu_b200.dist.GradientAllReducer or torch DDP (what the "
                          "reference uses, finetune/finetune_fully.py:220)")
+    ap.add_argument("--bucket-mb", type=int, default=2048,
+                    help="--mode finetune --dp ddp: DDP bucket_cap_mb (2048 = one bucket after the backward; 64 = overlapped)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--graph", default="on", choices=["on", "off"],
                     help="replay the step from a CUDA graph (pangu_b200.graph.GraphedForward) instead of ~100 "
