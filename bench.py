@@ -586,6 +586,21 @@ def main():
     h2d = (h_inp.numel() + h_inp_s.numel()) * 4            # per rank
     d2h = (h_out.numel() + h_out_s.numel()) * 4
 
+    # the two transfers of one step ALONE (all ranks at the same time, nothing else running): what the host side of this
+    # box sustains; explains how much of e2e - value is transfer time that a 2-deep pipeline cannot hide
+    def copy_in():
+        d_inp.copy_(h_inp.reshape(d_inp.shape), non_blocking=True)
+        d_inp_s.copy_(h_inp_s.reshape(d_inp_s.shape), non_blocking=True)
+
+    def copy_out():
+        h_out.copy_(step_out[0].reshape(h_out.shape), non_blocking=True)
+        h_out_s.copy_(step_out[1].reshape(h_out_s.shape), non_blocking=True)
+
+    step_out = step_resident()
+    copy_in(); copy_out()
+    h2d_ms = timed(copy_in, 10) / 10
+    d2h_ms = timed(copy_out, 10) / 10
+
     kernels, roofline = None, None
     peaks = load_peaks()
     if not args.no_kernel_times:
@@ -641,7 +656,10 @@ def main():
                 "scaling": "weak" if mode == "replicas" else "strong", "vs_baseline": None,
                 "dtype": args.dtype, "data": "synthetic (seeded random-init weights, ERA5-shaped inputs)", "config": config,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / args.steps, "api": ("pangu_b200.pipeline.StreamedForecaster(PanguModel / BandedPangu): pinned host in -> pinned host out, "
+                        "ms_per_step": e2e_ms / args.steps,
+                        "transfers_alone": {"h2d_ms": h2d_ms, "d2h_ms": d2h_ms, "h2d_gbs": h2d / h2d_ms / 1e6, "d2h_gbs": d2h / d2h_ms / 1e6,
+                                            "note": "one step's pinned-host copies timed alone, all ranks at once, max over ranks"},
+                        "api": ("pangu_b200.pipeline.StreamedForecaster(PanguModel / BandedPangu): pinned host in -> pinned host out, "
                                 "transfers of neighbouring samples overlap the forward" if streamer is not None else
                                 "models.pangu_model.PanguModel.forward on pinned host inputs, serial H2D / forward / D2H")},
                 "gpu_launches": launches, "launch_used": launch_used, "clocks": clocks, "roofline": roofline,

@@ -424,10 +424,12 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       if (i >= 3) tc::mbar_wait(&o_full[b], ((i / 3) & 1) ^ 1);
       tc::tcgen05_after_sync();
       const uint32_t aq = smem_u32(s_buf + st * kBufBytes), ak = aq + kTileBytes;
+      if (tc::elect_one()) {                                 // one elected lane, real branch: uniform-register descriptors
 #pragma unroll
-      for (int k = 0; k < 2; ++k)                            // K = 32: two 16-element steps, +32 B inside the 64 B swizzle span
-        if (tc::elect_one()) tc::umma_bf16(tmem_base + b * kColS, desc_k_sw64(aq) + 2 * k, desc_k_sw64(ak) + 2 * k, idesc_s, k);
-      if (tc::elect_one()) tc::umma_commit(&s_full[b]);
+        for (int k = 0; k < 2; ++k)                          // K = 32: two 16-element steps, +32 B inside the 64 B swizzle span
+          tc::umma_bf16(tmem_base + b * kColS, desc_k_sw64(aq) + 2 * k, desc_k_sw64(ak) + 2 * k, idesc_s, k);
+        tc::umma_commit(&s_full[b]);
+      }
       __syncwarp();
       if (trc) g_attn_trace[(i & 7) * 16 + 1] = clock64();
     }
@@ -443,11 +445,12 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       if (trc) g_attn_trace[(i & 7) * 16 + 2] = clock64();
       const uint32_t av = smem_u32(s_buf + st * kBufBytes + 2 * kTileBytes);
       const uint32_t tP = tmem_base + b * kColS, tO = tmem_base + kColO + 32 * (i & 1);
+      if (tc::elect_one()) {                                 // one elected lane, real branch: uniform-register descriptors
 #pragma unroll
-      for (int k = 0; k < 9; ++k)                            // K = 144 keys: 16 keys = 8 packed TMEM columns / 1 KiB of V per step
-        if (tc::elect_one())                                 // P of keys 0..79 at columns [0,40), of keys 80..143 at [80,112)
-          tc::umma_bf16_ts(tO, tP + 8 * k + (k >= 5 ? 40 : 0), desc_mn_sw64(av + 1024 * k), idesc_o, k);
-      if (tc::elect_one()) { tc::umma_commit(&o_rdy[i & 1]); tc::umma_commit(&o_full[b]); tc::umma_commit(&empty[st]); }
+        for (int k = 0; k < 9; ++k)                          // K = 144 keys: 16 keys = 8 packed TMEM columns / 1 KiB of V per step
+          tc::umma_bf16_ts(tO, tP + 8 * k + (k >= 5 ? 40 : 0), desc_mn_sw64(av + 1024 * k), idesc_o, k);   // P of keys 0..79 at columns [0,40), of keys 80..143 at [80,112)
+        tc::umma_commit(&o_rdy[i & 1]); tc::umma_commit(&o_full[b]); tc::umma_commit(&empty[st]);
+      }
       __syncwarp();
       if (trc) g_attn_trace[(i & 7) * 16 + 3] = clock64();
     }

@@ -171,14 +171,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
         const uint32_t sb = sa + A_STAGE_BYTES;
         const uint64_t da = make_desc_k_sw128(sa);
+        if (elect_one()) {                       // one elected lane issues the whole k-block (uniform-register descriptors, see tc_mlp.cu)
 #pragma unroll
-        for (int h = 0; h < Cfg::N_SPLIT; ++h) {
-          const uint64_t db = make_desc_k_sw128(sb + h * Cfg::UMMA_N * BK * 2);
+          for (int h = 0; h < Cfg::N_SPLIT; ++h) {
+            const uint64_t db = make_desc_k_sw128(sb + h * Cfg::UMMA_N * BK * 2);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)   // +32 bytes per UMMA_K=16 step inside the swizzle span
-            if (elect_one()) umma_bf16(d_tmem + h * Cfg::UMMA_N, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / 16; ++k)   // +32 bytes per UMMA_K=16 step inside the swizzle span
+              umma_bf16(d_tmem + h * Cfg::UMMA_N, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);        // frees the smem slot once these MMAs have read it
         }
-        if (elect_one()) umma_commit(&empty_bar[stage]);       // frees the smem slot once these MMAs have read it
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }

@@ -171,10 +171,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tcgen05_after_sync();
             const uint64_t da = make_desc_k_sw128(smem_u32(sA) + kb * 16384);
             const uint64_t db = make_desc_k_sw128(smem_u32(sW) + slot * G2_SLOT);
+            if (elect_one()) {                     // one elected lane issues the whole k-block (uniform-register descriptors, see tc_mlp.cu)
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (elect_one()) umma2_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            if (elect_one()) umma2_commit_mc(&w_empty[slot]);
+              for (int k = 0; k < 4; ++k) umma2_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              umma2_commit_mc(&w_empty[slot]);
+            }
             __syncwarp();
             if (++slot == NSLOT) { slot = 0; wphase ^= 1; }
           }

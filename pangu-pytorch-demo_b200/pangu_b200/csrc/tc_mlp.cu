@@ -246,17 +246,24 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           mbar_wait(&w_full[slot], wphase);
           tcgen05_after_sync();
           const uint32_t sw = smem_u32(sW + slot * Cfg::SLOT_BYTES);
+          // ONE elected lane runs the whole unrolled group behind a real branch: ptxas then keeps the descriptors in uniform
+          // registers (UIADD3 + UTCHMMA back to back, ~5 instructions per MMA); an `if (elect_one())` around every single MMA
+          // compiles to ~20 predicated instructions and 4-5 R2UR per MMA (r2: the issuing thread was the limiter at C = 192)
+          if (elect_one()) {
 #pragma unroll
-          for (int kb = 0; kb < KB1; ++kb) {
-            const uint64_t da = make_desc_k_sw128(smem_u32(sX) + kb * 16384);
-            const uint64_t db = make_desc_k_sw128(sw + kb * 4096);
+            for (int kb = 0; kb < KB1; ++kb) {
+              const uint64_t da = make_desc_k_sw128(smem_u32(sX) + kb * 16384);
+              const uint64_t db = make_desc_k_sw128(sw + kb * 4096);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if ((a.dbg & 4) && k) break;
-              if (elect_one()) umma2_bf16(tHP + b * 64, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+              for (int k = 0; k < 4; ++k) {
+                if ((a.dbg & 4) && k) break;
+                umma2_bf16(tHP + b * 64, da + 2 * k, db + 2 * k, idesc1, (kb | k) != 0);
+              }
             }
+            umma2_commit_mc(&w_empty[slot]);
+            umma2_commit_mc(&h_full[b]);
           }
-          if (elect_one()) { umma2_commit_mc(&w_empty[slot]); umma2_commit_mc(&h_full[b]); }
+          __syncwarp();
           advance();
         };
         for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
@@ -278,14 +285,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             mbar_wait(&w_full[slot], wphase);
             tcgen05_after_sync();
             const uint32_t sw = smem_u32(sW + slot * Cfg::SLOT_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int h = 0; h < NSPLIT; ++h) {
-              const uint64_t db = make_desc_k_sw128(sw + h * 12288);
+              for (int h = 0; h < NSPLIT; ++h) {
+                const uint64_t db = make_desc_k_sw128(sw + h * 12288);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)                        // Y += P_j . W2chunk^T ; K-step k lives at columns (k>>1)*32 + (k&1)*8
-                if (!((a.dbg & 8) && k) && elect_one()) umma2_bf16_ts(tmem_base + yb * 192 + h * 192, tHP + b * 64 + (k >> 1) * 32 + (k & 1) * 8, db + 2 * k, idesc2, (j | k) != 0);
+                for (int k = 0; k < 4; ++k)                      // Y += P_j . W2chunk^T ; K-step k lives at columns (k>>1)*32 + (k&1)*8
+                  if (!((a.dbg & 8) && k)) umma2_bf16_ts(tmem_base + yb * 192 + h * 192, tHP + b * 64 + (k >> 1) * 32 + (k & 1) * 8, db + 2 * k, idesc2, (j | k) != 0);
+              }
+              umma2_commit_mc(&w_empty[slot]);
             }
-            if (elect_one()) umma2_commit_mc(&w_empty[slot]);
+            __syncwarp();
             advance();
             if (tr) g_mlp_trace[j * 8 + 1] = clock64();
             if (j + 2 < NCH) {

@@ -95,13 +95,15 @@ wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       tcgen05_after_sync();
       const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
       const uint32_t sb = sa + Cfg::A_BYTES;
+      if (elect_one()) {                              // one elected lane issues the whole k-block (see tc_mlp.cu)
 #pragma unroll
-      for (int k = 0; k < WG_BK / 16; ++k) {          // 16 tokens = two 8-token groups = 2 KiB per MMA
-        const uint64_t da = make_desc_mn_sw128(sa + k * 2048, WG_CHUNK_BYTES, 1024);
-        const uint64_t db = make_desc_mn_sw128(sb + k * 2048, WG_CHUNK_BYTES, 1024);
-        if (elect_one()) umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
+        for (int k = 0; k < WG_BK / 16; ++k) {        // 16 tokens = two 8-token groups = 2 KiB per MMA
+          const uint64_t da = make_desc_mn_sw128(sa + k * 2048, WG_CHUNK_BYTES, 1024);
+          const uint64_t db = make_desc_mn_sw128(sb + k * 2048, WG_CHUNK_BYTES, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
       }
-      if (elect_one()) umma_commit(&empty_bar[stage]);
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
