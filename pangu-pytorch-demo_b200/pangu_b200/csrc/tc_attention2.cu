@@ -242,6 +242,61 @@ __device__ __noinline__ void swap_tile_fn(const SwapCtx* ctx, int u, int ctid, i
 // warp); 12 / 13 bias swap start / end (warp 0)
 __device__ long long g_attn_trace[8 * 16];
 
+// ---- softmax shift: per-thread bound of the row maximum of S + bias over its keys (hf = 0: keys [0, 80), hf = 1: [80, 144)).
+// The shift mask (gen_mask, layers.py:187-216) separates the 144 keys of a window into at most four contiguous sub-blocks
+// [0,36) [36,72) [72,108) [108,144) (dz x {dh < 3, dh >= 3}); inside one sub-block every key of a given row is either
+// masked (-100 folded into the staged bias tile) or not.  Taking max(S) + max(bias) PER SUB-BLOCK therefore bounds the row
+// maximum to within the spread of the un-masked bias values (r2: the single bound max(S) + max(bias row) was loose by up to
+// 144 log2 units on masked window types and underflowed every exponent -- NaN rows -- when a masked key carried the largest
+// score by more than ~126).  Same instruction count as the single bound.
+template <int HF> __device__ __forceinline__ constexpr int key_sub(int idx) {      // local key index -> local sub-block
+  return HF == 0 ? (idx < 36 ? 0 : (idx < 72 ? 1 : 2)) : (idx < 28 ? 0 : 1);
+}
+template <int HF>
+__device__ __forceinline__ void bias_sub_max(uint32_t brow, float (&bm)[3]) {
+  bm[0] = bm[1] = bm[2] = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < (HF ? 8 : 10); ++c) {
+    const uint4 bb = lds128(brow + 16 * c);
+    const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = 8 * c + 2 * e;                          // compile-time after unrolling; pairs never straddle a boundary
+      float& m = bm[key_sub<HF>(idx)];
+      m = fmaxf(m, fmaxf(__uint_as_float(bw[e] << 16), __uint_as_float(bw[e] & 0xffff0000u)));
+    }
+  }
+}
+template <int HF>
+__device__ __forceinline__ float score_bound(uint32_t tS, const float (&bm)[3]) {
+  float mx[3][2] = {{-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}, {-INFINITY, -INFINITY}};
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
+    tc::tmem_ld_32x32(tS + 32 * c, v);
+    tmem_ld_wait32(v);
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      float& m = mx[key_sub<HF>(32 * c + e)][e & 1];
+      m = fmaxf(m, __uint_as_float(v[e]));
+    }
+  }
+  if constexpr (HF == 0) {
+    uint32_t v[16];
+    tc::tmem_ld_32x16(tS + 64, v);
+    tmem_ld_wait16(v);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      float& m = mx[key_sub<0>(64 + e)][e & 1];
+      m = fmaxf(m, __uint_as_float(v[e]));
+    }
+  }
+  float r = fmaxf(mx[0][0], mx[0][1]) + bm[0];
+  r = fmaxf(r, fmaxf(mx[1][0], mx[1][1]) + bm[1]);
+  if constexpr (HF == 0) r = fmaxf(r, fmaxf(mx[2][0], mx[2][1]) + bm[2]);
+  return r;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __restrict__ qkv_bias,
                            const __nv_bfloat16* __restrict__ earth_bias, __nv_bfloat16* __restrict__ out,
@@ -510,23 +565,10 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       if (trc && warp == 0) g_attn_trace[13] = clock64();
     }
     const int i_end = min(nwin, (u0 + ts + 1) * g.nLon - p0);    // windows [.., i_end) lie in tile u0 + ts
-    bool masked_tile = exact_all != 0;                        // this tile's window type carries the shift mask (layers.py:187-216),
-    if (roll == 1) {                                          // or the caller asked for the exact maximum everywhere (wide bias tables)
-      const int tt = tile_type(g, bd, u0 + ts), tzw = tt / g.nH;
-      masked_tile = masked_tile || tzw == g.nZ - 1 || tt - tzw * g.nH == g.nH - 1;
-    }
-    float bmax = -INFINITY;                                   // maximum of my part of this tile's bias row
-    if (i < i_end) {
-#pragma unroll
-      for (int c = 0; c < 10; ++c) {
-        if (c < 2 * nchunk) {
-          const uint4 bb = lds128(brow + 16 * c);
-          const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            bmax = fmaxf(bmax, fmaxf(__uint_as_float(bw[e] << 16), __uint_as_float(bw[e] & 0xffff0000u)));
-        }
-      }
+    const bool masked_tile = exact_all != 0;                  // the caller asked for the exact row maximum (wide bias tables)
+    float bm[3] = {0.f, 0.f, 0.f};                            // per key sub-block: maximum of my part of this tile's bias row
+    if (i < i_end && !masked_tile) {
+      if (hf == 0) bias_sub_max<0>(brow, bm); else bias_sub_max<1>(brow, bm);
     }
 #pragma unroll 1
     for (; i < i_end; i += 2) {
@@ -543,16 +585,15 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       const uint32_t exm = exg + slot * 2048, exs = exm + 1024;
       float m;
       {
-        // ---- pass 1: an UPPER BOUND of the row maximum of S + bias over my keys: max(S) + max(bias).  Softmax is
-        // invariant under the shift, and bf16 P / fp32 sums keep their relative precision over the whole exponent range,
-        // so any bound within ~100 (log2 units) of the true maximum gives the same result; this one is off by at most
-        // the spread of the bias row.  It saves the bias reads and adds of a full pass.
-        // NOT on masked window types (r2, found by tests/test_gpu_stress.py): there the folded -100 makes the "spread"
-        // 144 log2 units -- when a MASKED key carries the largest score of the row by more than ~126, every exponent
-        // underflows, the row sum is 0 and the output NaN (the reference, with the true maximum, lets the masked key win
-        // because -100 is finite).  Those tiles (28 % of them) take the exact maximum of S + bias below.
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-        if (masked_tile) {
+        // ---- pass 1: an UPPER BOUND of the row maximum of S + bias over my keys (score_bound above: max(S) + max(bias)
+        // per shift-mask sub-block).  Softmax is invariant under the shift, and bf16 P / fp32 sums keep their relative
+        // precision over the whole exponent range, so any bound within ~100 (log2 units) of the true maximum gives the same
+        // result; this one is off by at most the spread of the un-masked bias values of the row.  It saves the bias reads
+        // and adds of a full pass.  (exact_all: bias rows that spread wider than that take the exact maximum instead.)
+        float mx0;
+        if (masked_tile) {                                    // exact maximum of S + bias (wide bias tables only)
+          float mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+          mx0 = -INFINITY;
 #pragma unroll
           for (int c = 0; c < 5; ++c) {
             if (c < nchunk) {
@@ -571,34 +612,10 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
               }
             }
           }
+          mx0 = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         } else {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tc::tmem_ld_32x32(tS + 32 * c, v);
-          tmem_ld_wait32(v);
-#pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            mx0 = fmaxf(mx0, __uint_as_float(v[e]));
-            mx1 = fmaxf(mx1, __uint_as_float(v[e + 1]));
-            mx2 = fmaxf(mx2, __uint_as_float(v[e + 2]));
-            mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
-          }
+          mx0 = hf == 0 ? score_bound<0>(tS, bm) : score_bound<1>(tS, bm);
         }
-        if (hf == 0) {
-          uint32_t v[16];
-          tc::tmem_ld_32x16(tS + 64, v);
-          tmem_ld_wait16(v);
-#pragma unroll
-          for (int e = 0; e < 16; e += 4) {
-            mx0 = fmaxf(mx0, __uint_as_float(v[e]));
-            mx1 = fmaxf(mx1, __uint_as_float(v[e + 1]));
-            mx2 = fmaxf(mx2, __uint_as_float(v[e + 2]));
-            mx3 = fmaxf(mx3, __uint_as_float(v[e + 3]));
-          }
-        }
-        }
-        mx0 = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) + (masked_tile ? 0.f : bmax);
         m = mx0;
         sts_f32(exm + (hf * 128 + row) * 4, m);
       }
