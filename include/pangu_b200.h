@@ -140,6 +140,18 @@ int pangu_mlp_ln_residual_bf16(const void* x, const void* w1, const float* b1, c
                                const float* residual, float* x_out, void* x_out_bf16, int64_t M,
                                int32_t C, float eps, void* stream);
 
+/* The whole tail of an EarthSpecificBlock after the window attention in ONE kernel (models/layers.py:481,296-297):
+ *   x1 = x_in + LayerNorm(o . w_proj^T + b_proj) * gamma1 + beta1;   x_out = x1 + LayerNorm(Mlp(x1)) * gamma2 + beta2
+ * i.e. pangu_linear_ln_residual_bf16 followed by pangu_mlp_ln_residual_bf16, bit-identical to that pair, but x1 and its bf16
+ * shadow never reach HBM: the fp32 x1 tile of a CTA lives in `scratch` (fp32 [scratch_rows, C], scratch_rows >= 128 * the
+ * number of SMs; it stays L2-resident), the bf16 x1 tile is written straight into the Mlp's operand tile in shared memory.
+ * o bf16 [M, C] (attention output), w_proj bf16 [C, C], w1 bf16 [4C, C], w2 fp16 [C, 4C]; C = 384. */
+int pangu_attn_proj_mlp_bf16(const void* o, const void* w_proj, const float* b_proj, const float* gamma1,
+                             const float* beta1, const float* x_in, const void* w1, const float* b1, const void* w2,
+                             const float* b2, const float* gamma2, const float* beta2, float* scratch,
+                             int64_t scratch_rows, float* x_out, void* x_out_bf16, int64_t M, int32_t C, float eps1,
+                             float eps2, void* stream);
+
 /* Bring-up aid: copies the fused-Mlp kernel's pipeline timeline (clock64 stamps recorded by CTA 0 when
  * $PANGU_MLP_DBG has bit 16 set) to HOST memory `out` (n <= 512 int64).  Synchronises the device. */
 int pangu_debug_mlp_trace(int64_t* out, int32_t n);

@@ -52,6 +52,7 @@ _PROTOS = {
     "pangu_linear_ln_residual_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p, c_int64, c_int32, c_int32, c_float, c_void_p]),
     "pangu_mlp_ln_residual_bf16": (c_int, [c_void_p] * 10 + [c_int64, c_int32, c_float, c_void_p]),
+    "pangu_attn_proj_mlp_bf16": (c_int, [c_void_p] * 13 + [c_int64, c_void_p, c_void_p, c_int64, c_int32, c_float, c_float, c_void_p]),
     "pangu_debug_mlp_trace": (c_int, [c_void_p, c_int32]),
     "pangu_debug_attn_trace": (c_int, [c_void_p, c_int32]),
     "pangu_window_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(Geom), c_int, c_int,

@@ -46,6 +46,10 @@ int launch_tc_linear_pair(const void* A, long long lda, const void* W, const flo
                           long long ldo, long long M, int K, int N, int act, int out_dtype, void* shadow, cudaStream_t st,
                           void* aux, int aux_mode, float* colsum);
 // tc_mlp.cu
+int launch_tc_attn_proj_mlp(const void* o, const void* wp, const float* bp, const float* gamma1, const float* beta1,
+                            const float* x_in, const void* w1, const float* b1, const void* w2, const float* b2,
+                            const float* gamma2, const float* beta2, float* scratch, long long scratch_rows, float* x_out,
+                            void* x_out_bf16, long long M, int C, float eps1, float eps2, cudaStream_t st);
 int launch_tc_mlp(const void* x, const void* w1, const float* b1, const void* w2, const float* b2,
                   const float* gamma, const float* beta, const float* residual, float* x_out,
                   void* x_out_bf16, long long M, int C, float eps, cudaStream_t st);
@@ -139,6 +143,17 @@ extern "C" int pangu_mlp_ln_residual_bf16(const void* x, const void* w1, const f
                                           int32_t C, float eps, void* stream) {
   if (!x || !w1 || !b1 || !w2 || !b2 || !gamma || !beta || !x_out || M < 0) { set_error("mlp_ln_residual: bad argument"); return PANGU_ERR_BAD_ARG; }
   return launch_tc_mlp(x, w1, b1, w2, b2, gamma, beta, residual, x_out, x_out_bf16, M, C, eps, as_stream(stream));
+}
+
+extern "C" int pangu_attn_proj_mlp_bf16(const void* o, const void* w_proj, const float* b_proj, const float* gamma1,
+                                       const float* beta1, const float* x_in, const void* w1, const float* b1,
+                                       const void* w2, const float* b2, const float* gamma2, const float* beta2,
+                                       float* scratch, int64_t scratch_rows, float* x_out, void* x_out_bf16, int64_t M,
+                                       int32_t C, float eps1, float eps2, void* stream) {
+  if (!o || !w_proj || !b_proj || !gamma1 || !beta1 || !x_in || !w1 || !b1 || !w2 || !b2 || !gamma2 || !beta2 || !scratch ||
+      !x_out || M < 0) { set_error("attn_proj_mlp: bad argument"); return PANGU_ERR_BAD_ARG; }
+  return launch_tc_attn_proj_mlp(o, w_proj, b_proj, gamma1, beta1, x_in, w1, b1, w2, b2, gamma2, beta2, scratch, scratch_rows,
+                                 x_out, x_out_bf16, M, C, eps1, eps2, as_stream(stream));
 }
 
 extern "C" int pangu_window_attention(const void* qkv, const float* qkv_bias, const void* earth_bias,

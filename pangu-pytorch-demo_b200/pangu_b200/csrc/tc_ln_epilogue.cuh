@@ -66,6 +66,10 @@ struct LnTileEpilogue {
   float* x_out;
   __nv_bfloat16* xb;
   long long M, m_base;                               // m_base: global row of this warp's first row
+  long long m_res = -1;                              // row of the residual tensor map to read instead of m_base (>= 0), e.g. a scratch tile
+  uint8_t* umma_x = nullptr;                         // when set: the bf16 result does not leave through tm_xb but is written into this
+                                                     // [C/64][128 rows x 128 B] SW128 K-major operand tile (the x tile of a following GEMM)
+  int x_row0 = 0;                                    // row of this warp's first row inside that operand tile
   float eps, mean, rstd;
   uint8_t* stg;                                      // per warp: UNIT_BYTES (x2 with ASYNC)
   float2* ln_part;                                   // [2 parity][NPART][128]
@@ -81,7 +85,7 @@ struct LnTileEpilogue {
       const int b = idx % NBUF;
       if (lane == 0) {
         mbar_expect_tx(&ld_bar[b], UNIT_BYTES);
-        tma_load_2d(stg + b * UNIT_BYTES, tm_res, &ld_bar[b], u * UW, (int)m_base);
+        tma_load_2d(stg + b * UNIT_BYTES, tm_res, &ld_bar[b], u * UW, (int)(m_res >= 0 ? m_res : m_base));
       }
       __syncwarp();
       return;
@@ -199,6 +203,10 @@ struct LnTileEpilogue {
       if constexpr (TMASTORE) {
         if (tm_xb != nullptr) {                        // 4 bf16 = 8 bytes: half of 16-byte chunk cc >> 1
           uint8_t* pb = stg_bu + stg_b_off(lane, cc >> 1) + (cc & 1) * 8;
+          *reinterpret_cast<uint2*>(pb) = make_uint2(pack_bf16(rr[cc].x, rr[cc].y), pack_bf16(rr[cc].z, rr[cc].w));
+        } else if (umma_x != nullptr) {                // straight into the UMMA operand tile: k-block col / 64, 16-byte chunk
+          const int col = u * UW + 4 * cc, r = x_row0 + lane;           // (col % 64) / 8 XOR-swizzled by the row, 8 bytes per float4
+          uint8_t* pb = umma_x + (col >> 6) * 16384 + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4) + ((col & 7) >> 2) * 8;
           *reinterpret_cast<uint2*>(pb) = make_uint2(pack_bf16(rr[cc].x, rr[cc].y), pack_bf16(rr[cc].z, rr[cc].w));
         }
       }

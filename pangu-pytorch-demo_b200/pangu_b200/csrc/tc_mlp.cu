@@ -60,6 +60,14 @@ struct MlpArgs {
   float* x_out;
   __nv_bfloat16* x_out_bf16;
   float eps;
+  const __nv_bfloat16* x_bf16;  // the kernel's bf16 A operand [M, C] (x, or the attention output o with PROJ): L2 prefetch of the next tile
+  // PROJ variant (attention.linear2 + norm1 + shortcut fused in front, models/layers.py:481,296): the x tile is produced in
+  // shared memory by a LayerNorm phase of its own instead of being loaded
+  const float* bp;              // attention.linear2.bias [C]
+  const float* gamma1;          // norm1 weight / bias (DropPath factor folded in by the caller)
+  const float* beta1;
+  const float* x_in;            // fp32 block input x [M, C]: the residual of norm1
+  float eps1;
   int stagger;   // clocks by which the odd CTA pairs start late: de-phases the HBM-bound LayerNorm epilogues of the pairs
   int dbg;   // bring-up knobs ($PANGU_MLP_DBG): 2 no LN pass 2 (C=384), 32 no LN stores, 4 G1 issues 1 of 4 k-steps, 8 G2 1 of 4
 };
@@ -69,7 +77,7 @@ struct MlpArgs {
 // 4-7 = epilogue warp 4 (h_full passed, H loaded, GELU packed, P stored).  Read with pangu_debug_trace().
 __device__ long long g_mlp_trace[64 * 8];
 
-template <int C>
+template <int C, bool PROJ = false>
 struct MlpCfg {
   static constexpr int KB1 = C / 64;             // 64-wide k-blocks of GEMM1 (K = C)
   static constexpr int NCH = 4 * C / NH;         // hidden chunks per row tile
@@ -92,14 +100,19 @@ struct MlpCfg {
   static constexpr int LN_WARPS = 4 * LN_NPART;
   static constexpr int STG_BYTES = LN_UW * 128 * LN_NBUF;     // per LayerNorm warp: fp32 staging tiles
   static constexpr int STGB_BYTES = LN_UW * 64 * LN_NB16;     // per LayerNorm warp: bf16 staging tiles of the TMA stores
-  static constexpr int PART_BYTES = 2 * LN_NPART * 128 * 8;   // LayerNorm partial sums
-  static constexpr int PARAM_BYTES = 3 * C * 4;      // b2, gamma, beta
+  static constexpr int PART_BYTES = 2 * LN_NPART * 128 * 8 * (PROJ ? 2 : 1);   // LayerNorm partial sums (one set per LayerNorm)
+  static constexpr int PARAM_BYTES = 3 * C * 4 * (PROJ ? 2 : 1);      // b2, gamma, beta (and bp, gamma1, beta1)
+  // PROJ: the first LayerNorm stages its fp32 tiles (the x1 scratch stores) in the weight ring only -- the x tile is being
+  // written with the bf16 x1 -- with one residual tile in flight and two draining
+  static constexpr int LN1_D = 1, LN1_NB16 = 2, LN1_NBUF = 3;
+  static constexpr int STG1_BYTES = LN_UW * 128 * LN1_NBUF;
   static constexpr int EPI_BYTES = (LN_ALIAS ? 0 : LN_WARPS * (STG_BYTES + STGB_BYTES)) + PART_BYTES + PARAM_BYTES;
-  static constexpr int BAR_BYTES = 1024;
+  static constexpr int BAR_BYTES = 2048;
   static constexpr int AVAIL = 227 * 1024 - 1024 - BAR_BYTES - X_BYTES - EPI_BYTES;
   static constexpr int NSLOT = AVAIL / SLOT_BYTES > 8 ? 8 : AVAIL / SLOT_BYTES;
   static constexpr int SMEM_BYTES = 1024 + X_BYTES + NSLOT * SLOT_BYTES + EPI_BYTES + BAR_BYTES;
   static_assert(!LN_ALIAS || LN_WARPS * (STG_BYTES + STGB_BYTES) <= X_BYTES + NSLOT * SLOT_BYTES, "staging must fit in x tile + weight ring");
+  static_assert(!PROJ || (LN_JOIN && LN_WARPS * STG1_BYTES <= NSLOT * SLOT_BYTES), "PROJ: 16 LayerNorm warps, first LayerNorm staged in the weight ring");
   static constexpr int NY = C == 192 ? 2 : 1;    // output accumulators: double-buffered when TMEM has room
   static constexpr int COL_HP = 384;             // two 64-column H/P buffers behind the Y accumulator(s)
   static_assert(C % 192 == 0 && C + 128 <= 512, "C must be 192 or 384");
@@ -107,13 +120,18 @@ struct MlpCfg {
 };
 
 
-template <int C>
+// PROJ = true: tmX is the attention OUTPUT o (bf16 [M, C]); the kernel first computes o . Wp^T into the Y accumulator, a first
+// LayerNorm phase turns it into x1 = x + LN1(. + bp) -- fp32 into a per-CTA scratch tile (tmRes: L2-resident, read back as the
+// residual of the second LayerNorm), bf16 straight into the x tile in shared memory -- and then runs the Mlp as before:
+// x1 and its bf16 shadow never reach HBM (12 of the block tail's 24 bytes per element).
+template <int C, bool PROJ = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
                  const __grid_constant__ CUtensorMap tmXb, const __grid_constant__ CUtensorMap tmRes,
+                 const __grid_constant__ CUtensorMap tmWp, const __grid_constant__ CUtensorMap tmRes1,
                  const MlpArgs a) {
-  using Cfg = MlpCfg<C>;
+  using Cfg = MlpCfg<C, PROJ>;
   constexpr int NSLOT = Cfg::NSLOT, NCH = Cfg::NCH, KB1 = Cfg::KB1, NSPLIT = Cfg::NSPLIT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -124,7 +142,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint8_t* stg_smem = Cfg::LN_ALIAS ? sX : epi_smem;
   uint8_t* stgb_smem = stg_smem + Cfg::LN_WARPS * Cfg::STG_BYTES;
   float2* ln_part = reinterpret_cast<float2*>(epi_smem + (Cfg::LN_ALIAS ? 0 : Cfg::LN_WARPS * (Cfg::STG_BYTES + Cfg::STGB_BYTES)));
-  float* sparams = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ln_part) + Cfg::PART_BYTES);
+  float* sparams = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ln_part) + Cfg::PART_BYTES);   // [3][C] (+ [3][C] of norm1)
+  float2* ln_part1 = ln_part + 2 * Cfg::LN_NPART * 128;       // PROJ: partial sums of the first LayerNorm
+  float* sparams1 = sparams + 3 * C;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
   uint64_t* x_full = bars + 0;
   uint64_t* x_empty = bars + 1;      // MMA -> producer (and LayerNorm warps): every GEMM1 of the row tile has read x  (both CTAs)
@@ -133,11 +153,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* y_full = bars + 6;       // [2]  MMA -> LayerNorm: Y accumulator complete        (both CTAs)
   uint64_t* y_empty = bars + 8;      // [2]  LayerNorm -> MMA: Y accumulator drained         (leader's copy)
   uint64_t* xs_free = bars + 10;     // LayerNorm -> producer: the staging tiles inside the x tile are free (local)
-  uint64_t* w_full = bars + 11;      // [NSLOT]
-  uint64_t* w_empty = bars + 11 + NSLOT;
-  uint64_t* ln_bar = bars + 11 + 2 * NSLOT;      // [LN warps][4] barriers of the residual tile loads
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11 + 2 * NSLOT + 4 * Cfg::LN_WARPS);
-  static_assert((11 + 2 * 8 + 4 * Cfg::LN_WARPS) * 8 + 8 <= Cfg::BAR_BYTES, "barrier area");
+  uint64_t* x1_ready = bars + 11;    // PROJ: LayerNorm 1 -> MMA: the bf16 x1 tile is in shared memory             (leader's copy)
+  uint64_t* ring_free = bars + 12;   // PROJ: LayerNorm 1 -> producer: its staging tiles inside the weight ring are free (local)
+  uint64_t* w_full = bars + 13;      // [NSLOT]
+  uint64_t* w_empty = bars + 13 + NSLOT;
+  uint64_t* ln_bar = bars + 13 + 2 * NSLOT;      // [LN warps][8] barriers of the residual tile loads (4 per LayerNorm)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13 + 2 * NSLOT + 8 * Cfg::LN_WARPS);
+  static_assert((13 + 2 * 8 + 8 * Cfg::LN_WARPS) * 8 + 8 <= Cfg::BAR_BYTES, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                    // 0 = leader of the pair
@@ -150,17 +172,23 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmOut);
     tma_prefetch_desc(&tmRes);
     if (a.x_out_bf16 != nullptr) tma_prefetch_desc(&tmXb);
+    if (PROJ) { tma_prefetch_desc(&tmWp); tma_prefetch_desc(&tmRes1); }
   }
   for (int i = threadIdx.x; i < 3 * C; i += kMlpThreads)      // affine parameters of the row-tile epilogue -> smem
     sparams[i] = i < C ? a.b2[i] : (i < 2 * C ? a.gamma[i - C] : a.beta[i - 2 * C]);
+  if constexpr (PROJ) {
+    for (int i = threadIdx.x; i < 3 * C; i += kMlpThreads)
+      sparams1[i] = i < C ? a.bp[i] : (i < 2 * C ? a.gamma1[i - C] : a.beta1[i - 2 * C]);
+  }
   if (warp == 1 && lane == 0) {
     mbar_init(x_full, 1); mbar_init(x_empty, 1);
     mbar_init(&h_full[0], 1); mbar_init(&h_full[1], 1);
     mbar_init(&p_full[0], 2 * kMlpEpiWarps); mbar_init(&p_full[1], 2 * kMlpEpiWarps);
     for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 2 * Cfg::LN_WARPS); }
     mbar_init(xs_free, Cfg::LN_WARPS);
+    mbar_init(x1_ready, 2 * Cfg::LN_WARPS); mbar_init(ring_free, Cfg::LN_WARPS);
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    for (int i = 0; i < 4 * Cfg::LN_WARPS; ++i) mbar_init(&ln_bar[i], 1);
+    for (int i = 0; i < 8 * Cfg::LN_WARPS; ++i) mbar_init(&ln_bar[i], 1);
     fence_barrier_init();
   }
   cluster_sync_all();                                         // barrier inits visible to the peer CTA
@@ -221,7 +249,27 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const long long r0 = (long long)m0 + lane * 16;
           long long nrows = a.M - r0;
           if (nrows > 16) nrows = 16;
-          if (nrows > 0) prefetch_l2_bulk(a.residual + r0 * C, (uint32_t)(nrows * C * 4));
+          if (nrows > 0) prefetch_l2_bulk((PROJ ? a.x_in : a.residual) + r0 * C, (uint32_t)(nrows * C * 4));
+        }
+        // the NEXT row tile's operand rows -> L2 as well: its load can only be issued after this tile's LayerNorm (the x tile
+        // is LayerNorm staging at C = 384), and an L2 hit shortens that exposed restart (6.8 k -> ~3 k clocks per tile)
+        if (Cfg::LN_ALIAS && lane >= 8 && lane < 16 && pt + npairs < a.pair_tiles) {
+          const long long r0 = (long long)(pt + npairs) * 256 + rank * 128 + (lane - 8) * 16;
+          long long nrows = a.M - r0;
+          if (nrows > 16) nrows = 16;
+          if (nrows > 0) prefetch_l2_bulk(a.x_bf16 + r0 * C, (uint32_t)(nrows * C * 2));
+        }
+        if constexpr (PROJ) {
+          // attention.linear2: Wp k-blocks, laid out exactly like a W2 chunk (rows [192h + 96 rank, +96), k-cols [64kb, +64))
+          for (int kb = 0; kb < KB1; ++kb) {
+            const uint32_t bar = acquire_slot();
+            uint8_t* dst = sW + slot * Cfg::SLOT_BYTES;
+#pragma unroll
+            for (int h = 0; h < NSPLIT; ++h)
+              if (elect_one()) tma_load_2d_cg2(dst + h * 12288, &tmWp, bar, kb * 64, h * 192 + (int)rank * 96);
+            advance();
+          }
+          mbar_wait(ring_free, xphase ^ 1);                   // the first LayerNorm has staged through the ring: wait until it is done
         }
         load_w1(0);
         load_w1(1);
@@ -273,6 +321,38 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int tn = (pt - pair0) / npairs;
           const bool trt = (a.dbg & 16) && blockIdx.x == 0 && lane == 0 && tn >= 1 && tn <= 2;
           if (trt) g_mlp_trace[256 + tn * 16 + 1] = clock64();
+          if constexpr (PROJ) {
+            // Y = o . Wp^T (attention.linear2; K = C, A = the o tile in shared memory, SS form), then the first LayerNorm
+            // replaces the o tile by the bf16 x1 tile
+            constexpr uint32_t idescp = make_idesc_bf16(256, 192, 0, 0);
+            mbar_wait(&y_empty[yb], ((yphase >> yb) & 1) ^ 1);  // the previous row tile's LayerNorm 2 has drained Y
+            yphase ^= 1u << yb;
+            tcgen05_after_sync();
+#pragma unroll 1
+            for (int kb = 0; kb < KB1; ++kb) {
+              mbar_wait(&w_full[slot], wphase);
+              tcgen05_after_sync();
+              const uint32_t sw = smem_u32(sW + slot * Cfg::SLOT_BYTES);
+              if (elect_one()) {
+                const uint64_t da = make_desc_k_sw128(smem_u32(sX) + kb * 16384);
+#pragma unroll
+                for (int h = 0; h < NSPLIT; ++h) {
+                  const uint64_t db = make_desc_k_sw128(sw + h * 12288);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma2_bf16(tmem_base + yb * 192 + h * 192, da + 2 * k, db + 2 * k, idescp, (kb | k) != 0);
+                }
+                umma2_commit_mc(&w_empty[slot]);
+              }
+              __syncwarp();
+              advance();
+            }
+            if (elect_one()) umma2_commit_mc(&y_full[yb]);      // first completion of this row tile: proj done
+            __syncwarp();
+            if (trt) g_mlp_trace[256 + tn * 16 + 11] = clock64();
+            mbar_wait(x1_ready, tn & 1);                        // bf16 x1 is in the x tile (both CTAs)
+            tcgen05_after_sync();
+            if (trt) g_mlp_trace[256 + tn * 16 + 12] = clock64();
+          }
           issue_g1(0);
           issue_g1(1);
           for (int j = 0; j < NCH; ++j) {
@@ -334,8 +414,22 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     ln.x_out = a.x_out; ln.xb = a.x_out_bf16; ln.M = a.M; ln.eps = a.eps;
     ln.tm_out = &tmOut; ln.tm_xb = a.x_out_bf16 != nullptr ? &tmXb : nullptr;
     ln.stg = stg_smem + (is_ln ? lw : 0) * Cfg::STG_BYTES; ln.stg_b = stgb_smem + (is_ln ? lw : 0) * Cfg::STGB_BYTES; ln.sparams = sparams;
-    ln.tm_res = &tmRes; ln.ld_bar = &ln_bar[(is_ln ? lw : 0) * 4];
+    ln.tm_res = &tmRes; ln.ld_bar = &ln_bar[(is_ln ? lw : 0) * 8];
     ln.ln_part = ln_part; ln.q = q; ln.hf = lw >> 2; ln.lane = lane; ln.tile_par = 0;
+    // PROJ: the first LayerNorm of the row tile, x1 = x + LN1(o Wp^T + bp): residual x by TMA from global memory, fp32 result
+    // through the ring-resident staging tiles into this CTA's scratch rows (tmRes), bf16 result into the x tile
+    using Ln1 = LnTileEpilogue<C, Cfg::LN_UW, Cfg::LN1_D, true, true, Cfg::LN1_NB16, Cfg::LN1_NBUF, Cfg::LN_NPART>;
+    Ln1 ln1;
+    if constexpr (PROJ) {
+      ln1.bias = a.bp; ln1.gamma = a.gamma1; ln1.beta = a.beta1; ln1.residual = a.x_in;
+      ln1.x_out = nullptr; ln1.xb = nullptr; ln1.M = a.M; ln1.eps = a.eps1;
+      ln1.tm_out = &tmRes; ln1.tm_xb = nullptr; ln1.umma_x = sX; ln1.x_row0 = q * 32;
+      ln1.stg = sW + lw * Cfg::STG1_BYTES; ln1.stg_b = nullptr; ln1.sparams = sparams1;
+      ln1.tm_res = &tmRes1; ln1.ld_bar = &ln_bar[lw * 8 + 4];
+      ln1.ln_part = ln_part1; ln1.q = q; ln1.hf = lw >> 2; ln1.lane = lane; ln1.tile_par = 0;
+    }
+    const uint32_t x1_ready_L = mapa_u32(smem_u32(x1_ready), 0);
+    const long long scratch_row = (long long)blockIdx.x * 128 + q * 32;   // this warp's rows of the CTA's scratch tile
     const bool ln_store = !(a.dbg & 32);
     int yb = 0;
     // one row tile of GELU work: per hidden chunk  H_j (TMEM) -> +b1, GELU (packed fp16) -> P_j (TMEM, over the warp's own columns)
@@ -376,9 +470,38 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (lane == 0) mbar_arrive_cluster(b ? p_full_L1 : p_full_L0);
       }
     };
+    // PROJ: first LayerNorm of the row tile (see ln1 above)
+    auto ln1_tile = [&](int pt, int tn) {
+      ln1.m_base = scratch_row;                               // fp32 x1 -> scratch rows
+      ln1.m_res = (long long)pt * 256 + rank * 128 + q * 32;  // residual x <- global rows
+      const bool trl = (a.dbg & 16) && blockIdx.x == 0 && warp == kMlpLnWarp0 && lane == 0 && tn >= 1 && tn <= 2;
+      mbar_wait(&y_full[yb], (yphase >> yb) & 1);             // o . Wp^T complete: the o tile and the ring slots are dead
+      yphase ^= 1u << yb;
+      tcgen05_after_sync();
+      if (trl) g_mlp_trace[256 + tn * 16 + 13] = clock64();
+      ln1.prefetch();
+      const uint32_t y = lane_base + yb * 192 * (Cfg::NY - 1);
+      ln1.stats(y);
+      ln1.all_units(y, true);
+      tcgen05_before_sync();                                  // all TMEM reads of Y are done: GEMM2 may accumulate into it
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(yb ? y_empty_L1 : y_empty_L0);
+        tma_store_wait_read();                                // the scratch stores have read the ring-resident staging tiles
+        mbar_arrive(ring_free);
+        mbar_arrive_cluster(x1_ready_L);                      // (every unit fenced its x-tile writes for the async proxy)
+      }
+      __syncwarp();
+      if (trl) g_mlp_trace[256 + tn * 16 + 14] = clock64();
+    };
     // one row tile of LayerNorm work:  Y (TMEM) -> +b2, LayerNorm, + residual -> fp32 + bf16 (tc_ln_epilogue.cuh)
     auto ln_tile = [&](int pt, int tn) {
       ln.m_base = (long long)pt * 256 + rank * 128 + q * 32;
+      if constexpr (PROJ) {
+        ln.m_res = scratch_row;                               // residual x1 <- this CTA's scratch rows, written by ln1_tile:
+        if (lane == 0) tma_store_wait_all();                  // those bulk stores (same thread) are complete, not just read
+        __syncwarp();
+      }
       const bool trl = (a.dbg & 16) && blockIdx.x == 0 && warp == kMlpLnWarp0 && lane == 0 && tn >= 1 && tn <= 2;
       if (!Cfg::LN_ALIAS) ln.prefetch();                      // dedicated staging: the first residual tiles can fly already
       if (trl) g_mlp_trace[256 + tn * 16 + 4] = clock64();
@@ -407,6 +530,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if constexpr (Cfg::LN_JOIN) {
       for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
         const int tn = (pt - pair0) / npairs;
+        if constexpr (PROJ) ln1_tile(pt, tn);
         if (is_gelu) gelu_tile(tn);
         ln_tile(pt, tn);
       }
@@ -424,9 +548,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (warp == 2) tmem_dealloc_cg2(tmem_base, 512);
 }
 
-template <int C>
-static int launch_mlp_t(const void* x, const void* w1, const void* w2, MlpArgs& a, cudaStream_t st) {
-  using Cfg = MlpCfg<C>;
+// PROJ: x = the attention output o; wp = attention.linear2.weight (bf16 [C, C]); scratch = fp32 [>= 128 * grid CTAs, C]
+template <int C, bool PROJ = false>
+static int launch_mlp_t(const void* x, const void* w1, const void* w2, MlpArgs& a, cudaStream_t st, const void* wp = nullptr,
+                        float* scratch = nullptr, long long scratch_rows = 0) {
+  using Cfg = MlpCfg<C, PROJ>;
   CUtensorMap tmX, tmW1, tmW2;
   if (!encode_tmap_2d_bf16(&tmX, x, C, (uint64_t)a.M, (uint64_t)C * 2, 64, 128)) return PANGU_ERR_CUDA;
   if (!encode_tmap_2d_bf16(&tmW1, w1, C, 4 * C, (uint64_t)C * 2, 64, 32)) return PANGU_ERR_CUDA;
@@ -441,17 +567,29 @@ static int launch_mlp_t(const void* x, const void* w1, const void* w2, MlpArgs& 
   }
   CUtensorMap tmRes = tmOut;
   if (a.residual != nullptr && !encode_tmap_2d(&tmRes, 0, a.residual, C, (uint64_t)a.M, (uint64_t)C * 4, UW, 32, UW * 4)) return PANGU_ERR_CUDA;
-  if (a.residual == nullptr) { set_error("mlp_fused<%d>: a residual tensor is required", C); return PANGU_ERR_BAD_ARG; }
+  if (a.residual == nullptr && !PROJ) { set_error("mlp_fused<%d>: a residual tensor is required", C); return PANGU_ERR_BAD_ARG; }
   a.pair_tiles = (int)((a.M + 255) / 256);
-  auto kern = mlp_fused_kernel<C>;
+  a.x_bf16 = reinterpret_cast<const __nv_bfloat16*>(x);
+  const int max_pairs = num_sms() / 2;
+  const int pairs = a.pair_tiles < max_pairs ? a.pair_tiles : max_pairs;
+  CUtensorMap tmWp = tmW2, tmRes1 = tmRes;
+  if constexpr (PROJ) {
+    if (wp == nullptr || scratch == nullptr || a.x_in == nullptr || scratch_rows < 256LL * pairs) {
+      set_error("attn_proj_mlp<%d>: missing operand or scratch smaller than %lld rows", C, 256LL * pairs);
+      return PANGU_ERR_BAD_ARG;
+    }
+    if (!encode_tmap_2d_bf16(&tmWp, wp, C, C, (uint64_t)C * 2, 64, 96)) return PANGU_ERR_CUDA;
+    if (!encode_tmap_2d(&tmRes1, 0, a.x_in, C, (uint64_t)a.M, (uint64_t)C * 4, UW, 32, UW * 4)) return PANGU_ERR_CUDA;
+    // the second LayerNorm's residual is x1 in the scratch tiles (row = CTA * 128 + row of the tile)
+    if (!encode_tmap_2d(&tmRes, 0, scratch, C, (uint64_t)scratch_rows, (uint64_t)C * 4, UW, 32, UW * 4)) return PANGU_ERR_CUDA;
+  }
+  auto kern = mlp_fused_kernel<C, PROJ>;
   static unsigned long long configured = 0;
   {
     cudaError_t e = pangu::set_max_smem_once(configured, kern, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("mlp_fused<%d>: cudaFuncSetAttribute(%d B): %s", C, Cfg::SMEM_BYTES, cudaGetErrorString(e)); return PANGU_ERR_CUDA; }
   }
-  const int max_pairs = num_sms() / 2;
-  const int pairs = a.pair_tiles < max_pairs ? a.pair_tiles : max_pairs;
-  cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(kMlpThreads), Cfg::SMEM_BYTES, st, tmX, tmW1, tmW2, tmOut, tmXb, tmRes, a);
+  cudaError_t le = launch_pdl(kern, dim3(2 * pairs), dim3(kMlpThreads), Cfg::SMEM_BYTES, st, tmX, tmW1, tmW2, tmOut, tmXb, tmRes, tmWp, tmRes1, a);
   if (le != cudaSuccess) { set_error("mlp_fused: launch: %s", cudaGetErrorString(le)); return PANGU_ERR_CUDA; }
   return check_launch("mlp_fused");
 }
@@ -484,6 +622,27 @@ int launch_tc_mlp(const void* x, const void* w1, const float* b1, const void* w2
   if (C == 384) return tc::launch_mlp_t<384>(x, w1, w2, a, st);
   set_error("mlp_ln_residual(bf16): C=%d unsupported (192/384)", C);
   return PANGU_ERR_UNSUPPORTED;
+}
+
+
+// attention.linear2 + norm1 + shortcut + Mlp + norm2 + shortcut in ONE kernel (the tail of an EarthSpecificBlock after the
+// window attention, models/layers.py:481,296-297).  C = 384 only (stage B: 12 of the 16 blocks).
+int launch_tc_attn_proj_mlp(const void* o, const void* wp, const float* bp, const float* gamma1, const float* beta1,
+                            const float* x_in, const void* w1, const float* b1, const void* w2, const float* b2,
+                            const float* gamma2, const float* beta2, float* scratch, long long scratch_rows, float* x_out,
+                            void* x_out_bf16, long long M, int C, float eps1, float eps2, cudaStream_t st) {
+  if (M == 0) return PANGU_OK;
+  if (C != 384) { set_error("attn_proj_mlp(bf16): C=%d unsupported (384)", C); return PANGU_ERR_UNSUPPORTED; }
+  tc::MlpArgs a{};
+  a.M = M; a.b1 = b1; a.b2 = b2; a.gamma = gamma2; a.beta = beta2; a.residual = nullptr;
+  a.bp = bp; a.gamma1 = gamma1; a.beta1 = beta1; a.x_in = x_in; a.eps1 = eps1;
+  a.x_out = x_out; a.x_out_bf16 = reinterpret_cast<__nv_bfloat16*>(x_out_bf16); a.eps = eps2;
+  const char* dbg = getenv("PANGU_MLP_DBG");
+  a.dbg = dbg ? atoi(dbg) : 0;
+  const char* stg = getenv("PANGU_MLP_STAGGER");
+  const long long tiles = (M + 255) / 256;
+  a.stagger = stg ? atoi(stg) : (tiles >= 4LL * (tc::num_sms() / 2) ? 20000 : 0);
+  return tc::launch_mlp_t<384, true>(o, w1, w2, a, st, wp, scratch, scratch_rows);
 }
 
 }  // namespace pangu

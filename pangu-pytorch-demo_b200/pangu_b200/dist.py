@@ -211,6 +211,14 @@ class _Worker:
         if o_first is not None:                          # rows 0..2 of this band were computed by the northern neighbour
             hr, W = self.plan.nrows(stage), TOK_W[stage]
             self.o.view(Z, hr, W, self.o.shape[-1])[:, :3].copy_(o_first.view(Z, 3, W, self.o.shape[-1]))
+        if PF.FUSED_MLP and PF.FUSED_PROJ and self.o.shape[-1] == 384:
+            self.x, self.xb = ops.attn_proj_mlp_ln_bf16(
+                self.o, wc.bf16("a2", PF.lin_w(att.linear2)), PF._f(PF.lin_b(att.linear2)), PF._f(blk.norm1.weight),
+                PF._f(blk.norm1.bias), self.x, wc.bf16("m1", PF.lin_w(mlp.linear1)), PF._f(PF.lin_b(mlp.linear1)),
+                wc.f16("m2h", PF.lin_w(mlp.linear2)), PF._f(PF.lin_b(mlp.linear2)), PF._f(blk.norm2.weight),
+                PF._f(blk.norm2.bias), eps1=blk.norm1.eps, eps2=blk.norm2.eps)
+            self.o = self.halo_o = None
+            return
         x1, x1b = ops.linear_ln_residual_bf16(self.o, wc.bf16("a2", PF.lin_w(att.linear2)), PF._f(PF.lin_b(att.linear2)),
                                               PF._f(blk.norm1.weight), PF._f(blk.norm1.bias), self.x, eps=blk.norm1.eps)
         self.o = self.halo_o = None

@@ -18,6 +18,8 @@ from .abi import ACT_GELU, ACT_NONE, ROLL_NONE, ROLL_SHIFT, WINDOWED, PanguError
 MODES = ("fp32", "bf16")
 # bf16 mode: Mlp + norm2 + residual as ONE tcgen05 kernel (0 = two GEMM kernels; kept for A/B measurements)
 FUSED_MLP = os.environ.get("PANGU_B200_FUSED_MLP", "1") != "0"
+# bf16 mode, C = 384: attention.linear2 + norm1 + shortcut fused IN FRONT of the Mlp kernel (x1 never reaches HBM); 0 = two kernels
+FUSED_PROJ = os.environ.get("PANGU_B200_FUSED_PROJ", "1") != "0"
 
 
 def default_mode():
@@ -230,6 +232,12 @@ def block_forward(blk, x, Z, H, W, roll, mode, xb=None, s1=1.0, s2=1.0):
                                          prescaled=True, exact_max=attention_exact_max(att, wc))
         del qkv
         g1, b1 = _affine(blk.norm1, s1)
+        if FUSED_MLP and FUSED_PROJ and s2 != 0.0 and x.shape[-1] == 384:
+            g2, b2 = _affine(blk.norm2, s2)
+            return ops.attn_proj_mlp_ln_bf16(o, wc.bf16("a2", lin_w(att.linear2)), _f(lin_b(att.linear2)), g1, b1, x,
+                                             wc.bf16("m1", lin_w(mlp.linear1)), _f(lin_b(mlp.linear1)),
+                                             wc.f16("m2h", lin_w(mlp.linear2)), _f(lin_b(mlp.linear2)), g2, b2,
+                                             eps1=blk.norm1.eps, eps2=blk.norm2.eps)
         x1, x1b = ops.linear_ln_residual_bf16(o, wc.bf16("a2", lin_w(att.linear2)), _f(lin_b(att.linear2)), g1, b1, x,
                                               eps=blk.norm1.eps)
         del o

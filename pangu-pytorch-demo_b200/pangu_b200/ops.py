@@ -238,6 +238,34 @@ def mlp_ln_residual_bf16(xb, w1, b1, w2, b2, gamma, beta, residual, want_bf16=Tr
     return x_out, xo_b
 
 
+_SCRATCH = {}         # (device, C) -> fp32 [128 * SMs, C] x1 scratch of attn_proj_mlp_ln_bf16 (29 MB at C = 384: L2-resident)
+SCRATCH_ROWS = 128 * 160
+
+
+def attn_proj_mlp_ln_bf16(o, w_proj, b_proj, gamma1, beta1, x_in, w1, b1, w2, b2, gamma2, beta2, eps1=1e-5, eps2=1e-5,
+                          want_bf16=True):
+    """x1 = x_in + LN(o @ w_proj.T + b_proj) * gamma1 + beta1;  out = x1 + LN(gelu(x1 @ w1.T + b1) @ w2.T + b2) * gamma2 + beta2
+    in ONE kernel (C = 384): linear_ln_residual_bf16 + mlp_ln_residual_bf16 without the HBM round trip of x1."""
+    _chk(o, torch.bfloat16, "o")
+    _chk(w_proj, torch.bfloat16, "w_proj")
+    _chk(w1, torch.bfloat16, "w1")
+    _chk(w2, torch.float16, "w2 (the GELU output / second GEMM run in fp16)")
+    _chk(x_in, torch.float32, "x_in")
+    M, C = o.shape
+    assert w_proj.shape == (C, C) and w1.shape == (4 * C, C) and w2.shape == (C, 4 * C) and x_in.shape == (M, C)
+    key = (o.device, C)
+    scratch = _SCRATCH.get(key)
+    if scratch is None:
+        scratch = _SCRATCH[key] = torch.empty((SCRATCH_ROWS, C), dtype=torch.float32, device=o.device)
+    x_out = torch.empty((M, C), dtype=torch.float32, device=o.device)
+    xo_b = torch.empty((M, C), dtype=torch.bfloat16, device=o.device) if want_bf16 else None
+    _call("attn_proj_mlp_bf16[C=%d]" % C, "pangu_attn_proj_mlp_bf16",
+          (_ptr(o), _ptr(w_proj), _ptr(b_proj), _ptr(gamma1), _ptr(beta1), _ptr(x_in), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2),
+           _ptr(gamma2), _ptr(beta2), _ptr(scratch), SCRATCH_ROWS, _ptr(x_out), _ptr(xo_b), M, C, eps1, eps2, _stream(),),
+          flops=18.0 * M * C * C, nbytes=float(M * C * (2 + 4 + 4 + 2 * want_bf16) + 18 * C * C))
+    return x_out, xo_b
+
+
 def window_attention(qkv, qkv_bias, earth_bias, Z, H, W, heads, mode):
     """qkv [N, 3C] (token order, or window order when mode == WINDOWED) -> [N, C]."""
     _chk(qkv, name="qkv")

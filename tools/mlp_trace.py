@@ -19,8 +19,13 @@ w1 = (torch.randn(4 * C, C, device="cuda", generator=g) * 0.05).bfloat16()
 w2 = (torch.randn(C, 4 * C, device="cuda", generator=g) * 0.05).half()
 b1, b2 = torch.zeros(4 * C, device="cuda"), torch.zeros(C, device="cuda")
 ga, be = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+PROJ = len(sys.argv) > 2 and sys.argv[2] == "proj"
+wp = (torch.randn(C, C, device="cuda", generator=g) * 0.05).bfloat16()
 for _ in range(3):
-    ops.mlp_ln_residual_bf16(xb, w1, b1, w2, b2, ga, be, x)
+    if PROJ:
+        ops.attn_proj_mlp_ln_bf16(xb, wp, b2, ga, be, x, w1, b1, w2, b2, ga, be)
+    else:
+        ops.mlp_ln_residual_bf16(xb, w1, b1, w2, b2, ga, be, x)
 torch.cuda.synchronize()
 buf = (ctypes.c_int64 * 512)()
 abi.check(abi.lib().pangu_debug_mlp_trace(ctypes.cast(buf, ctypes.c_void_p), 512), "trace")
@@ -33,7 +38,8 @@ for j in range(nch):
 
 print("tile-level events of CTA 0, row tiles 1 and 2 (cycles since tile 1's x load was issued):")
 names = ["x load issued", "x_full passed (MMA)", "y_empty passed (MMA)", "y_full committed (MMA issue)", "LN: x_empty passed", "LN: y_full passed",
-         "LN: stats done", "LN: units done", "LN: stores read, xs_free", "GELU: first h_full", "GELU: last h_full"]
+         "LN: stats done", "LN: units done", "LN: stores read, xs_free", "GELU: first h_full", "GELU: last h_full",
+         "PROJ: proj MMAs issued", "PROJ: x1_ready passed (MMA)", "PROJ: LN1 y_full passed", "PROJ: LN1 done"]
 base = buf[256 + 16]
 for n in (1, 2):
     for k, nm in enumerate(names):
