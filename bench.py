@@ -38,15 +38,16 @@ FLOPS_TOTAL = 8.421e12            # algorithmic FLOPs of one forwar
 FLOPS_ATTN_MLP = 8.132e12         # attention + MLP blocks
 
 
-TRAFFIC_FILE = "profiles/r2_ncu_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")) \
-    else "profiles/r1_ncu_traffic.json"
+TRAFFIC_FILE = next((f for f in ("profiles/r2c_ncu_traffic.json", "profiles/r2b_ncu_traffic.json", "profiles/r2_ncu_traffic.json")
+                     if os.path.exists(os.path.join(ROOT, f))), "profiles/r1_ncu_traffic.json")   # newest committed capture
 
 
 def ncu_traffic(kernel_tag):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     (dram__bytes_read.sum + dram__bytes_write.sum of the un-sharded, full-grid launch), or None."""
     p = os.path.join(ROOT, TRAFFIC_FILE)
-    want = {"mlp_fused_bf16[C=384]": ("tc::mlp_fused_kernel<384>", 148), "mlp_fused_bf16[C=192]": ("tc::mlp_fused_kernel<192>", 148)}
+    want = {"mlp_fused_bf16[C=384]": ("tc::mlp_fused_kernel<384, 0>", 148), "mlp_fused_bf16[C=192]": ("tc::mlp_fused_kernel<192, 0>", 148),
+            "attn_proj_mlp_bf16[C=384]": ("tc::mlp_fused_kernel<384, 1>", 148)}
     if kernel_tag not in want or not os.path.exists(p):
         return None
     name, grid = want[kernel_tag]
@@ -613,7 +614,7 @@ def main():
                        "tflops": (v[2] / (v[1] / 1000.0) / 1e12) if v[1] > 0 and v[2] > 0 else None,
                        "gbs": (v[3] / (v[1] / 1000.0) / 1e9) if v[1] > 0 and v[3] > 0 else None}
                    for k, v in sorted(table.items(), key=lambda kv: -kv[1][1])}
-        gemm = {k: v for k, v in table.items() if k.startswith("gemm") or k.startswith("mlp_fused")}
+        gemm = {k: v for k, v in table.items() if k.startswith("gemm") or k.startswith("mlp_fused") or k.startswith("attn_proj_mlp")}
         if gemm:
             dom = max(gemm, key=lambda k: gemm[k][1])
             calls, tms, fl, _ = gemm[dom]
