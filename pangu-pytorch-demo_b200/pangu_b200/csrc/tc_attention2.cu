@@ -50,7 +50,14 @@ constexpr int kTailWarps = 4;
 constexpr int kWarpTma = 16, kWarpMma = 17, kWarpPv = 18, kWarpTail0 = 20;   // warp 19 only fills the warpgroup
 constexpr int kThreads = (kWarpTail0 + kTailWarps) * 32;           // 768 = 6 warpgroups
 constexpr int kConsumers = (kSoftmaxWarps + kTailWarps) * 32;      // 640 threads read the bias tile
-constexpr int kStages = 6;
+#ifndef PANGU_ATTN_STAGES
+#define PANGU_ATTN_STAGES 4
+#endif
+// Ring depth.  Measured (tools/gpu_exp_attn2.sh, same box): 4 stages are 5 % FASTER than 6 (0.284 / 0.322 vs 0.299 / 0.335 ms at
+// C = 192, 0.168 / 0.200 vs 0.180 / 0.207 ms at C = 384): three windows are in flight between the S / softmax / PV buffers
+// anyway, and a producer that runs further ahead only spreads the CTAs of a team over more windows (their 64-byte head
+// slices then hit different DRAM bursts).  One stage per tail warp.
+constexpr int kStages = PANGU_ATTN_STAGES;
 #ifdef PANGU_ATTN_TRACE
 constexpr bool kTrace = true;                      // clock64 stamps of CTA 0 (costs registers in the softmax loop)
 #else
@@ -117,6 +124,19 @@ __device__ __forceinline__ void add_bias2(uint32_t w, float& s0, float& s1) {
   asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.bf16 %0, lo, %0;\n\tadd.rn.f32.bf16 %1, hi, %1;\n\t}"
       : "+f"(s0), "+f"(s1) : "r"(w));
 }
+// (s0, s1) += (b0, b1) as ONE packed fp32 instruction (sm_100 FADD2: two fp32 lanes per issue slot)
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+// bf16 pair by TRUNCATION: one PRMT on the ALU pipe instead of an F2FP, which shares the 16-lane XU pipe with the MUFU.EX2 of
+// the same loop (r2 ncu: the MUFUs of pass 2 stall on the MIO queue).  Against round-to-nearest the truncated value is low
+// by u * ulp, u uniform in [0, 1): the mean, 0.5 ulp = 2^-8 * E[1 / mantissa] = 0.2818 %, is the same for every key and comes
+// back as one factor on 1 / rowsum (kTruncFix); what is left is the same +-0.5 ulp noise as rounding has.
+__device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
+}
+constexpr float kTruncFix = 1.0028260f;
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
@@ -532,7 +552,7 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       tc::tmem_ld_32x16(tmem_base + lane_addr + kColO + 32 * (i & 1) + hf * 16, o);
       const uint32_t exs = exg + (slot * 512 + 256 + row) * 4;
       const float sum = lds_f32(exs) + lds_f32(exs + 512);
-      const float inv = 1.0f / sum;
+      const float inv = kTruncFix / sum;                        // P was truncated to bf16 (pack_bf16_trunc)
       tmem_ld_wait16(o);
       if (tokc >= 0) {
         uint4 a, c;
@@ -643,10 +663,10 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
             for (int e = 0; e < 8; ++e) {
               float s0 = __uint_as_float(v[2 * e]), s1 = __uint_as_float(v[2 * e + 1]);
               add_bias2(bw[e], s0, s1);
-              const float e0 = ex2(s0 - m), e1 = ex2(s1 - m);
-              sm0 += e0;
-              sm1 += e1;
-              pk[e] = pack_bf16(e0, e1);
+              add2(s0, s1, -m, -m);
+              const float e0 = ex2(s0), e1 = ex2(s1);
+              add2(sm0, sm1, e0, e1);
+              pk[e] = pack_bf16_trunc(e0, e1);
             }
             tmem_st_32x8(tS + 8 * c, pk);
           }

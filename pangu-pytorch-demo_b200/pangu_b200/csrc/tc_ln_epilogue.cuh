@@ -75,6 +75,7 @@ struct LnTileEpilogue {
   float2* ln_part;                                   // [2 parity][NPART][128]
   int q, hf, lane;
   uint32_t tile_par;
+  uint64_t out_hint = 0, res_hint = 0;               // L2 cache-hint policies of the fp32 tile stores / residual tile loads (0 = none)
   long long* dbg = nullptr;                          // bring-up: 6 clock64 stamps per unit when non-null
   float4 rg[ASYNC ? 1 : D][ASYNC ? 1 : NV];
 
@@ -85,7 +86,8 @@ struct LnTileEpilogue {
       const int b = idx % NBUF;
       if (lane == 0) {
         mbar_expect_tx(&ld_bar[b], UNIT_BYTES);
-        tma_load_2d(stg + b * UNIT_BYTES, tm_res, &ld_bar[b], u * UW, (int)(m_res >= 0 ? m_res : m_base));
+        if (res_hint) tma_load_2d_hint(stg + b * UNIT_BYTES, tm_res, &ld_bar[b], u * UW, (int)(m_res >= 0 ? m_res : m_base), res_hint);
+        else tma_load_2d(stg + b * UNIT_BYTES, tm_res, &ld_bar[b], u * UW, (int)(m_res >= 0 ? m_res : m_base));
       }
       __syncwarp();
       return;
@@ -217,7 +219,8 @@ struct LnTileEpilogue {
       __syncwarp();
       if (dbg) dbg[4] = clock64();
       if (lane == 0 && store) {
-        tma_store_2d(tm_out, stg_u, u * UW, (int)m_base);
+        if (out_hint) tma_store_2d_hint(tm_out, stg_u, u * UW, (int)m_base, out_hint);
+        else tma_store_2d(tm_out, stg_u, u * UW, (int)m_base);
         if (tm_xb != nullptr) tma_store_2d(tm_xb, stg_bu, u * UW, (int)m_base);
         tma_store_commit();
       }

@@ -69,7 +69,7 @@ struct MlpArgs {
   const float* x_in;            // fp32 block input x [M, C]: the residual of norm1
   float eps1;
   int stagger;   // clocks by which the odd CTA pairs start late: de-phases the HBM-bound LayerNorm epilogues of the pairs
-  int dbg;   // bring-up knobs ($PANGU_MLP_DBG): 2 no LN pass 2 (C=384), 32 no LN stores, 4 G1 issues 1 of 4 k-steps, 8 G2 1 of 4
+  int dbg;   // bring-up knobs ($PANGU_MLP_DBG): 2 no LN pass 2 (C=384), 32 no LN stores, 4 G1 issues 1 of 4 k-steps, 8 G2 1 of 4, 128 no L2 evict_last hint on the x1 scratch (PROJ)
 };
 
 // Bring-up timeline: with dbg bit 16 set, CTA 0 records clock64() at pipeline events of its SECOND row tile (steady state).
@@ -427,6 +427,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       ln1.stg = sW + lw * Cfg::STG1_BYTES; ln1.stg_b = nullptr; ln1.sparams = sparams1;
       ln1.tm_res = &tmRes1; ln1.ld_bar = &ln_bar[lw * 8 + 4];
       ln1.ln_part = ln_part1; ln1.q = q; ln1.hf = lw >> 2; ln1.lane = lane; ln1.tile_par = 0;
+      // the x1 scratch tile (128 rows x C fp32 per CTA, 29 MB over the grid) is rewritten every row tile: pin it in the L2
+      // (r2 ncu: without the hint 178 of its 201 MB per launch were evicted to DRAM by the streaming traffic and 52 MB re-read)
+      if (!(a.dbg & 128)) { ln1.out_hint = l2_policy_evict_last(); ln.res_hint = ln1.out_hint; }
     }
     const uint32_t x1_ready_L = mapa_u32(smem_u32(x1_ready), 0);
     const long long scratch_row = (long long)blockIdx.x * 128 + q * 32;   // this warp's rows of the CTA's scratch tile
