@@ -100,6 +100,24 @@ def test_attention_bf16_vs_fp32_kernel(Z, H, W, C, heads, roll):
     assert orc.rel_l2(got.float().cpu(), want.cpu()) <= 6e-3      # P and the output are rounded to bf16
 
 
+def test_attention_truncated_probabilities_are_unbiased():
+    """The tcgen05 kernel packs P to bf16 by truncation (PRMT instead of F2FP, tc_attention2.cu) and multiplies 1 / rowsum by the
+    mean truncation loss (kTruncFix = 1.002826): the output must carry no magnitude bias against the fp32 kernel -- a missing
+    correction shows up as -2.8e-3 here, a doubled one as +2.8e-3."""
+    from pangu_b200 import ops
+    Z, H, W, C, heads = 8, 91, 24, 384, 12
+    g = torch.Generator().manual_seed(12)
+    T = (Z // 2) * ((H + 5) // 6)
+    qkv = torch.randn(Z * H * W, 3 * C, generator=g).bfloat16()
+    qb = torch.randn(3 * C, generator=g) * 0.1
+    eb = (torch.randn(T, heads, 144, 144, generator=g) * 0.5).bfloat16()
+    for roll in (0, 1):
+        want = ops.window_attention(qkv.float().cuda(), qb.bfloat16().float().cuda(), eb.float().cuda(), Z, H, W, heads, roll).double()
+        got = ops.window_attention(qkv.cuda(), qb.cuda(), eb.cuda(), Z, H, W, heads, roll).double()
+        bias = float(((got - want) * torch.sign(want)).sum() / want.abs().sum())
+        assert abs(bias) <= 5e-4, f"roll {roll}: signed magnitude bias {bias:.2e}"
+
+
 @pytest.mark.parametrize("tag,dim,heads,Z,H,W,pfx", [
     ("blockA", 192, 6, 8, 181, 24, "layers.EarthSpecificLayer0.blocks.EarthSpecificBlock1."),
     ("blockB", 384, 12, 8, 91, 24, "layers.EarthSpecificLayer1.blocks.EarthSpecificBlock3."),
