@@ -409,6 +409,9 @@ def main():
                          "ctypes launches per step")
     ap.add_argument("--scheme", default="redundant", choices=["redundant", "sendback"],
                     help="halo exchange scheme of --mode bands (pangu_b200/dist.py)")
+    ap.add_argument("--e2e-depth", type=int, default=0,
+                    help="slots (captured graphs + pinned output buffers) of the streamed e2e leg; 0 = 2 on one GPU, 3 for bands")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind each rank's host thread to its GPU's NUMA node")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-times", action="store_true")
     args = ap.parse_args()
@@ -454,6 +457,11 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_cpus = None
+    if world > 1 and not args.no_numa_bind:
+        # one process per GPU: bind each rank to its GPU's NUMA node BEFORE any pinned buffer exists (see prefetch.py)
+        from pangu_b200.prefetch import bind_host_thread_to_gpu
+        numa_cpus = bind_host_thread_to_gpu(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -563,7 +571,10 @@ def main():
         # (every sample still pays both of its transfers inside the timed region)
         from pangu_b200.pipeline import StreamedForecaster
         try:
-            streamer = StreamedForecaster(forward, (d_inp, d_inp_s, stats, maps, const_h))
+            # bands: every replay holds NCCL halo swaps, so one rank whose host thread blocks (slot re-use waits for that slot's
+            # D2H) delays all of them; a third slot keeps the host a full step ahead of the device on every rank
+            depth = args.e2e_depth if args.e2e_depth > 0 else (3 if (world > 1 and mode == "bands") else 2)
+            streamer = StreamedForecaster(forward, (d_inp, d_inp_s, stats, maps, const_h), depth=depth)
         except Exception as exc:                                  # noqa: BLE001
             sys.stderr.write(f"[bench] StreamedForecaster unavailable on rank {rank} ({type(exc).__name__}: {exc})\n")
         if world > 1:
@@ -658,10 +669,11 @@ def main():
                 "dtype": args.dtype, "data": "synthetic (seeded random-init weights, ERA5-shaped inputs)", "config": config,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps,
+                        "host_thread_numa_bound_cpus": len(numa_cpus) if numa_cpus else None,
                         "transfers_alone": {"h2d_ms": h2d_ms, "d2h_ms": d2h_ms, "h2d_gbs": h2d / h2d_ms / 1e6, "d2h_gbs": d2h / d2h_ms / 1e6,
                                             "note": "one step's pinned-host copies timed alone, all ranks at once, max over ranks"},
                         "api": ("pangu_b200.pipeline.StreamedForecaster(PanguModel / BandedPangu): pinned host in -> pinned host out, "
-                                "transfers of neighbouring samples overlap the forward" if streamer is not None else
+                                "transfers of neighbouring samples overlap the forward, %d slots" % streamer.depth if streamer is not None else
                                 "models.pangu_model.PanguModel.forward on pinned host inputs, serial H2D / forward / D2H")},
                 "gpu_launches": launches, "launch_used": launch_used, "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "band_check": band_check, "kernels": kernels, "tflops_model_per_gpu": FLOPS_TOTAL * value / world / 1e12}
