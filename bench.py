@@ -410,7 +410,7 @@ def main():
     ap.add_argument("--scheme", default="redundant", choices=["redundant", "sendback"],
                     help="halo exchange scheme of --mode bands (pangu_b200/dist.py)")
     ap.add_argument("--e2e-depth", type=int, default=0,
-                    help="slots (captured graphs + pinned output buffers) of the streamed e2e leg; 0 = 2 on one GPU, 3 for bands")
+                    help="slots (captured graphs + pinned output buffers) of the streamed e2e leg; 0 = 2")
     ap.add_argument("--no-numa-bind", action="store_true", help="N > 1: do not bind each rank's host thread to its GPU's NUMA node")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-times", action="store_true")
@@ -571,9 +571,9 @@ def main():
         # (every sample still pays both of its transfers inside the timed region)
         from pangu_b200.pipeline import StreamedForecaster
         try:
-            # bands: every replay holds NCCL halo swaps, so one rank whose host thread blocks (slot re-use waits for that slot's
-            # D2H) delays all of them; a third slot keeps the host a full step ahead of the device on every rank
-            depth = args.e2e_depth if args.e2e_depth > 0 else (3 if (world > 1 and mode == "bands") else 2)
+            # (a third slot -- the host a full step ahead of the device on every rank -- measured neutral in band mode at 4 GPUs:
+            # profiles/r2_e2e_bands_transfers.md)
+            depth = args.e2e_depth if args.e2e_depth > 0 else 2
             streamer = StreamedForecaster(forward, (d_inp, d_inp_s, stats, maps, const_h), depth=depth)
         except Exception as exc:                                  # noqa: BLE001
             sys.stderr.write(f"[bench] StreamedForecaster unavailable on rank {rank} ({type(exc).__name__}: {exc})\n")
