@@ -129,8 +129,9 @@ __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
   asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
       : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
 }
-// bf16 pair by TRUNCATION: one PRMT on the ALU pipe instead of an F2FP, which shares the 16-lane XU pipe with the MUFU.EX2 of
-// the same loop (r2 ncu: the MUFUs of pass 2 stall on the MIO queue).  Against round-to-nearest the truncated value is low
+// bf16 pair by TRUNCATION: one full-rate PRMT instead of an F2FP (measured -3 % on the kernel together with the FADD2 adds; the
+// XU-pipe share in ncu did not change, so the F2FP was not XU work -- it simply issues slower).  Against round-to-nearest the
+// truncated value is low
 // by u * ulp, u uniform in [0, 1): the mean, 0.5 ulp = 2^-8 * E[1 / mantissa] = 0.2818 %, is the same for every key and comes
 // back as one factor on 1 / rowsum (kTruncFix); what is left is the same +-0.5 ulp noise as rounding has.
 __device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
