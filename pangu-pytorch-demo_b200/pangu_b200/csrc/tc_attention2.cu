@@ -16,8 +16,9 @@
 //              two passes over its TMEM columns in 16-column chunks: max of S + bias (+ mask), then exp2 -> bf16 P
 //              written back over its OWN first columns (tcgen05.st), so no registers hold a whole row.  The bf16 bias
 //              is added with the mixed-precision add (one FHADD.BF16 per score, no unpacking).
-//   O = P V    tcgen05.mma, A = P from TMEM (TS form), B = V from smem (MN-major), N=32 K=144; three S/P buffers and two
-//              O buffers, S and PV issued by different warps, so S(i+2) is complete long before its group needs it
+//   O = P V    tcgen05.mma, A = P from TMEM (TS form), B = V from smem (MN-major), N=32 K=144; every softmax group owns an S,
+//              a P and an O buffer (2 x (144 + 72 + 32) = 496 TMEM columns): S(i+2) is issued the moment the group has
+//              READ S(i) and completes under the group's epilogue of window i-2; S and PV are issued by different warps
 //   epilogue   of window i-2 inside pass 2 of window i: 16 columns per thread -> one 32-byte sector at the un-rolled
 //              token position
 //   rows 128..143  (they do not fit M=128) run on four "tail" warps with mma.sync fragments on the same smem tiles,
@@ -66,8 +67,10 @@ constexpr bool kTrace = false;
 constexpr int kBiasBytes = 44032;                  // 144 x 152 bf16 = 43 776, padded to a multiple of 1024
 constexpr int kBufBytes = 3 * kTileBytes;          // q, k, v: 27 648 = 27 x 1024
 constexpr int kTmemCols = 512;
-constexpr int kColS = 144;                         // S/P buffer b (3 of them): columns [144 b, 144 b + 144)
-constexpr int kColO = 432;                         // O buffer k (2 of them): columns [432 + 32 k, +32)
+// TMEM: every softmax group g (= window parity) owns one S buffer, one P buffer and one O buffer
+constexpr int kColS = 144;                         // S of group g: columns [144 g, 144 g + 144), fp32
+constexpr int kColP = 288;                         // P of group g: columns [288 + 72 g, +72), bf16 pairs (keys 0..79 | 80..143)
+constexpr int kColO = 432;                         // O of group g: columns [432 + 32 g, +32), fp32
 constexpr int kKeys0 = 80;                         // key split between the two threads of a score row: 80 + 64
 constexpr int kRunBytes = 12 * 64;                 // one run of 12 tokens x 32 channels
 constexpr int kBiasTileBytes = kWinTokens * kWinTokens * 2;
@@ -340,13 +343,11 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
   uint64_t* full = bars;                 // [6] TMA -> MMA / tail warp (tx bytes)
   uint64_t* empty = bars + 6;            // [6] 1 (tcgen05.commit after PV) + 1 (tail warp)
-  uint64_t* s_full = bars + 12;          // [3] S(i) complete in TMEM buffer i % 3
-  uint64_t* p_full = bars + 15;          // [3] P(i) written (8 warps)
-  uint64_t* o_full = bars + 18;          // [3] PV(i) complete: S/P buffer i % 3 may take S(i + 3)
-  uint64_t* o_rdy = bars + 21;           // [2] PV(i) complete: O buffer i & 1 may be read by the epilogue.  (Two barriers
-                                         // for one event: each must be unable to complete twice before its waiter looks --
-                                         // the next PV into O buffer i & 1 needs this epilogue's group, the next PV out of
-                                         // S/P buffer i % 3 needs the S that waits on o_full.)
+  // per softmax group g = i & 1 (the k-th window of a group completes phase k of each of its barriers):
+  uint64_t* s_full = bars + 12;          // [2] S(i) complete in S_g                                   (S issuer -> group)
+  uint64_t* s_free = bars + 14;          // [2] the group's 8 warps have read S(i): S_g may take S(i + 2) (group -> S issuer)
+  uint64_t* p_full = bars + 16;          // [2] P(i) written to P_g and O_g(i-2) drained (8 warps)     (group -> PV issuer)
+  uint64_t* pv_done = bars + 18;         // [2] PV(i) complete: O_g holds O(i), P_g may be rewritten   (PV issuer -> group)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -369,10 +370,9 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
   }
   if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < kStages; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 2); }
-    for (int i = 0; i < 3; ++i) {
-      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&p_full[i], 8); tc::mbar_init(&o_full[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_free[i], 8); tc::mbar_init(&p_full[i], 8); tc::mbar_init(&pv_done[i], 1);
     }
-    tc::mbar_init(&o_rdy[0], 1); tc::mbar_init(&o_rdy[1], 1);
     tc::fence_barrier_init();
   }
   if (warp == kWarpTma) {
@@ -488,44 +488,47 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
     }
   } else if (warp == kWarpMma) {
     // ==================================================================== S = Q K^T issuer
-    // Three S/P buffers: S(i) needs its operands (full) and buffer i % 3, which is free once PV(i-3) has read P(i-3)
-    // (o_full) -- about a PV after the softmax of window i-3 ended, i.e. S(i) is complete well before the softmax
-    // group of window i has finished window i-2.  The PV MMAs are issued by ANOTHER warp: issuing one tcgen05.mma costs
-    // the issuing warp ~100 cycles (descriptor build, R2UR, ELECT), and an S queued behind nine PV issues would stall a
-    // whole softmax group.  No tensor-pipe ordering between S and PV is assumed; every hand-over has its mbarrier.
+    // S(i) goes to the S buffer of softmax group g = i & 1 as soon as that group has finished READING S(i-2) (s_free: the end
+    // of its pass 2) -- P lives in a buffer of its own, so S_g does not wait for PV(i-2).  The group covers the latency of
+    // this MMA with the epilogue of window i-2, which it runs between its s_free and p_full arrivals; S(i) therefore never
+    // depends on the OTHER group's progress (r2: with three shared S/P buffers S(i) waited for PV(i-3), a window of the other
+    // group, and the groups spent 24 % of their time waiting for S whenever they drifted into phase).
+    // The PV MMAs are issued by ANOTHER warp: issuing one tcgen05.mma costs the issuing warp cycles (descriptor build, ELECT),
+    // and an S queued behind nine PV issues would stall a whole softmax group.  No tensor-pipe ordering between S and PV is
+    // assumed; every hand-over has its mbarrier.
     constexpr uint32_t idesc_s = tc::make_idesc_bf16(128, 144, 0, 0);
     for (int i = 0; i < nwin; ++i) {
-      const int st = i % kStages, b = i % 3;
+      const int st = i % kStages, g2 = i & 1;
       tc::mbar_wait(&full[st], (i / kStages) & 1);
-      if (i >= 3) tc::mbar_wait(&o_full[b], ((i / 3) & 1) ^ 1);
+      if (i >= 2) tc::mbar_wait(&s_free[g2], ((i >> 1) & 1) ^ 1);
       tc::tcgen05_after_sync();
       const uint32_t aq = smem_u32(s_buf + st * kBufBytes), ak = aq + kTileBytes;
       if (tc::elect_one()) {                                 // one elected lane, real branch: uniform-register descriptors
 #pragma unroll
         for (int k = 0; k < 2; ++k)                          // K = 32: two 16-element steps, +32 B inside the 64 B swizzle span
-          tc::umma_bf16(tmem_base + b * kColS, desc_k_sw64(aq) + 2 * k, desc_k_sw64(ak) + 2 * k, idesc_s, k);
-        tc::umma_commit(&s_full[b]);
+          tc::umma_bf16(tmem_base + g2 * kColS, desc_k_sw64(aq) + 2 * k, desc_k_sw64(ak) + 2 * k, idesc_s, k);
+        tc::umma_commit(&s_full[g2]);
       }
       __syncwarp();
       if (trc) g_attn_trace[(i & 7) * 16 + 1] = clock64();
     }
   } else if (warp == kWarpPv) {
     // ==================================================================== O = P V issuer
-    // O(i) goes to O buffer i & 1: its previous content, O(i-2), was read by the epilogue in the middle of the softmax of
-    // window i (same group), i.e. before that group arrived on p_full(i).
+    // O(i) goes to the O buffer of group i & 1: its previous content, O(i-2), was read by the group's epilogue before it
+    // arrived on p_full(i).
     constexpr uint32_t idesc_o = tc::make_idesc_bf16(128, 32, 0, 1);
     for (int i = 0; i < nwin; ++i) {
-      const int st = i % kStages, b = i % 3;
-      tc::mbar_wait(&p_full[b], (i / 3) & 1);
+      const int st = i % kStages, g2 = i & 1;
+      tc::mbar_wait(&p_full[g2], (i >> 1) & 1);
       tc::tcgen05_after_sync();
       if (trc) g_attn_trace[(i & 7) * 16 + 2] = clock64();
       const uint32_t av = smem_u32(s_buf + st * kBufBytes + 2 * kTileBytes);
-      const uint32_t tP = tmem_base + b * kColS, tO = tmem_base + kColO + 32 * (i & 1);
+      const uint32_t tP = tmem_base + kColP + 72 * g2, tO = tmem_base + kColO + 32 * g2;
       if (tc::elect_one()) {                                 // one elected lane, real branch: uniform-register descriptors
 #pragma unroll
         for (int k = 0; k < 9; ++k)                          // K = 144 keys: 16 keys = 8 packed TMEM columns / 1 KiB of V per step
-          tc::umma_bf16_ts(tO, tP + 8 * k + (k >= 5 ? 40 : 0), desc_mn_sw64(av + 1024 * k), idesc_o, k);   // P of keys 0..79 at columns [0,40), of keys 80..143 at [80,112)
-        tc::umma_commit(&o_rdy[i & 1]); tc::umma_commit(&o_full[b]); tc::umma_commit(&empty[st]);
+          tc::umma_bf16_ts(tO, tP + 8 * k, desc_mn_sw64(av + 1024 * k), idesc_o, k);
+        tc::umma_commit(&pv_done[g2]); tc::umma_commit(&empty[st]);
       }
       __syncwarp();
       if (trc) g_attn_trace[(i & 7) * 16 + 3] = clock64();
@@ -543,14 +546,14 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
     const bool trw = trc && (warp & 7) == 0;
 
     int tok_prev = -1;                                        // output token (x 2 + buffer class) of window i-2, or -1
+    float m_prev = 0.f;                                       // merged row maximum of window i-2 (for its lse row)
 
     // O(i) -> global (each thread 16 channels of its row = one 32-byte sector)
-    auto epilogue = [&](int i, int tokc) {
+    // (the caller has waited for pv_done of window i)
+    auto epilogue = [&](int i, int tokc, float m_row) {
       const int slot = (i >> 1) & 1;
-      tc::mbar_wait(&o_rdy[i & 1], (i >> 1) & 1);
-      tc::tcgen05_after_sync();
       uint32_t o[16];
-      tc::tmem_ld_32x16(tmem_base + lane_addr + kColO + 32 * (i & 1) + hf * 16, o);
+      tc::tmem_ld_32x16(tmem_base + lane_addr + kColO + 32 * grp + hf * 16, o);
       const uint32_t exs = exg + (slot * 512 + 256 + row) * 4;
       const float sum = lds_f32(exs) + lds_f32(exs + 512);
       const float inv = kTruncFix / sum;                        // P was truncated to bf16 (pack_bf16_trunc)
@@ -571,8 +574,7 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       }
       if (lse != nullptr && hf == 0) {                        // training only: log2-sum-exp of the row, for the backward
         const int p = p0 + i, pu = p / g.nLon, pl = p - pu * g.nLon;
-        const float m = lds_f32(exg + (slot * 512 + row) * 4);        // the row maximum (both halves hold the merged value)
-        lse[((pl * g.T + tile_type(g, bd, pu)) * g.heads + head) * kWinTokens + row] = m + log2f(sum);
+        lse[((pl * g.T + tile_type(g, bd, pu)) * g.heads + head) * kWinTokens + row] = m_row + log2f(sum);   // m_row: the merged row maximum
       }
     };
 
@@ -593,14 +595,15 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
     }
 #pragma unroll 1
     for (; i < i_end; i += 2) {
-      const int slot = (i >> 1) & 1, b = i % 3;
+      const int slot = (i >> 1) & 1;
       const int l = p0 + i - (u0 + ts) * g.nLon;
       long long* tr = g_attn_trace + (i & 7) * 16;
       const int rcls = s_ccls[rrun], rrb = s_crun[rrun];      // tables of the current tile (rebuilt by every swap)
       const int tok_cur = (rcls == 1 || (rcls == 2 && halo_out != nullptr)) ? (int)run_token(g, roll, l, rrb, rdw) * 2 + (rcls == 2) : -1;
-      const uint32_t tS = tmem_base + lane_addr + b * kColS + k0;
+      const uint32_t tS = tmem_base + lane_addr + grp * kColS + k0;              // my keys of S(i)
+      const uint32_t tP = tmem_base + lane_addr + kColP + 72 * grp + hf * 40;    // my keys of P(i), two per column
 
-      tc::mbar_wait(&s_full[b], (i / 3) & 1);
+      tc::mbar_wait(&s_full[grp], (i >> 1) & 1);
       tc::tcgen05_after_sync();
       if (trw) tr[4] = clock64();
       const uint32_t exm = exg + slot * 2048, exs = exm + 1024;
@@ -646,13 +649,12 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
         m = fmaxf(m, lds_f32(exm + ((hf ^ 1) * 128 + row) * 4));
         sts_f32(exm + (hf * 128 + row) * 4, m);               // the merged maximum, for the lse of the epilogue
         if (trw) tr[6] = clock64();
-        // ---- pass 2: P = exp2(S + bias - m) -> bf16, packed over my own first columns; row sum
+        // PV(i-2), issued when this group finished window i-2, has read P_g and left O(i-2) in O_g (complete long ago)
+        if (i >= 2) { tc::mbar_wait(&pv_done[grp], ((i >> 1) & 1) ^ 1); tc::tcgen05_after_sync(); }
+        // ---- pass 2: P = exp2(S + bias - m) -> bf16 pairs into the group's P buffer; row sum
         float sm0 = 0.f, sm1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-          // the epilogue of window i-2 sits inside pass 2: PV(i-2), issued when this group finished window i-2, has
-          // completed by now, and O buffer i & 1 is drained before this group's arrival on p_full lets PV(i) refill it
-          if (c == 2 && i >= 2) epilogue(i - 2, tok_prev);
           if (c < nchunk) {
             uint32_t v[16];
             tc::tmem_ld_32x16(tS + 16 * c, v);
@@ -669,20 +671,31 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
               add2(sm0, sm1, e0, e1);
               pk[e] = pack_bf16_trunc(e0, e1);
             }
-            tmem_st_32x8(tS + 8 * c, pk);
+            tmem_st_32x8(tP + 8 * c, pk);
           }
         }
         sts_f32(exs + (hf * 128 + row) * 4, sm0 + sm1);
       }
+      // S(i) has been read (every load's registers were consumed): S_g may take S(i+2) NOW; its MMAs run under the epilogue
+      tc::tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s_free[grp]);
+      // the epilogue of window i-2 drains O_g before this group's arrival on p_full lets PV(i) refill it
+      if (i >= 2) epilogue(i - 2, tok_prev, m_prev);
       tc::tmem_st_wait();
       tc::tcgen05_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&p_full[b]);
+      if (lane == 0) tc::mbar_arrive(&p_full[grp]);
       if (trw) tr[7] = clock64();
       tok_prev = tok_cur;
+      m_prev = m;
     }
     }
-    if (i >= 2) epilogue(i - 2, tok_prev);                    // the last window of this group
+    if (i >= 2) {                                             // the last window of this group
+      tc::mbar_wait(&pv_done[grp], ((i - 2) >> 1) & 1);
+      tc::tcgen05_after_sync();
+      epilogue(i - 2, tok_prev, m_prev);
+    }
   } else {
     // ==================================================================== tail warps: rows 128..143 of window i = j (mod 4)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
