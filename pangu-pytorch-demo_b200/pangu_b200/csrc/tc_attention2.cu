@@ -141,6 +141,12 @@ __device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
   return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
 }
 constexpr float kTruncFix = 1.0028260f;
+// Timing knock-outs (WRONG RESULTS; tools/ab_variant.sh ... -DPANGU_ATTN_KO=<bits>): what each part of the window loop costs.
+// 1 no max pass, 2 no MUFU (exp replaced by a copy), 4 no bias reads / adds, 8 no output stores, 16 tail warps idle,
+// 32 no max exchange between the two warps of a row
+#ifndef PANGU_ATTN_KO
+#define PANGU_ATTN_KO 0
+#endif
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
@@ -558,7 +564,7 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       const float sum = lds_f32(exs) + lds_f32(exs + 512);
       const float inv = kTruncFix / sum;                        // P was truncated to bf16 (pack_bf16_trunc)
       tmem_ld_wait16(o);
-      if (tokc >= 0) {
+      if (tokc >= 0 && !(PANGU_ATTN_KO & 8)) {
         uint4 a, c;
         a.x = pack_bf16(__uint_as_float(o[0]) * inv, __uint_as_float(o[1]) * inv);
         a.y = pack_bf16(__uint_as_float(o[2]) * inv, __uint_as_float(o[3]) * inv);
@@ -637,6 +643,8 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
             }
           }
           mx0 = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        } else if (PANGU_ATTN_KO & 1) {
+          mx0 = 30.0f;
         } else {
           mx0 = hf == 0 ? score_bound<0>(tS, bm) : score_bound<1>(tS, bm);
         }
@@ -645,7 +653,7 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       }
       if (trw) tr[5] = clock64();
       {
-        named_bar(1 + grp * 4 + q, 64);                       // the two warps of this lane quarter
+        if (!(PANGU_ATTN_KO & 32)) named_bar(1 + grp * 4 + q, 64);                       // the two warps of this lane quarter
         m = fmaxf(m, lds_f32(exm + ((hf ^ 1) * 128 + row) * 4));
         sts_f32(exm + (hf * 128 + row) * 4, m);               // the merged maximum, for the lse of the epilogue
         if (trw) tr[6] = clock64();
@@ -658,16 +666,17 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
           if (c < nchunk) {
             uint32_t v[16];
             tc::tmem_ld_32x16(tS + 16 * c, v);
-            const uint4 b0 = lds128(brow + 32 * c), b1 = lds128(brow + 32 * c + 16);
+            uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
+            if (!(PANGU_ATTN_KO & 4)) { b0 = lds128(brow + 32 * c); b1 = lds128(brow + 32 * c + 16); }
             const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             tmem_ld_wait16(v);
             uint32_t pk[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               float s0 = __uint_as_float(v[2 * e]), s1 = __uint_as_float(v[2 * e + 1]);
-              add_bias2(bw[e], s0, s1);
+              if (!(PANGU_ATTN_KO & 4)) add_bias2(bw[e], s0, s1);
               add2(s0, s1, -m, -m);
-              const float e0 = ex2(s0), e1 = ex2(s1);
+              const float e0 = (PANGU_ATTN_KO & 2) ? s0 : ex2(s0), e1 = (PANGU_ATTN_KO & 2) ? s1 : ex2(s1);
               add2(sm0, sm1, e0, e1);
               pk[e] = pack_bf16_trunc(e0, e1);
             }
@@ -716,6 +725,7 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       uint8_t* sk = sq + kTileBytes;
       uint8_t* sv = sk + kTileBytes;
       tc::mbar_wait(&full[st], (i / kStages) & 1);
+      if (PANGU_ATTN_KO & 16) { __syncwarp(); if (lane == 0) tc::mbar_arrive(&empty[st]); continue; }
       if (trc) g_attn_trace[(i & 7) * 16 + 10] = clock64();
       uint32_t qa[2][4];
 #pragma unroll
