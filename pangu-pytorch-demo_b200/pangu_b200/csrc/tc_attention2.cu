@@ -143,7 +143,8 @@ __device__ __forceinline__ uint32_t pack_bf16_trunc(float lo, float hi) {
 constexpr float kTruncFix = 1.0028260f;
 // Timing knock-outs (WRONG RESULTS; tools/ab_variant.sh ... -DPANGU_ATTN_KO=<bits>): what each part of the window loop costs.
 // 1 no max pass, 2 no MUFU (exp replaced by a copy), 4 no bias reads / adds, 8 no output stores, 16 tail warps idle,
-// 32 no max exchange between the two warps of a row
+// 32 no max exchange between the two warps of a row, 64 no TMA gather (the operand tiles keep whatever they hold), 128 no
+// TMEM round trip in pass 2 (no tcgen05.ld of S, no tcgen05.st of P)
 #ifndef PANGU_ATTN_KO
 #define PANGU_ATTN_KO 0
 #endif
@@ -457,6 +458,11 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
         tc::fence_async_smem();                               // generic-proxy writes -> visible to the tensor core
       }
       __syncwarp();
+      if (PANGU_ATTN_KO & 64) {
+        if (lane == 0) { s_stage_u[st] = u; tc::mbar_arrive(&full[st]); }
+        __syncwarp();
+        continue;
+      }
       if (lane == 0) {
         s_stage_u[st] = u;
         tc::mbar_expect_tx(&full[st], real_runs * 3 * kRunBytes);
@@ -665,7 +671,12 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
         for (int c = 0; c < 5; ++c) {
           if (c < nchunk) {
             uint32_t v[16];
-            tc::tmem_ld_32x16(tS + 16 * c, v);
+            if (PANGU_ATTN_KO & 128) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(m) + e;
+            } else {
+              tc::tmem_ld_32x16(tS + 16 * c, v);
+            }
             uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
             if (!(PANGU_ATTN_KO & 4)) { b0 = lds128(brow + 32 * c); b1 = lds128(brow + 32 * c + 16); }
             const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -680,7 +691,8 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
               add2(sm0, sm1, e0, e1);
               pk[e] = pack_bf16_trunc(e0, e1);
             }
-            tmem_st_32x8(tP + 8 * c, pk);
+            if (PANGU_ATTN_KO & 128) { sm0 += __uint_as_float(pk[0] ^ pk[3] ^ pk[5] ^ pk[7]); sm1 += __uint_as_float(pk[1] ^ pk[2] ^ pk[4] ^ pk[6]); }
+            else tmem_st_32x8(tP + 8 * c, pk);
           }
         }
         sts_f32(exs + (hf * 128 + row) * 4, sm0 + sm1);
