@@ -188,6 +188,10 @@ int pangu_window_attention(const void* qkv, const float* qkv_bias, const void* e
  * window type instead of the bound max(S) + max(bias row) -- for bias tables whose rows spread over more than ~100 log2
  * units (the bound would underflow every exponent); shift-masked window types always take the exact maximum. */
 #define PANGU_ATTN_EXACT_MAX 2
+/* Bit 2 of `prescaled` (pre-scaled bf16 path, halo_out == NULL): the halo buffers hold only the K and V columns of the
+ * neighbours' rows, [Z*halo*W, 2C] -- the neighbours' queries are never needed when each rank keeps only its own output
+ * rows (the "redundant" exchange scheme of pangu_b200/dist.py), so a third of the halo bytes does not travel. */
+#define PANGU_ATTN_HALO_KV 4
 int pangu_window_attention_band(const void* qkv, const void* halo_qkv, const void* halo_lo_qkv,
                                 const float* qkv_bias, const void* earth_bias, int bias_dtype, void* out,
                                 void* halo_out, const pangu_geom* g, const pangu_band* band, int roll,

@@ -182,7 +182,14 @@ extern "C" int pangu_window_attention_band(const void* qkv, const void* halo_qkv
   if (!make_geom(gg, g) || !band || !qkv || !qkv_bias || !earth_bias || !out) { set_error("window_attention_band: bad argument"); return PANGU_ERR_BAD_ARG; }
   if (g.C != g.heads * kHeadDim) { set_error("window_attention_band: C=%d must equal heads*32", g.C); return PANGU_ERR_BAD_ARG; }
   if (roll != 0 && roll != 1) { set_error("window_attention_band: roll must be 0 or 1"); return PANGU_ERR_BAD_ARG; }
-  const BandGeom bd{band->h0, band->hrows, band->hw0, band->nhw, band->wrap, band->halo, band->halo_lo};
+  BandGeom bd{band->h0, band->hrows, band->hw0, band->nhw, band->wrap, band->halo, band->halo_lo};
+  if (prescaled & PANGU_ATTN_HALO_KV) {
+    if (!(prescaled & 1) || bias_dtype != PANGU_BF16 || halo_out != nullptr) {
+      set_error("window_attention_band: K/V-only halos need the pre-scaled bf16 path and no halo output");
+      return PANGU_ERR_BAD_ARG;
+    }
+    bd.halo_kv = 1;
+  }
   const int last_hw = bd.hw0 + bd.nhw - (bd.wrap ? 1 : 0);          // one past the last regular window
   if (bd.h0 < 0 || bd.hrows <= 0 || bd.h0 + bd.hrows > g.H || bd.hw0 < 0 || bd.nhw < 0 || last_hw > g.nH ||
       bd.halo < 0 || (bd.halo > 0 && !halo_qkv) || bd.halo_lo < 0 || (bd.halo_lo > 0 && !halo_lo_qkv) ||

@@ -30,6 +30,7 @@ struct BandGeom {
   int wrap;
   int halo;          // rows available in the halo buffers right after the own rows
   int halo_lo;       // rows available in the northern halo buffer right before the own rows
+  int halo_kv = 0;   // 1: the halo buffers hold only the K and V columns, [rows, 2C] (PANGU_ATTN_HALO_KV; tcgen05 kernel only)
 };
 
 inline bool make_geom(const pangu_geom* g, WinGeom& o) {

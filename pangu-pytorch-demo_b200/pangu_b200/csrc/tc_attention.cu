@@ -303,6 +303,7 @@ int launch_window_attention_bf16(const void* qkv, const void* halo_qkv, const vo
       return launch_window_attention_tc(qkv, halo_qkv, halo_lo_qkv, qkv_bias, earth_bias, out, halo_out, g, bd, roll, st, lse, (prescaled >> 1) & 1);
     prescaled &= 1;
   }
+  if (bd.halo_kv) { set_error("attention_bf16: K/V-only halos are only implemented in the tcgen05 kernel"); return PANGU_ERR_UNSUPPORTED; }
   // longitude windows per CTA (they share the staged bias tile): as many as possible (<= 5) while the grid
   // still fills the GPU for at least ~4 waves of 2 CTAs/SM -- small latitude bands get finer CTAs
   int lon_chunk = 1;

@@ -412,7 +412,7 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");      // all four warps of the group, converged
   if (warp == kWarpTma) {
     // ==================================================================== TMA producer
-    int cur_u = -1, real_runs = 0;
+    int cur_u = -1, real_runs = 0, halo_runs = 0;
     bool box3d[2] = {false, false};
     for (int i = 0; i < nwin; ++i) {
       const int p = p0 + i, u = p / g.nLon, l = p - u * g.nLon;
@@ -428,8 +428,8 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
           s_pcls[lane] = cls;
         }
         __syncwarp();
-        real_runs = 0;
-        for (int r = 0; r < 12; ++r) real_runs += s_pcls[r] != 0;
+        real_runs = halo_runs = 0;
+        for (int r = 0; r < 12; ++r) { real_runs += s_pcls[r] != 0; halo_runs += s_pcls[r] >= 2; }
         // a half window (fixed dz: 6 latitude rows x 12 longitudes) whose rows are consecutive own rows is ONE 3-D box
         // per tensor; otherwise (pad rows, halo rows, the latitude wrap) its runs are fetched one by one
 #pragma unroll
@@ -465,7 +465,8 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
       }
       if (lane == 0) {
         s_stage_u[st] = u;
-        tc::mbar_expect_tx(&full[st], real_runs * 3 * kRunBytes);
+        // (K/V-only halos: the q runs of halo rows are not fetched -- those score rows are never stored)
+        tc::mbar_expect_tx(&full[st], (real_runs * 3 - (bd.halo_kv ? halo_runs : 0)) * kRunBytes);
       }
       __syncwarp();
       const int w = 12 * l + (roll == 1 ? 6 : 0);
@@ -483,7 +484,11 @@ window_attention_tc_kernel(const __grid_constant__ Maps maps, const float* __res
         if (cls == 0 || (box3d[r / 6] && w + 12 <= g.W)) continue;
         const int rb = s_prun[r];
         uint8_t* dst = s_buf + st * kBufBytes + s * kTileBytes + r * kRunBytes;
-        const int c0 = s * C + head * kHeadDim;
+        int c0 = s * C + head * kHeadDim;
+        if (bd.halo_kv && cls >= 2) {                         // halo buffers are [rows, 2C] = (k | v)
+          if (s == 0) continue;
+          c0 -= C;
+        }
         if (roll == 2) {
           tc::tma_load_2d(dst, &maps.own12, &full[st], c0, l * g.T * kWinTokens + rb);
         } else if (w + 12 <= g.W) {
@@ -863,18 +868,21 @@ int launch_window_attention_tc(const void* qkv, const void* halo_qkv, const void
   const uint64_t own_rows = roll == 2 ? (uint64_t)g.nLon * g.T * kWinTokens : (uint64_t)g.Z * bd.hrows * g.W;
   const uint64_t pitch = (uint64_t)3 * g.C * 2;
   Maps maps;
-  auto enc = [&](CUtensorMap* m12, CUtensorMap* m6, const void* p, uint64_t rows) -> bool {
-    return tc::encode_tmap_2d(m12, 1, p, (uint64_t)3 * g.C, rows, pitch, 32, 12, 64) &&
-           tc::encode_tmap_2d(m6, 1, p, (uint64_t)3 * g.C, rows, pitch, 32, 6, 64);
+  auto enc = [&](CUtensorMap* m12, CUtensorMap* m6, const void* p, uint64_t rows, int ntens = 3) -> bool {
+    const uint64_t cols = (uint64_t)ntens * g.C;
+    return tc::encode_tmap_2d(m12, 1, p, cols, rows, cols * 2, 32, 12, 64) &&
+           tc::encode_tmap_2d(m6, 1, p, cols, rows, cols * 2, 32, 6, 64);
   };
   if (!enc(&maps.own12, &maps.own6, qkv, own_rows)) return PANGU_ERR_CUDA;
+  const int halo_tens = bd.halo_kv ? 2 : 3;
+  if (bd.halo_kv && halo_out != nullptr) { set_error("attention_tc: K/V-only halos cannot produce halo outputs"); return PANGU_ERR_BAD_ARG; }
   maps.hs12 = maps.own12; maps.hs6 = maps.own6; maps.hn12 = maps.own12; maps.hn6 = maps.own6;
   {   // [Z * rows][W][3C] view of the own rows (not meaningful for pre-partitioned windows, where it is never used)
     const uint64_t rows3 = roll == 2 ? 1 : (uint64_t)g.Z * bd.hrows, W3 = roll == 2 ? 12 : (uint64_t)g.W;
     if (!tc::encode_tmap_3d_bf16(&maps.own3d12, qkv, (uint64_t)3 * g.C, W3, rows3, pitch, pitch * W3, 32, 12, 6, 64)) return PANGU_ERR_CUDA;
   }
-  if (bd.halo > 0 && !enc(&maps.hs12, &maps.hs6, halo_qkv, (uint64_t)g.Z * bd.halo * g.W)) return PANGU_ERR_CUDA;
-  if (bd.halo_lo > 0 && !enc(&maps.hn12, &maps.hn6, halo_lo_qkv, (uint64_t)g.Z * bd.halo_lo * g.W)) return PANGU_ERR_CUDA;
+  if (bd.halo > 0 && !enc(&maps.hs12, &maps.hs6, halo_qkv, (uint64_t)g.Z * bd.halo * g.W, halo_tens)) return PANGU_ERR_CUDA;
+  if (bd.halo_lo > 0 && !enc(&maps.hn12, &maps.hn6, halo_lo_qkv, (uint64_t)g.Z * bd.halo_lo * g.W, halo_tens)) return PANGU_ERR_CUDA;
   // teams of `heads` CTAs share a range of (window type, longitude window) pairs
   if (g.heads > tc::num_sms()) { set_error("attention_tc: more heads (%d) than SMs", g.heads); return PANGU_ERR_BAD_ARG; }
   const long long npairs = (long long)g.nZ * bd.nhw * g.nLon;

@@ -27,6 +27,8 @@ The exchanges are NCCL point-to-point (`torch.distributed.batch_isend_irecv`) of
 direction); a `LocalComm` runs all ranks of a plan inside ONE process (tests on a single GPU: the banded result
 must equal the un-sharded forward bit for bit).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -187,14 +189,15 @@ class _Worker:
         w_qkv, b_qkv, _ = PF.attention_operands(att, wc)
         self.qkv = ops.linear(self.xb, w_qkv, b_qkv)
 
-    def first_rows(self, t, stage, rows=3):
-        """The first `rows` latitude rows of a band tensor [Z*hrows*W, F] as a contiguous [Z*rows*W, F] block."""
+    def first_rows(self, t, stage, rows=3, col0=0):
+        """The first `rows` latitude rows of a band tensor [Z*hrows*W, F] as a contiguous [Z*rows*W, F - col0] block
+        (col0 = C on a qkv tensor: only the K and V columns)."""
         hr, W = self.plan.nrows(stage), TOK_W[stage]
-        return t.view(Z, hr, W, t.shape[-1])[:, :rows].reshape(Z * rows * W, t.shape[-1]).contiguous()
+        return t.view(Z, hr, W, t.shape[-1])[:, :rows, :, col0:].reshape(Z * rows * W, t.shape[-1] - col0).contiguous()
 
-    def last_rows(self, t, stage, rows=3):
+    def last_rows(self, t, stage, rows=3, col0=0):
         hr, W = self.plan.nrows(stage), TOK_W[stage]
-        return t.view(Z, hr, W, t.shape[-1])[:, hr - rows:].reshape(Z * rows * W, t.shape[-1]).contiguous()
+        return t.view(Z, hr, W, t.shape[-1])[:, hr - rows:, :, col0:].reshape(Z * rows * W, t.shape[-1] - col0).contiguous()
 
     def block_attend(self, blk, stage, roll, scheme):
         att, wc = blk.attention, blk._wcache
@@ -203,7 +206,7 @@ class _Worker:
         self.o, self.halo_o = ops.window_attention_band(
             self.qkv, self.halo_qkv, b_qkv, eb, Z, TOK_H[stage], TOK_W[stage], att.head_number, band, roll,
             halo_lo_qkv=self.halo_lo_qkv, return_halo=(scheme == "sendback"), prescaled=True,
-            exact_max=PF.attention_exact_max(att, wc))
+            exact_max=PF.attention_exact_max(att, wc), halo_kv=(scheme == "redundant" and HALO_KV_ONLY))
         self.qkv = self.halo_qkv = self.halo_lo_qkv = None
 
     def block_finish(self, blk, stage, o_first):
@@ -228,6 +231,8 @@ class _Worker:
 
 
 SCHEMES = ("redundant", "sendback")
+# "redundant" scheme: exchange only the K and V columns of the halo rows (0 = whole qkv rows, for A/B measurements)
+HALO_KV_ONLY = os.environ.get("PANGU_B200_HALO_KV", "1") != "0"
 
 
 def _run(model, workers, comm, inputs, scheme="redundant"):
@@ -252,9 +257,12 @@ def _run(model, workers, comm, inputs, scheme="redundant"):
                 w.block_qkv(blk, stage)
             exchange = roll and comm.world > 1
             if exchange and scheme == "redundant":
-                firsts_ = [None if w.plan.first else w.first_rows(w.qkv, stage) for w in workers]
-                lasts_ = [None if w.plan.last else w.last_rows(w.qkv, stage) for w in workers]
-                like = [_halo_like(w.qkv, stage) for w in workers]
+                # each rank runs the straddling window for its OWN rows only: the neighbours' queries are never needed, so only
+                # the K and V columns travel (2/3 of the bytes)
+                c0 = workers[0].qkv.shape[-1] // 3 if HALO_KV_ONLY else 0
+                firsts_ = [None if w.plan.first else w.first_rows(w.qkv, stage, col0=c0) for w in workers]
+                lasts_ = [None if w.plan.last else w.last_rows(w.qkv, stage, col0=c0) for w in workers]
+                like = [_halo_like(w.qkv, stage, cols=w.qkv.shape[-1] - c0) for w in workers]
                 for w, (south, north) in zip(workers, comm.swap_edges(firsts_, lasts_, like)):
                     w.halo_qkv, w.halo_lo_qkv = south, north
             elif exchange:
@@ -275,8 +283,8 @@ def _run(model, workers, comm, inputs, scheme="redundant"):
     return [w.recover() for w in workers]
 
 
-def _halo_like(t, stage, rows=3):
-    return torch.empty((Z * rows * TOK_W[stage], t.shape[-1]), dtype=t.dtype, device=t.device)
+def _halo_like(t, stage, rows=3, cols=None):
+    return torch.empty((Z * rows * TOK_W[stage], t.shape[-1] if cols is None else cols), dtype=t.dtype, device=t.device)
 
 
 def _check_model(model):

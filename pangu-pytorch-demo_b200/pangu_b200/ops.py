@@ -290,11 +290,12 @@ def full_band(H):
 
 
 def window_attention_band(qkv, halo_qkv, qkv_bias, earth_bias, Z, H, W, heads, band, roll, halo_lo_qkv=None,
-                          return_halo=True, prescaled=False, exact_max=False):
+                          return_halo=True, prescaled=False, exact_max=False, halo_kv=False):
     """Band-sharded window attention (bf16): qkv [Z*hrows*W, 3C] holds the band's own rows of the GLOBAL
     (Z, H, W) grid, halo_qkv [Z*halo*W, 3C] the southern neighbour's first rows, halo_lo_qkv the northern
     neighbour's last rows.  -> (out, halo_out): halo_out (attention output of the southern halo rows, to be sent
-    back) only when return_halo, else None (the neighbour computes those rows itself)."""
+    back) only when return_halo, else None (the neighbour computes those rows itself).
+    halo_kv: the halo tensors hold only the K and V columns, [Z*halo*W, 2C] (PANGU_ATTN_HALO_KV: no halo output possible)."""
     _chk(qkv, torch.bfloat16, "qkv")
     _chk(qkv_bias, torch.float32, "qkv_bias")
     _chk(earth_bias, name="earth_bias")
@@ -306,8 +307,10 @@ def window_attention_band(qkv, halo_qkv, qkv_bias, earth_bias, Z, H, W, heads, b
     for t, n, nm in ((halo_qkv, band.halo, "halo_qkv"), (halo_lo_qkv, band.halo_lo, "halo_lo_qkv")):
         if n:
             _chk(t, torch.bfloat16, nm)
-            if t.shape[0] != Z * n * W:
-                raise abi.PanguError(f"{nm} has the wrong number of rows")
+            if t.shape[0] != Z * n * W or t.shape[1] != (2 if halo_kv else 3) * C:
+                raise abi.PanguError(f"{nm} has the wrong shape {tuple(t.shape)}")
+    if halo_kv and return_halo:
+        raise abi.PanguError("window_attention_band: K/V-only halos cannot return the halo rows' output")
     if band.halo and return_halo:
         halo_out = torch.empty((Z * band.halo * W, C), dtype=qkv.dtype, device=qkv.device)
     g = geom(Z, H, W, C, heads)
@@ -315,7 +318,7 @@ def window_attention_band(qkv, halo_qkv, qkv_bias, earth_bias, Z, H, W, heads, b
     _call("attention_bf16[C=%d]" % C, "pangu_window_attention_band",
           (_ptr(qkv), _ptr(halo_qkv) if band.halo else None, _ptr(halo_lo_qkv) if band.halo_lo else None, _ptr(qkv_bias),
            _ptr(earth_bias), _DT[earth_bias.dtype], _ptr(out), _ptr(halo_out), g, band, int(roll),
-           int(bool(prescaled)) | (2 if exact_max else 0),
+           int(bool(prescaled)) | (2 if exact_max else 0) | (4 if halo_kv else 0),
            _stream(),),
           flops=nwin * heads * 4.0 * 144 * 144 * 32,
           nbytes=float(qkv.numel() * 2 + out.numel() * 2 + earth_bias.numel() * earth_bias.element_size() * band.nhw / ((H + 5) // 6)))
