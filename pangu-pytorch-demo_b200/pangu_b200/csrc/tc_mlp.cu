@@ -36,6 +36,10 @@
 #include "tc_common.cuh"
 #include "tc_ln_epilogue.cuh"
 
+#ifndef PANGU_MLP_X2
+#define PANGU_MLP_X2 1                            // C = 192: double-buffered x tile (0 = the single-buffer kernel, for A/B runs)
+#endif
+
 namespace pangu {
 namespace tc {
 
@@ -84,7 +88,12 @@ struct MlpCfg {
   static constexpr int NSPLIT = C / 192;         // GEMM2: N = C issued as NSPLIT MMAs of N = 192
   static constexpr int X_BYTES = 128 * C * 2;    // this CTA's rows of the x tile
   static constexpr int SLOT_BYTES = C * 64;      // half W1 chunk [32 x C] == half W2 chunk [C/2 x 64] (bf16)
-  static constexpr int LN_UW = C == 192 ? 32 : 16;   // LayerNorm unit width (columns)
+  // C = 192 (no PROJ): the x tile is DOUBLE-BUFFERED -- the next row tile's operand rows land while this tile's MMAs run (the
+  // single buffer could only be re-loaded after the tile's last GEMM1: 5.2 k clocks from load to landing with the tensor pipe
+  // idle for ~3.7 k of the 24 k per tile, profiles/r2_mlp_trace.md).  The 48 KB come from the LayerNorm staging (16-column
+  // units: 5 instead of 10 KB per warp) and one ring slot.
+  static constexpr int NX = (C == 192 && !PROJ && PANGU_MLP_X2) ? 2 : 1;
+  static constexpr int LN_UW = (C == 192 && NX == 1) ? 32 : 16;   // LayerNorm unit width (columns)
   static constexpr int LN_D = C == 192 ? 1 : 2;      // residual tiles in flight per LayerNorm warp (TMA loads)
   static constexpr int LN_NB16 = C == 192 ? 1 : 2;   // bf16 staging tiles: 2 = the store of unit i drains while unit i+1 is computed
   static constexpr int LN_NBUF = LN_D + LN_NB16;      // fp32 staging tiles: LN_D landing + LN_NB16 draining
@@ -108,10 +117,11 @@ struct MlpCfg {
   static constexpr int STG1_BYTES = LN_UW * 128 * LN1_NBUF;
   static constexpr int EPI_BYTES = (LN_ALIAS ? 0 : LN_WARPS * (STG_BYTES + STGB_BYTES)) + PART_BYTES + PARAM_BYTES;
   static constexpr int BAR_BYTES = 2048;
-  static constexpr int AVAIL = 227 * 1024 - 1024 - BAR_BYTES - X_BYTES - EPI_BYTES;
+  static constexpr int AVAIL = 227 * 1024 - 1024 - BAR_BYTES - NX * X_BYTES - EPI_BYTES;
   static constexpr int NSLOT = AVAIL / SLOT_BYTES > 8 ? 8 : AVAIL / SLOT_BYTES;
-  static constexpr int SMEM_BYTES = 1024 + X_BYTES + NSLOT * SLOT_BYTES + EPI_BYTES + BAR_BYTES;
+  static constexpr int SMEM_BYTES = 1024 + NX * X_BYTES + NSLOT * SLOT_BYTES + EPI_BYTES + BAR_BYTES;
   static_assert(!LN_ALIAS || LN_WARPS * (STG_BYTES + STGB_BYTES) <= X_BYTES + NSLOT * SLOT_BYTES, "staging must fit in x tile + weight ring");
+  static_assert(NX == 1 || !LN_ALIAS, "the double-buffered x tile is never LayerNorm staging");
   static_assert(!PROJ || (LN_JOIN && LN_WARPS * STG1_BYTES <= NSLOT * SLOT_BYTES), "PROJ: 16 LayerNorm warps, first LayerNorm staged in the weight ring");
   static constexpr int NY = C == 192 ? 2 : 1;    // output accumulators: double-buffered when TMEM has room
   static constexpr int COL_HP = 384;             // two 64-column H/P buffers behind the Y accumulator(s)
@@ -135,8 +145,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   constexpr int NSLOT = Cfg::NSLOT, NCH = Cfg::NCH, KB1 = Cfg::KB1, NSPLIT = Cfg::NSPLIT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sX = smem;                                         // [KB1][128 rows x 128 B]   (SW128 K-major)
-  uint8_t* sW = smem + Cfg::X_BYTES;                          // [NSLOT][SLOT_BYTES]
+  uint8_t* sX = smem;                                         // [NX][KB1][128 rows x 128 B]   (SW128 K-major)
+  uint8_t* sW = smem + Cfg::NX * Cfg::X_BYTES;                // [NSLOT][SLOT_BYTES]
   uint8_t* epi_smem = sW + NSLOT * Cfg::SLOT_BYTES;
   // LayerNorm staging: fp32 tiles of all warps, then bf16 tiles of all warps (inside the x tile at C = 384)
   uint8_t* stg_smem = Cfg::LN_ALIAS ? sX : epi_smem;
@@ -158,8 +168,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* w_full = bars + 13;      // [NSLOT]
   uint64_t* w_empty = bars + 13 + NSLOT;
   uint64_t* ln_bar = bars + 13 + 2 * NSLOT;      // [LN warps][8] barriers of the residual tile loads (4 per LayerNorm)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13 + 2 * NSLOT + 8 * Cfg::LN_WARPS);
-  static_assert((13 + 2 * 8 + 8 * Cfg::LN_WARPS) * 8 + 8 <= Cfg::BAR_BYTES, "barrier area");
+  uint64_t* x_full2 = bars + 13 + 2 * NSLOT + 8 * Cfg::LN_WARPS;   // second x buffer (NX == 2): same roles as x_full / x_empty
+  uint64_t* x_empty2 = x_full2 + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15 + 2 * NSLOT + 8 * Cfg::LN_WARPS);
+  static_assert((15 + 2 * 8 + 8 * Cfg::LN_WARPS) * 8 + 8 <= Cfg::BAR_BYTES, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();                    // 0 = leader of the pair
@@ -181,7 +193,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       sparams1[i] = i < C ? a.bp[i] : (i < 2 * C ? a.gamma1[i - C] : a.beta1[i - 2 * C]);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(x_full, 1); mbar_init(x_empty, 1);
+    mbar_init(x_full, 1); mbar_init(x_empty, 1); mbar_init(x_full2, 1); mbar_init(x_empty2, 1);
     mbar_init(&h_full[0], 1); mbar_init(&h_full[1], 1);
     mbar_init(&p_full[0], 2 * kMlpEpiWarps); mbar_init(&p_full[1], 2 * kMlpEpiWarps);
     for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 2 * Cfg::LN_WARPS); }
@@ -209,9 +221,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");      // the control warpgroup gives registers to the GELU warps
     if (warp == 0) {
       // ------------------------------------------------------------ TMA producer (both CTAs)
-      const uint32_t x_full_L = mapa_u32(smem_u32(x_full), 0);
+      const uint32_t x_full_L = mapa_u32(smem_u32(x_full), 0), x_full2_L = mapa_u32(smem_u32(x_full2), 0);
       int slot = 0;
-      uint32_t wphase = 0, xphase = 0;
+      uint32_t wphase = 0, xphase = 0;                        // xphase: bit b = phase of x_empty (b = 0) / x_empty2 (b = 1)
       auto acquire_slot = [&]() -> uint32_t {
         mbar_wait(&w_empty[slot], wphase ^ 1);
         if (rank == 0 && elect_one()) mbar_expect_tx(&w_full[slot], 2 * Cfg::SLOT_BYTES);
@@ -234,16 +246,23 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (elect_one()) tma_load_2d_cg2(dst + h * 12288, &tmW2, bar, j * NH, h * 192 + (int)rank * 96);
         advance();
       };
-      for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
-        const int m0 = pt * 256 + (int)rank * 128;
-        mbar_wait(x_empty, xphase ^ 1);                       // every GEMM1 of the previous row tile has read x
-        if (Cfg::LN_ALIAS) mbar_wait(xs_free, xphase ^ 1);    // ... and its LayerNorm no longer stages through x tile + ring
-        xphase ^= 1;
-        if ((a.dbg & 16) && blockIdx.x == 0 && lane == 0) { const int n = (pt - pair0) / npairs; if (n >= 1 && n <= 2) g_mlp_trace[256 + n * 16 + 0] = clock64(); }
-        if (rank == 0 && elect_one()) mbar_expect_tx(x_full, 2 * Cfg::X_BYTES);
+      // x tile of row tile pt_ -> buffer xb_ (waits until every GEMM1 of the tile that used the buffer before has read it)
+      auto load_x = [&](int pt_, int xb_) {
+        const int m0_ = pt_ * 256 + (int)rank * 128;
+        mbar_wait(xb_ ? x_empty2 : x_empty, ((xphase >> xb_) & 1) ^ 1);
+        if (Cfg::LN_ALIAS) mbar_wait(xs_free, ((xphase >> xb_) & 1) ^ 1);   // ... and its LayerNorm no longer stages through x tile + ring
+        xphase ^= 1u << xb_;
+        if ((a.dbg & 16) && blockIdx.x == 0 && lane == 0) { const int n = (pt_ - pair0) / npairs; if (n >= 1 && n <= 2) g_mlp_trace[256 + n * 16 + 0] = clock64(); }
+        if (rank == 0 && elect_one()) mbar_expect_tx(xb_ ? x_full2 : x_full, 2 * Cfg::X_BYTES);
 #pragma unroll
         for (int kb = 0; kb < KB1; ++kb)
-          if (elect_one()) tma_load_2d_cg2(sX + kb * 16384, &tmX, x_full_L, kb * 64, m0);
+          if (elect_one()) tma_load_2d_cg2(sX + xb_ * Cfg::X_BYTES + kb * 16384, &tmX, xb_ ? x_full2_L : x_full_L, kb * 64, m0_);
+      };
+      if (Cfg::NX == 2 && pair0 < a.pair_tiles) load_x(pair0, 0);
+      int tn_p = 0;                                           // row tiles this pair has started
+      for (int pt = pair0; pt < a.pair_tiles; pt += npairs, ++tn_p) {
+        const int m0 = pt * 256 + (int)rank * 128;
+        if (Cfg::NX == 1) load_x(pt, 0);
         // this row tile's residual rows -> L2, long before the LayerNorm warps ask for them (16 rows per lane 0..7)
         if (lane < 8 && !(a.dbg & 64)) {
           const long long r0 = (long long)m0 + lane * 16;
@@ -269,10 +288,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               if (elect_one()) tma_load_2d_cg2(dst + h * 12288, &tmWp, bar, kb * 64, h * 192 + (int)rank * 96);
             advance();
           }
-          mbar_wait(ring_free, xphase ^ 1);                   // the first LayerNorm has staged through the ring: wait until it is done
+          mbar_wait(ring_free, (xphase & 1) ^ 1);             // the first LayerNorm has staged through the ring: wait until it is done
         }
         load_w1(0);
         load_w1(1);
+        if (Cfg::NX == 2 && pt + npairs < a.pair_tiles) load_x(pt + npairs, (tn_p + 1) & 1);   // the NEXT row tile's operand rows, a tile ahead
         for (int j = 0; j < NCH; ++j) {                       // same order as the MMA issuer consumes
           load_w2(j);
           if (j + 2 < NCH) load_w1(j + 2);
@@ -290,6 +310,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         int slot = 0;
         uint32_t wphase = 0, xphase = 0, yphase = 0, pphase = 0;   // pphase: bit b = phase of p_full[b]
         auto advance = [&]() { if (++slot == NSLOT) { slot = 0; wphase ^= 1; } };
+        uint32_t sXa = smem_u32(sX);                            // x buffer of the current row tile
         auto issue_g1 = [&](int b) {                            // HP_b = X . W1chunk^T   (K = C)
           mbar_wait(&w_full[slot], wphase);
           tcgen05_after_sync();
@@ -300,7 +321,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           if (elect_one()) {
 #pragma unroll
             for (int kb = 0; kb < KB1; ++kb) {
-              const uint64_t da = make_desc_k_sw128(smem_u32(sX) + kb * 16384);
+              const uint64_t da = make_desc_k_sw128(sXa + kb * 16384);
               const uint64_t db = make_desc_k_sw128(sw + kb * 4096);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -315,10 +336,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           advance();
         };
         for (int pt = pair0; pt < a.pair_tiles; pt += npairs) {
-          mbar_wait(x_full, xphase);
-          xphase ^= 1;
-          tcgen05_after_sync();
           const int tn = (pt - pair0) / npairs;
+          const int xb = Cfg::NX == 2 ? (tn & 1) : 0;
+          mbar_wait(xb ? x_full2 : x_full, (xphase >> xb) & 1);
+          xphase ^= 1u << xb;
+          sXa = smem_u32(sX) + xb * Cfg::X_BYTES;
+          tcgen05_after_sync();
           const bool trt = (a.dbg & 16) && blockIdx.x == 0 && lane == 0 && tn >= 1 && tn <= 2;
           if (trt) g_mlp_trace[256 + tn * 16 + 1] = clock64();
           if constexpr (PROJ) {
@@ -381,7 +404,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             if (j + 2 < NCH) {
               issue_g1(b);
               if (tr) g_mlp_trace[j * 8 + 2] = clock64();                                      // H_{j+2} overwrites HP_b after G2(j) (pipe order)
-              if (j + 2 == NCH - 1 && elect_one()) umma2_commit_mc(x_empty);   // last read of the x tile
+              if (j + 2 == NCH - 1 && elect_one()) umma2_commit_mc(xb ? x_empty2 : x_empty);   // last read of the x tile
             }
           }
           if (elect_one()) umma2_commit_mc(&y_full[yb]);

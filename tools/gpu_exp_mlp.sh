@@ -1,8 +1,9 @@
 #!/bin/bash
-# fused-Mlp kernel alone (tools/bench_kernels.py-style timing through mlp_trace's operands): A/B of $PANGU_MLP_DBG bits
-for dbg in 256 0 256 0; do
+# fused-Mlp kernel alone, L2 flushed between launches: tools/gpu_exp_mlp.sh "<lib tags>"   (cur = in-tree build)
+for v in ${1:-cur}; do
+  if [ $v = cur ]; then unset PANGU_B200_LIB; else export PANGU_B200_LIB=$PWD/ab/libpangu_$v.so; fi
   for C in 192 384; do
-    PANGU_MLP_DBG=$dbg timeout 120 python - <<PY
+    timeout 120 python - <<PY
 import os, sys, torch
 sys.path.insert(0, "pangu-pytorch-demo_b200")
 from pangu_b200 import ops
@@ -19,7 +20,7 @@ for _ in range(10):
     big.zero_()                                   # flush L2
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); run(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
-ts.sort(); print("dbg=$dbg C=%d: median %.4f ms  min %.4f" % (C, ts[len(ts)//2], ts[0]))
+ts.sort(); print("lib=$v C=%d: median %.4f ms  min %.4f" % (C, ts[len(ts)//2], ts[0]))
 PY
   done
-done 2>&1 | grep dbg= | tee gpurun_out/exp_mlp_prefetch.log
+done 2>&1 | grep lib= | tee gpurun_out/exp_mlp.log
