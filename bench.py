@@ -38,7 +38,7 @@ FLOPS_TOTAL = 8.421e12            # algorithmic FLOPs of one forwar
 FLOPS_ATTN_MLP = 8.132e12         # attention + MLP blocks
 
 
-TRAFFIC_FILE = next((f for f in ("profiles/r2c_ncu_traffic.json", "profiles/r2b_ncu_traffic.json", "profiles/r2_ncu_traffic.json")
+TRAFFIC_FILE = next((f for f in ("profiles/r2d_ncu_traffic.json", "profiles/r2c_ncu_traffic.json", "profiles/r2b_ncu_traffic.json", "profiles/r2_ncu_traffic.json")
                      if os.path.exists(os.path.join(ROOT, f))), "profiles/r1_ncu_traffic.json")   # newest committed capture
 
 
